@@ -1,0 +1,285 @@
+"""ctypes face of libamplisolve_b200.so (include/amplisolve_b200.h).
+
+The function names mirror the reference code each one replaces:
+
+    Context.estimate_thresholds   estimateThresholds + the Germ_Max part of storeGermlineStatistics
+                                  (AmpliSolveErrorEstimation.cpp:1484-2544, :1247-1467)
+    Context.thresholds_caller_view  the "%f" -> std::stof hand-over (EE:1787 -> VC:889-890)
+    Context.call_variants         the row loop of callVariants (AmpliSolveVariantCalling.cpp:723-3296)
+    Context.mutation_rules_poisson_quality_score   VC:3834-3884, element-wise
+    Context.kf_gammaq             VC:3726, element-wise
+
+Host arrays are numpy, device arrays are torch CUDA tensors (torch is used for device memory and
+streams only).  There is no CPU fallback: without the built library or without a B200 every compute
+call raises AmpliSolveError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+ABSENT = 0xFFFFFFFF
+CALL_DTYPE = np.dtype([("sample", "<i4"), ("slot", "<i4"), ("alt", "<i4"), ("ref", "<i4"), ("p_fw", "<f8"),
+                       ("p_bw", "<f8"), ("q_fw", "<f8"), ("q_bw", "<f8")])
+assert CALL_DTYPE.itemsize == 48
+
+EXPORTS = [
+    "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
+    "as_set_call_kernel", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
+    "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host", "as_poisson_test_host",
+    "as_kf_gammaq_host", "as_synth_counts_dev", "as_hash_iteration_order", "as_error_estimation_main",
+    "as_variant_calling_main",
+]
+
+
+class AmpliSolveError(RuntimeError):
+    pass
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("mean_depth", C.c_float), ("depth_sigma", C.c_float),
+                ("germline_rate", C.c_float), ("somatic_rate", C.c_float), ("somatic_vaf_lo", C.c_float),
+                ("somatic_vaf_hi", C.c_float), ("absent_rate", C.c_float), ("sample_offset", C.c_int32),
+                ("slot_offset", C.c_int64)]
+
+
+_lib = None
+
+
+def lib_path() -> Path:
+    return Path(__file__).resolve().parent / "lib" / "libamplisolve_b200.so"
+
+
+def lib():
+    """Load (building first if the sources are newer) the shared library.  Never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from . import build as _build
+    try:
+        path = _build.build()
+    except Exception as exc:  # no nvcc (e.g. the GPU box): use the prebuilt library that travelled with the tree
+        path = lib_path()
+        if not path.exists():
+            raise AmpliSolveError(f"libamplisolve_b200.so is missing and cannot be built: {exc}") from exc
+    L = C.CDLL(str(path))
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    L.as_last_error.restype = C.c_char_p
+    L.as_version.restype = C.c_char_p
+    L.as_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.as_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.as_destroy.argtypes = [vp]
+    L.as_destroy.restype = None
+    L.as_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    L.as_host_free.argtypes = [vp]
+    L.as_set_call_kernel.argtypes = [vp, C.c_int]
+    L.as_kernel_launches.argtypes = [vp]
+    L.as_kernel_launches.restype = i64
+    L.as_noise_estimate_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
+    L.as_noise_estimate_host.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp]
+    L.as_thresholds_caller_view_dev.argtypes = [vp, vp, vp, i64, vp]
+    L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
+    L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.as_poisson_test_host.argtypes = [vp, vp, vp, vp, i64, vp, vp]
+    L.as_kf_gammaq_host.argtypes = [vp, vp, vp, i64, vp]
+    L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
+    L.as_hash_iteration_order.argtypes = [C.POINTER(C.c_char_p), i32, vp]
+    for name in ("as_error_estimation_main", "as_variant_calling_main"):
+        if hasattr(L, name):
+            getattr(L, name).argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+    _lib = L
+    return L
+
+
+def _check(rc: int, allow_overflow: bool = False) -> int:
+    if rc == 0 or (allow_overflow and rc == -5):
+        return rc
+    raise AmpliSolveError(f"amplisolve_b200 error {rc}: {lib().as_last_error().decode(errors='replace')}")
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _hp(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dp(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def hash_iteration_order(keys) -> list:
+    """Order in which libstdc++ iterates an unordered_map<string,string> filled with `keys`
+    (the reference's file order, EE:1081 / VC:672).  Host-only, needs no GPU."""
+    arr = (C.c_char_p * len(keys))(*[k.encode() for k in keys])
+    out = np.empty(max(1, len(keys)), dtype=np.int32)
+    n = lib().as_hash_iteration_order(arr, len(keys), _hp(out))
+    if n < 0:
+        raise AmpliSolveError("as_hash_iteration_order failed")
+    return [int(i) for i in out[:n]]
+
+
+def twin_links(pos_id) -> tuple[np.ndarray, np.ndarray]:
+    """twin_next / twin_head arrays from a slot -> unique-position map (slots in panel order)."""
+    pos_id = np.asarray(pos_id)
+    P = len(pos_id)
+    nxt = np.full(P, -1, dtype=np.int32)
+    head = np.arange(P, dtype=np.int32)
+    last: dict = {}
+    for p in range(P):
+        u = int(pos_id[p])
+        if u in last:
+            nxt[last[u]] = p
+            head[p] = head[last[u]]
+        last[u] = p
+    return nxt, head
+
+
+class Context:
+    """One per device (as_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        self.device = device
+        _check(lib().as_create(device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().as_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(lib().as_kernel_launches(self._h))
+
+    def set_call_kernel(self, variant: int):
+        _check(lib().as_set_call_kernel(self._h, variant))
+
+    # ---- host-buffer entry points --------------------------------------------------------------
+    def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None):
+        """counts: uint32 [S][2][P][4] host array, normals in the reference's file order."""
+        counts = _np(counts, np.uint32)
+        S, two, P, four = counts.shape
+        assert two == 2 and four == 4
+        out = {"thr": np.empty((P, 4, 2), np.float32), "germ_val": np.empty((P, 4), np.float32),
+               "germ_state": np.empty((P, 4), np.uint8), "count": np.empty((P, 4), np.uint32),
+               "nrec": np.empty(P, np.uint32)}
+        tn = th = None
+        if twin_next is not None:
+            tn, th = _np(twin_next, np.int32), _np(twin_head, np.int32)
+        _check(lib().as_noise_estimate_host(self._h, _hp(counts), S, P, None if tn is None else _hp(tn),
+                                            None if th is None else _hp(th), np.float32(c_value), int(coverage_cutoff),
+                                            _hp(out["thr"]), _hp(out["germ_val"]), _hp(out["germ_state"]),
+                                            _hp(out["count"]), _hp(out["nrec"])))
+        return out
+
+    def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None):
+        """counts: uint32 [T][2][P][4] host array.  Returns calls sorted by (sample, slot, alt)."""
+        counts = _np(counts, np.uint32)
+        T, two, P, four = counts.shape
+        assert two == 2 and four == 4
+        ref = _np(ref, np.uint8)
+        thr_view = _np(thr_view, np.float32)
+        assert ref.shape == (P,) and thr_view.shape == (P, 4, 2)
+        if cap is None:
+            cap = max(1024, T * P // 8)
+        calls = np.zeros(cap, dtype=CALL_DTYPE)
+        n = C.c_int64(0)
+        rc = lib().as_call_variants_host(self._h, _hp(counts), T, P, _hp(ref), _hp(thr_view), int(coverage_cutoff),
+                                         _hp(calls), cap, C.byref(n))
+        _check(rc, allow_overflow=True)
+        if rc == -5:
+            return self.call_variants(counts, ref, thr_view, coverage_cutoff, cap=int(n.value))
+        return calls[:n.value]
+
+    def mutation_rules_poisson_quality_score(self, k, rd, err):
+        k, rd, err = _np(k, np.int32), _np(rd, np.int32), _np(err, np.float32)
+        p, q = np.empty(k.shape, np.float64), np.empty(k.shape, np.float64)
+        _check(lib().as_poisson_test_host(self._h, _hp(k), _hp(rd), _hp(err), k.size, _hp(p), _hp(q)))
+        return p, q
+
+    def kf_gammaq(self, s, z):
+        s, z = _np(s, np.float64), _np(z, np.float64)
+        out = np.empty(s.shape, np.float64)
+        _check(lib().as_kf_gammaq_host(self._h, _hp(s), _hp(z), s.size, _hp(out)))
+        return out
+
+    # ---- device-resident entry points (torch CUDA tensors) -------------------------------------
+    @staticmethod
+    def _stream(stream=None):
+        import torch
+        return C.c_void_p((stream or torch.cuda.current_stream()).cuda_stream)
+
+    def alloc_noise_outputs(self, P):
+        import torch
+        dev = f"cuda:{self.device}"
+        return {"thr": torch.empty((P, 4, 2), dtype=torch.float32, device=dev),
+                "germ_val": torch.empty((P, 4), dtype=torch.float32, device=dev),
+                "germ_state": torch.empty((P, 4), dtype=torch.uint8, device=dev),
+                "count": torch.empty((P, 4), dtype=torch.int32, device=dev),
+                "nrec": torch.empty(P, dtype=torch.int32, device=dev)}
+
+    def estimate_thresholds_dev(self, counts, c_value, coverage_cutoff, out, twin_next=None, twin_head=None,
+                                slot_range=None, stream=None):
+        """counts: torch int32 CUDA tensor [S][2][P][4] (bit pattern of the uint32 counts)."""
+        S, two, P, four = counts.shape
+        b, e = slot_range if slot_range is not None else (0, P)
+        _check(lib().as_noise_estimate_dev(self._h, _dp(counts), S, P, b, e, _dp(twin_next), _dp(twin_head),
+                                           np.float32(c_value), int(coverage_cutoff), _dp(out["thr"]),
+                                           _dp(out["germ_val"]), _dp(out["germ_state"]), _dp(out["count"]),
+                                           _dp(out["nrec"]), self._stream(stream)))
+        return out
+
+    def thresholds_caller_view_dev(self, thr, view=None, stream=None):
+        import torch
+        if view is None:
+            view = torch.empty_like(thr)
+        _check(lib().as_thresholds_caller_view_dev(self._h, _dp(thr), _dp(view), thr.numel(), self._stream(stream)))
+        return view
+
+    def call_variants_dev(self, counts, ref, thr_view, coverage_cutoff, calls, n_calls, slot_range=None, stream=None):
+        """calls: torch uint8 CUDA tensor of cap*48 bytes; n_calls: torch int64 CUDA tensor [1] (added to)."""
+        T, two, P, four = counts.shape
+        b, e = slot_range if slot_range is not None else (0, P)
+        cap = calls.numel() * calls.element_size() // CALL_DTYPE.itemsize
+        _check(lib().as_call_variants_dev(self._h, _dp(counts), T, P, b, e, _dp(ref), _dp(thr_view),
+                                          int(coverage_cutoff), _dp(calls), cap, _dp(n_calls), self._stream(stream)))
+
+    def synth_counts_dev(self, n_samples, P, *, seed, mean_depth, somatic_rate=0.0, sample_offset=0, slot_offset=0,
+                         depth_sigma=0.5, germline_rate=1e-3, vaf=(0.01, 0.2), absent_rate=0.0, want_ref=True,
+                         stream=None):
+        """Synthetic panel generated in HBM.  Returns (counts int32 [n][2][P][4], ref uint8 [P])."""
+        import torch
+        dev = f"cuda:{self.device}"
+        counts = torch.empty((n_samples, 2, P, 4), dtype=torch.int32, device=dev)
+        ref = torch.empty(P, dtype=torch.uint8, device=dev) if want_ref else None
+        prm = SynthParams(seed, mean_depth, depth_sigma, germline_rate, somatic_rate, vaf[0], vaf[1], absent_rate,
+                          sample_offset, slot_offset)
+        _check(lib().as_synth_counts_dev(self._h, _dp(counts), n_samples, P, _dp(ref), C.byref(prm),
+                                         self._stream(stream)))
+        return counts, ref
+
+
+def calls_from_device(calls, n_calls) -> np.ndarray:
+    """Download a device call list and sort it into the reference's row order."""
+    n = int(n_calls.item())
+    cap = calls.numel() * calls.element_size() // CALL_DTYPE.itemsize
+    if n > cap:
+        raise AmpliSolveError(f"call list overflow: {n} calls, capacity {cap}")
+    raw = calls.view(-1)[: n * CALL_DTYPE.itemsize].cpu().numpy().view(CALL_DTYPE)
+    return np.sort(raw, order=["sample", "slot", "alt"])

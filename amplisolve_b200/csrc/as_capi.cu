@@ -1,0 +1,453 @@
+// C ABI of libamplisolve_b200.so: contexts, the _dev entry points (enqueue on the caller's stream) and
+// the _host entry points (slot-tiled, double-buffered H2D -> kernel -> D2H pipelines).
+// Interface contract and reference citations: include/amplisolve_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "as_kernels.h"
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return fail(AS_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                           \
+    } while (0)
+
+struct DevBuf {  // grow-only device scratch
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t need(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct as_ctx {
+    int device = 0;
+    int call_variant = 1;
+    int64_t launches = 0;
+    cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
+    DevBuf tile[2], out[2], aux[2], misc, calls;  // _host pipelines
+};
+
+extern "C" {
+
+const char* as_last_error(void) { return g_err; }
+const char* as_version(void) { return "amplisolve_b200 0.1 (sm_100a)"; }
+
+int as_device_count(int* n) {
+    if (!n) return fail(AS_EINVAL, "n is NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return fail(AS_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e)); }
+    *n = c;
+    return AS_OK;
+}
+
+int as_create(int device, as_ctx** out) {
+    if (!out) return fail(AS_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(AS_ECUDA, "no CUDA device available (%s): amplisolve_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= n) return fail(AS_EINVAL, "device %d out of range (0..%d)", device, n - 1);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(AS_ECUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    CU(cudaSetDevice(device));
+    as_ctx* c = new as_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->exec_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return AS_OK;
+}
+
+void as_destroy(as_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release();
+    for (int i = 0; i < 2; ++i) {
+        c->tile[i].release(); c->out[i].release(); c->aux[i].release();
+        if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
+    delete c;
+}
+
+int as_host_alloc(void** out, size_t bytes) {
+    if (!out) return fail(AS_EINVAL, "out is NULL");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return AS_OK;
+}
+int as_host_free(void* p) {
+    CU(cudaFreeHost(p));
+    return AS_OK;
+}
+
+int as_set_call_kernel(as_ctx* c, int variant) {
+    if (!c || variant < 0 || variant > 1) return fail(AS_EINVAL, "bad call kernel variant");
+    c->call_variant = variant;
+    return AS_OK;
+}
+int64_t as_kernel_launches(const as_ctx* c) { return c ? c->launches : 0; }
+
+static int check_common(as_ctx* c, const void* counts, int32_t n_samples, int64_t P, int64_t b, int64_t e, int32_t cut) {
+    if (!c) return fail(AS_EINVAL, "ctx is NULL");
+    if (!counts) return fail(AS_EINVAL, "counts is NULL");
+    if (((uintptr_t)counts & 15) != 0) return fail(AS_EINVAL, "counts must be 16-byte aligned");
+    if (n_samples < 0 || P < 0) return fail(AS_EINVAL, "negative extent");
+    if (P > 0x7fffffffll) return fail(AS_EINVAL, "at most 2^31-1 slots per call (shard the panel)");
+    if (b < 0 || e > P || b > e) return fail(AS_EINVAL, "bad slot range [%lld,%lld) of %lld", (long long)b, (long long)e, (long long)P);
+    if (cut < 1) return fail(AS_EINVAL, "coverage cutoff must be >= 1 (the programs map <= 0 to 100, EE:383, VC:277)");
+    return AS_OK;
+}
+
+// ---- noise -----------------------------------------------------------------------------------------
+int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_t P, int64_t b, int64_t e,
+                          const int32_t* d_twin_next, const int32_t* d_twin_head, float C, int32_t cut, float* d_thr,
+                          float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, void* stream) {
+    int rc = check_common(c, d_counts, S, P, b, e, cut);
+    if (rc) return rc;
+    if (!d_thr || !d_germ_val || !d_germ_state || !d_count || !d_nrec) return fail(AS_EINVAL, "output pointer is NULL");
+    if ((d_twin_next == nullptr) != (d_twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CU(as_launch_noise_main(d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
+                            d_germ_state, d_count, d_nrec, st));
+    c->launches += 1;
+    if (d_twin_next) {
+        CU(c->heads.need(sizeof(int32_t) * (size_t)std::max<int64_t>(1, (e - b + 1) / 2 + 1)));
+        CU(c->nheads.need(sizeof(uint32_t)));
+        CU(as_launch_noise_twins(d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
+                                 (uint32_t*)c->nheads.p, C, (uint32_t)cut, d_thr, d_germ_val, d_germ_state, d_count,
+                                 d_nrec, st));
+        c->launches += 2;
+    }
+    return AS_OK;
+}
+
+int as_thresholds_caller_view_dev(as_ctx* c, const float* d_thr, float* d_view, int64_t n, void* stream) {
+    if (!c || !d_thr || !d_view || n < 0) return fail(AS_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(as_launch_thr_view(d_thr, d_view, n, (cudaStream_t)stream));
+    c->launches += 1;
+    return AS_OK;
+}
+
+// Slots per tile of the _host pipelines: ~256 MiB of counts per buffer, multiple of 1024 slots.
+static int64_t tile_slots(int32_t n_samples, int64_t P) {
+    const int64_t per_slot = 32ll * std::max(1, n_samples);
+    int64_t t = (256ll << 20) / per_slot;
+    t = std::max<int64_t>(1024, (t / 1024) * 1024);
+    return std::min(t, std::max<int64_t>(P, 1));
+}
+
+// upload slots [p0, p0+n) of a host tensor [n_samples][2][P][4] into a packed device tile [n_samples][2][n][4]
+static cudaError_t upload_tile(void* d_tile, const uint32_t* counts, int32_t n_samples, int64_t P, int64_t p0, int64_t n,
+                               cudaStream_t st) {
+    return cudaMemcpy2DAsync(d_tile, (size_t)n * 16, counts + p0 * 4, (size_t)P * 16, (size_t)n * 16,
+                             (size_t)n_samples * 2, cudaMemcpyHostToDevice, st);
+}
+
+struct NoiseOutLayout {  // one device block per tile: thr | germ_val | count | nrec | germ_state
+    size_t thr, germ_val, count, nrec, germ_state, total;
+    explicit NoiseOutLayout(int64_t n) {
+        thr = 0;
+        germ_val = thr + (size_t)n * 32;
+        count = germ_val + (size_t)n * 16;
+        nrec = count + (size_t)n * 16;
+        germ_state = nrec + (size_t)n * 4;
+        total = germ_state + (size_t)n * 4;
+    }
+};
+
+int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
+                           const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
+                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec) {
+    int rc = check_common(c, counts, S, P, 0, P, cut);
+    if (rc) return rc;
+    if (!thr || !germ_val || !germ_state || !count || !nrec) return fail(AS_EINVAL, "output pointer is NULL");
+    if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
+    if (P == 0) return AS_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t TP = tile_slots(S, P);
+    const NoiseOutLayout lay(TP);
+    for (int i = 0; i < 2; ++i) {
+        CU(c->tile[i].need((size_t)TP * 32 * (size_t)std::max(1, S)));
+        CU(c->out[i].need(lay.total));
+        if (twin_next) CU(c->aux[i].need((size_t)TP * 8));
+    }
+    // pass 1: singleton slots, tile by tile (copy of tile i+1 overlaps the kernel of tile i)
+    int64_t ntiles = (P + TP - 1) / TP;
+    for (int64_t t = 0; t < ntiles; ++t) {
+        const int bsel = (int)(t & 1);
+        const int64_t p0 = t * TP, n = std::min(TP, P - p0);
+        if (t >= 2) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));  // buffer free again
+        CU(upload_tile(c->tile[bsel].p, counts, S, P, p0, n, c->copy_stream));
+        int32_t *d_tn = nullptr, *d_th = nullptr;
+        if (twin_next) {
+            d_tn = (int32_t*)c->aux[bsel].p;
+            d_th = d_tn + TP;
+            CU(cudaMemcpyAsync(d_tn, twin_next + p0, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaMemcpyAsync(d_th, twin_head + p0, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        CU(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
+        CU(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
+        char* o = (char*)c->out[bsel].p;
+        if (twin_next) CU(cudaMemsetAsync(o, 0, lay.total, c->exec_stream));  // twin members are filled in pass 2
+        CU(as_launch_noise_main((const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th, p0, C, (uint32_t)cut,
+                                (float*)(o + lay.thr), (float*)(o + lay.germ_val), (uint8_t*)(o + lay.germ_state),
+                                (uint32_t*)(o + lay.count), (uint32_t*)(o + lay.nrec), c->exec_stream));
+        c->launches += 1;
+        CU(cudaMemcpyAsync(thr + p0 * 8, o + lay.thr, (size_t)n * 32, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaMemcpyAsync(germ_val + p0 * 4, o + lay.germ_val, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaMemcpyAsync(count + p0 * 4, o + lay.count, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaMemcpyAsync(nrec + p0, o + lay.nrec, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaMemcpyAsync(germ_state + p0 * 4, o + lay.germ_state, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
+    }
+    CU(cudaStreamSynchronize(c->exec_stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    if (!twin_next) return AS_OK;
+
+    // pass 2: twin groups.  Their member slots may lie in different tiles, so the records of all members
+    // are gathered (pure data movement) into one compact tensor [S][2][M][4] with compact twin links.
+    std::vector<int32_t> members;  // compact id -> panel slot
+    std::vector<int32_t> c_next, c_head;
+    for (int64_t p = 0; p < P; ++p) {
+        if (twin_head[p] == (int32_t)p && twin_next[p] >= 0) {
+            const int32_t head_c = (int32_t)members.size();
+            for (int32_t q = (int32_t)p; q >= 0; q = twin_next[q]) {
+                if (q >= P) return fail(AS_EINVAL, "twin_next[%d] out of range", q);
+                members.push_back(q);
+                c_head.push_back(head_c);
+                c_next.push_back(twin_next[q] >= 0 ? (int32_t)members.size() : -1);
+                if ((int64_t)members.size() > P) return fail(AS_EINVAL, "twin_next contains a cycle");
+            }
+        }
+    }
+    const int64_t M = (int64_t)members.size();
+    if (M == 0) return AS_OK;
+    uint32_t* h_gather = nullptr;
+    CU(cudaHostAlloc((void**)&h_gather, (size_t)M * 32 * (size_t)std::max(1, S), cudaHostAllocDefault));
+    for (int64_t row = 0; row < (int64_t)S * 2; ++row) {
+        const uint32_t* src = counts + row * P * 4;
+        uint32_t* dst = h_gather + row * M * 4;
+        for (int64_t m = 0; m < M; ++m) memcpy(dst + m * 4, src + (int64_t)members[m] * 4, 16);
+    }
+    const NoiseOutLayout ml(M);
+    DevBuf d_cnt, d_out, d_links;
+    cudaError_t e1 = d_cnt.need((size_t)M * 32 * (size_t)std::max(1, S));
+    cudaError_t e2 = d_out.need(ml.total);
+    cudaError_t e3 = d_links.need((size_t)M * 12 + 16);
+    std::vector<char> h_out(ml.total);
+    int ret = AS_OK;
+    do {
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { ret = fail(AS_ENOMEM, "cudaMalloc failed for the twin tensor"); break; }
+        int32_t* d_next = (int32_t*)d_links.p;
+        int32_t* d_head = d_next + M;
+        int32_t* d_heads = d_head + M;
+        cudaStream_t st = c->exec_stream;
+#define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
+        CUB(c->nheads.need(sizeof(uint32_t)));
+        CUB(cudaMemcpyAsync(d_cnt.p, h_gather, (size_t)M * 32 * (size_t)S, cudaMemcpyHostToDevice, st));
+        CUB(cudaMemcpyAsync(d_next, c_next.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        CUB(cudaMemcpyAsync(d_head, c_head.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
+        char* o = (char*)d_out.p;
+        CUB(as_launch_noise_twins((const uint32_t*)d_cnt.p, S, M, 0, M, d_next, d_head, d_heads, (uint32_t*)c->nheads.p, C,
+                                  (uint32_t)cut, (float*)(o + ml.thr), (float*)(o + ml.germ_val),
+                                  (uint8_t*)(o + ml.germ_state), (uint32_t*)(o + ml.count), (uint32_t*)(o + ml.nrec), st));
+        c->launches += 2;
+        CUB(cudaMemcpyAsync(h_out.data(), o, ml.total, cudaMemcpyDeviceToHost, st));
+        CUB(cudaStreamSynchronize(st));
+#undef CUB
+        for (int64_t m = 0; m < M; ++m) {
+            const int64_t p = members[m];
+            memcpy(thr + p * 8, h_out.data() + ml.thr + m * 32, 32);
+            memcpy(germ_val + p * 4, h_out.data() + ml.germ_val + m * 16, 16);
+            memcpy(count + p * 4, h_out.data() + ml.count + m * 16, 16);
+            memcpy(nrec + p, h_out.data() + ml.nrec + m * 4, 4);
+            memcpy(germ_state + p * 4, h_out.data() + ml.germ_state + m * 4, 4);
+        }
+    } while (0);
+    d_cnt.release(); d_out.release(); d_links.release();
+    cudaFreeHost(h_gather);
+    return ret;
+}
+
+// ---- caller ----------------------------------------------------------------------------------------
+int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t P, int64_t b, int64_t e,
+                         const uint8_t* d_ref, const float* d_thr_view, int32_t cut, as_call* d_calls, int64_t cap,
+                         unsigned long long* d_n_calls, void* stream) {
+    int rc = check_common(c, d_counts, T, P, b, e, cut);
+    if (rc) return rc;
+    if (!d_ref || !d_thr_view || !d_n_calls || (!d_calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
+    if (T >= (1 << 30)) return fail(AS_EINVAL, "at most 2^30-1 samples per call");
+    CU(cudaSetDevice(c->device));
+    CU(as_launch_call(c->call_variant, d_counts, T, P, b, e, d_ref, d_thr_view, (uint32_t)cut, d_calls, cap, d_n_calls,
+                      (cudaStream_t)stream));
+    c->launches += 1;
+    return AS_OK;
+}
+
+int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
+                          const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
+    int rc = check_common(c, counts, T, P, 0, P, cut);
+    if (rc) return rc;
+    if (!ref || !thr_view || !n_calls || (!calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
+    *n_calls = 0;
+    if (P == 0 || T == 0) return AS_OK;
+    CU(cudaSetDevice(c->device));
+    const int64_t TP = tile_slots(T, P);
+    for (int i = 0; i < 2; ++i) {
+        CU(c->tile[i].need((size_t)TP * 32 * (size_t)T));
+        CU(c->aux[i].need((size_t)TP * 36));  // thr_view (32 B/slot) + ref (1 B/slot, padded)
+    }
+    CU(c->calls.need(sizeof(as_call) * (size_t)std::max<int64_t>(cap, 1)));
+    CU(c->misc.need(16));
+    unsigned long long* d_n = (unsigned long long*)c->misc.p;
+    CU(cudaMemsetAsync(d_n, 0, 8, c->exec_stream));
+    const int64_t ntiles = (P + TP - 1) / TP;
+    // the tile kernels emit tile-local slot ids; the offsets are fixed up after the download
+    unsigned long long* h_n = nullptr;
+    CU(cudaHostAlloc((void**)&h_n, sizeof(unsigned long long) * (size_t)ntiles, cudaHostAllocDefault));
+    int ret = AS_OK;
+    for (int64_t t = 0; t < ntiles && ret == AS_OK; ++t) {
+        const int bsel = (int)(t & 1);
+        const int64_t p0 = t * TP, n = std::min(TP, P - p0);
+#define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
+        if (t >= 2) CUB(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));
+        CUB(upload_tile(c->tile[bsel].p, counts, T, P, p0, n, c->copy_stream));
+        float* d_tv = (float*)c->aux[bsel].p;
+        uint8_t* d_rf = (uint8_t*)c->aux[bsel].p + (size_t)TP * 32;
+        CUB(cudaMemcpyAsync(d_tv, thr_view + p0 * 8, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
+        CUB(cudaMemcpyAsync(d_rf, ref + p0, (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
+        CUB(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
+        CUB(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
+        CUB(as_launch_call(c->call_variant, (const uint32_t*)c->tile[bsel].p, T, n, 0, n, d_rf, d_tv, (uint32_t)cut,
+                           (as_call*)c->calls.p, cap, d_n, c->exec_stream));
+        c->launches += 1;
+        CUB(cudaMemcpyAsync(h_n + t, d_n, 8, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUB(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
+#undef CUB
+    }
+    if (ret == AS_OK) {
+        cudaError_t e1 = cudaStreamSynchronize(c->exec_stream), e2 = cudaStreamSynchronize(c->copy_stream);
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+            ret = fail(AS_ECUDA, "caller pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    if (ret == AS_OK) {
+        const unsigned long long total = h_n[ntiles - 1];
+        *n_calls = (int64_t)total;
+        const int64_t have = std::min<int64_t>((int64_t)total, cap);
+        if (have > 0) {
+            cudaError_t e = cudaMemcpy(calls, c->calls.p, sizeof(as_call) * (size_t)have, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) ret = fail(AS_ECUDA, "download of calls failed: %s", cudaGetErrorString(e));
+        }
+        if (ret == AS_OK) {
+            // calls of tile t occupy list positions [h_n[t-1], h_n[t]) because tiles run in stream order
+            int64_t lo = 0;
+            for (int64_t t = 0; t < ntiles; ++t) {
+                const int64_t hi = std::min<int64_t>((int64_t)h_n[t], have);
+                for (int64_t i = lo; i < hi; ++i) calls[i].slot += (int32_t)(t * TP);
+                lo = std::max(lo, hi);
+            }
+            std::sort(calls, calls + have, [](const as_call& a, const as_call& b) {
+                if (a.sample != b.sample) return a.sample < b.sample;
+                if (a.slot != b.slot) return a.slot < b.slot;
+                return a.alt < b.alt;
+            });
+            if ((int64_t)total > cap) ret = fail(AS_EOVERFLOW, "%llu calls found, capacity %lld", total, (long long)cap);
+        }
+    }
+    cudaFreeHost(h_n);
+    return ret;
+}
+
+// ---- element-wise evaluators -----------------------------------------------------------------------
+int as_poisson_test_host(as_ctx* c, const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
+                         double* q) {
+    if (!c || !k || !rd || !err || !p || !q || n < 0) return fail(AS_EINVAL, "bad argument");
+    if (n == 0) return AS_OK;
+    CU(cudaSetDevice(c->device));
+    CU(c->misc.need((size_t)n * 28 + 64));
+    char* base = (char*)c->misc.p;
+    double* d_p = (double*)base;
+    double* d_q = d_p + n;
+    int32_t* d_k = (int32_t*)(d_q + n);
+    int32_t* d_rd = d_k + n;
+    float* d_err = (float*)(d_rd + n);
+    cudaStream_t st = c->exec_stream;
+    CU(cudaMemcpyAsync(d_k, k, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_rd, rd, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_err, err, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU(as_launch_poisson_test(d_k, d_rd, d_err, n, d_p, d_q, st));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(p, d_p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(q, d_q, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AS_OK;
+}
+
+int as_kf_gammaq_host(as_ctx* c, const double* s, const double* z, int64_t n, double* out) {
+    if (!c || !s || !z || !out || n < 0) return fail(AS_EINVAL, "bad argument");
+    if (n == 0) return AS_OK;
+    CU(cudaSetDevice(c->device));
+    CU(c->misc.need((size_t)n * 24));
+    double* d_s = (double*)c->misc.p;
+    double* d_z = d_s + n;
+    double* d_o = d_z + n;
+    cudaStream_t st = c->exec_stream;
+    CU(cudaMemcpyAsync(d_s, s, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_z, z, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    CU(as_launch_gammaq(d_s, d_z, n, d_o, st));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(out, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return AS_OK;
+}
+
+int as_synth_counts_dev(as_ctx* c, uint32_t* d_counts, int32_t n_samples, int64_t P, uint8_t* d_ref,
+                        const as_synth_params* prm, void* stream) {
+    if (!c || !d_counts || !prm || n_samples < 0 || P < 0) return fail(AS_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(as_launch_synth(d_counts, n_samples, P, d_ref, prm, (cudaStream_t)stream));
+    c->launches += 1;
+    return AS_OK;
+}
+
+}  // extern "C"

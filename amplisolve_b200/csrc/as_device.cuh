@@ -1,0 +1,148 @@
+// Device-side arithmetic of the AmpliSolve hot path, written for sm_100a.
+//
+// Everything here must be decision-identical to the reference's arithmetic:
+//   kfunc incomplete gamma      VC:3720-3830  (VC = source_codes/AmpliSolveVariantCalling.cpp)
+//   Poisson Q score             VC:3834-3884
+// The reference runs on x86-64 SSE2 without FMA, so every fp64 operation below is issued through
+// the round-to-nearest intrinsics (__dadd_rn/__dmul_rn/__ddiv_rn), which nvcc never contracts
+// into FMAs; the translation unit is additionally compiled with -fmad=false.  The only
+// operations that are not bit-identical by construction are exp/log/log10 (CUDA libdevice vs
+// glibc, both < 1 ulp): see DESIGN.md "p-value tolerance".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asdev {
+
+#define AS_KF_EPS 1e-14   /* VC:149 */
+#define AS_KF_TINY 1e-290 /* VC:150 */
+
+// Lanczos-style log-gamma of kfunc (VC:3817-3830), same operation order.
+__device__ __forceinline__ double kf_lgamma(double z) {
+    double x = 0.0;
+    x = __dadd_rn(x, __ddiv_rn(0.1659470187408462e-06, __dadd_rn(z, 7.0)));
+    x = __dadd_rn(x, __ddiv_rn(0.9934937113930748e-05, __dadd_rn(z, 6.0)));
+    x = __dsub_rn(x, __ddiv_rn(0.1385710331296526, __dadd_rn(z, 5.0)));
+    x = __dadd_rn(x, __ddiv_rn(12.50734324009056, __dadd_rn(z, 4.0)));
+    x = __dsub_rn(x, __ddiv_rn(176.6150291498386, __dadd_rn(z, 3.0)));
+    x = __dadd_rn(x, __ddiv_rn(771.3234287757674, __dadd_rn(z, 2.0)));
+    x = __dsub_rn(x, __ddiv_rn(1259.139216722289, __dadd_rn(z, 1.0)));
+    x = __dadd_rn(x, __ddiv_rn(676.5203681218835, z));
+    x = __dadd_rn(x, 0.9999999999995183);
+    // log(x) - 5.58106146679532777 - z + (z-0.5)*log(z+6.5), left to right
+    double t = __dsub_rn(__dsub_rn(log(x), 5.58106146679532777), z);
+    return __dadd_rn(t, __dmul_rn(__dsub_rn(z, 0.5), log(__dadd_rn(z, 6.5))));
+}
+
+// Lower regularised gamma by series, capped at 99 terms exactly like VC:3785-3794 (the cap is
+// part of the semantics: for s >~ 150 and z >~ 0.9 s the series is NOT converged when it stops).
+__device__ __forceinline__ double kf_lower_series(double s, double z) {
+    double sum = 1.0, x = 1.0;
+#pragma unroll 1
+    for (int k = 1; k < 100; ++k) {
+        x = __dmul_rn(x, __ddiv_rn(z, __dadd_rn(s, (double)k)));
+        sum = __dadd_rn(sum, x);
+        if (__ddiv_rn(x, sum) < AS_KF_EPS) break;
+    }
+    // exp(s*log(z) - z - kf_lgamma(s+1) + log(sum))
+    double e = __dsub_rn(__dmul_rn(s, log(z)), z);
+    e = __dsub_rn(e, kf_lgamma(__dadd_rn(s, 1.0)));
+    e = __dadd_rn(e, log(sum));
+    return exp(e);
+}
+
+// Upper regularised gamma by modified Lentz, capped at 99 steps exactly like VC:3733-3752.
+__device__ __forceinline__ double kf_upper_cf(double s, double z) {
+    double f = __dsub_rn(__dadd_rn(1.0, z), s);
+    double C = f, D = 0.0;
+#pragma unroll 1
+    for (int j = 1; j < 100; ++j) {
+        double a = __dmul_rn((double)j, __dsub_rn(s, (double)j));
+        double b = __dsub_rn(__dadd_rn((double)((j << 1) + 1), z), s);
+        D = __dadd_rn(b, __dmul_rn(a, D));
+        if (D < AS_KF_TINY) D = AS_KF_TINY;
+        C = __dadd_rn(b, __ddiv_rn(a, C));
+        if (C < AS_KF_TINY) C = AS_KF_TINY;
+        D = __ddiv_rn(1.0, D);
+        double d = __dmul_rn(C, D);
+        f = __dmul_rn(f, d);
+        if (fabs(__dsub_rn(d, 1.0)) < AS_KF_EPS) break;
+    }
+    // exp(s*log(z) - z - kf_lgamma(s) - log(f))
+    double e = __dsub_rn(__dmul_rn(s, log(z)), z);
+    e = __dsub_rn(e, kf_lgamma(s));
+    e = __dsub_rn(e, log(f));
+    return exp(e);
+}
+
+__device__ __forceinline__ bool kf_uses_cf(double s, double z) { return !(z <= 1.0 || z < s); }
+
+__device__ __forceinline__ double kf_gammaq(double s, double z) { /* VC:3726-3729 */
+    return kf_uses_cf(s, z) ? kf_upper_cf(s, z) : __dsub_rn(1.0, kf_lower_series(s, z));
+}
+
+// err as the caller holds it (float).  VC:3852-3856: a zero error rate becomes 0.0010008f.
+__device__ __forceinline__ float effective_err(float err) { return err == 0.0f ? 0.0010008f : err; }
+
+// The double p-value of VC:3858-3866 (k == 0 -> 1).  err must not be -1 (caller handles that).
+__device__ __forceinline__ double poisson_p(int k, int rd, float err) {
+    if (k == 0) return 1.0;
+    double m = __dmul_rn((double)rd, (double)effective_err(err)); /* VC:3864 */
+    return __dsub_rn(1.0, kf_gammaq((double)k, m));
+}
+
+// Q of VC:3868-3882 in fp64.  Reported for information; the DECISION never uses it (see q_at_least_5).
+__device__ __forceinline__ double q_from_p(double p) {
+    if (p < 1e-10) return 100.0; /* -10*log10l(1e-10) rounds to 100 in double */
+    if (p == 1.0) return 0.0;
+    return __dmul_rn(-10.0, log10(p));
+}
+
+// The reference compares the x87 long double Q = -10*log10l(p) with 5 (VC:898).  As a predicate on the
+// double p that is a threshold: Q >= 5 <=> p <= AS_P_STAR, where AS_P_STAR = 0x3FD43D136248490E is the
+// largest double for which glibc's x87 evaluation gives Q >= 5 (found by bisection over the doubles,
+// tests/test_oracle_vs_ref.py pins it against the compiled reference; plain fp64 log10 would accept one
+// more double).  p < 1e-10 gives Q = 100, NaN gives NaN >= 5 = false.
+#define AS_P_STAR_BITS 0x3FD43D136248490Eull
+__device__ __forceinline__ bool q_at_least_5(double p) { return p <= __longlong_as_double(AS_P_STAR_BITS); }
+
+// The "%f" -> std::stof round trip of a threshold (EE:1787 -> VC:889-890) without text:
+// v*1e6 is exact in fp64 for any float32 v (24+20 significant bits), so rint() is printf's
+// round-half-even on the exact value; n/1e6 rounded to double and then to float equals strtof's
+// correctly rounded result because n/1e6 is never within 2^-53 relative of a float midpoint
+// (the gap is >= 1/(15625*2^25)).  "-1_-1" (NaN here) is written as 0.01_0.01.
+__device__ __forceinline__ float thr_caller_view(float v) {
+    if (isnan(v)) return 0.01f;
+    double n = rint(__dmul_rn((double)v, 1e6));
+    return __double2float_rn(__ddiv_rn(n, 1e6));
+}
+
+// ---- counter-based RNG for the synthetic generator (not on the parity path) -------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ uint64_t key4(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    return mix64(seed ^ mix64(a + 0x9e3779b97f4a7c15ull * (b + 1)) ^ (c * 0xd1b54a32d192ed03ull));
+}
+__device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float gauss(uint64_t h) {
+    float u1 = u01(h), u2 = u01(mix64(h ^ 0x5851f42d4c957f2dull));
+    return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2);
+}
+// Poisson(mean) sample: inversion for small means, rounded normal otherwise.
+__device__ __forceinline__ uint32_t poisson_sample(float mean, uint64_t h) {
+    if (mean <= 0.0f) return 0;
+    if (mean < 24.0f) {
+        float u = u01(h), p = __expf(-mean), c = p;
+        uint32_t k = 0;
+        while (u > c && k < 200) { ++k; p *= mean / k; c += p; }
+        return k;
+    }
+    float v = mean + sqrtf(mean) * gauss(h) + 0.5f;
+    return v < 0.0f ? 0u : (uint32_t)v;
+}
+
+}  // namespace asdev

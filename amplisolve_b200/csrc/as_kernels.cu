@@ -1,0 +1,546 @@
+// CUDA kernels of the AmpliSolve hot path for sm_100a, and their launchers.
+//
+//   EE = source_codes/AmpliSolveErrorEstimation.cpp, VC = source_codes/AmpliSolveVariantCalling.cpp
+//
+// Both kernels are scans over a dense count tensor uint32 [sample][strand][slot][base]: one 16-byte
+// word per (sample, strand, slot), so a warp covering 32 consecutive slots reads 512 contiguous bytes
+// per (sample, strand) with one LDG.128 per lane.  Nothing here is a dense contraction: no tensor
+// cores.  The bound is HBM (32 algorithmic bytes per record); the instruction budget at the roofline
+// is ~150 issue slots per record, which is why the filter arithmetic is division-free (as_noise.cuh)
+// and why the caller screens records with integer tests and only evaluates the fp64 incomplete-gamma
+// series for the rare survivors, compacted through per-warp shared-memory queues so that the fp64
+// loops run on full warps.
+#include "as_kernels.h"
+
+#include "as_device.cuh"
+#include "as_noise.cuh"
+
+namespace asdev {
+
+// 128-bit streaming load: read-only path, do not allocate in L1 (every record is read exactly once).
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise model, singleton slots: one thread per slot, all normals in sequence
+// ------------------------------------------------------------------------------------------------
+template <int UNROLL>
+__global__ void __launch_bounds__(AS_NOISE_THREADS)
+noise_main_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t p0, int64_t p1,
+                  const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head, int64_t twin_base,
+                  float C, uint32_t cut, float* __restrict__ thr, float* __restrict__ germ_val,
+                  uint8_t* __restrict__ germ_state, uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
+    const int64_t p = p0 + (int64_t)blockIdx.x * AS_NOISE_THREADS + threadIdx.x;
+    if (p >= p1) return;
+    // members of a twin group (position enumerated by overlapping amplicons) are done by noise_twin_kernel;
+    // twin_head holds panel-global slot ids, p + twin_base is this slot's
+    if (twin_next != nullptr && (twin_next[p] >= 0 || twin_head[p] != (int32_t)(p + twin_base))) return;
+
+    NoiseAcc acc;
+    noise_init(acc);
+    const uint4* q = counts + p;
+    const int64_t sstride = 2 * P;  // uint4 words per sample
+    int s = 0;
+    for (; s + UNROLL <= S; s += UNROLL) {
+        uint4 fw[UNROLL], bw[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            fw[u] = ld_stream(q + (int64_t)(s + u) * sstride);
+            bw[u] = ld_stream(q + (int64_t)(s + u) * sstride + P);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) noise_accumulate<false>(acc, fw[u], bw[u], C, cut);
+    }
+    for (; s < S; ++s) {
+        const uint4 fw = ld_stream(q + (int64_t)s * sstride);
+        const uint4 bw = ld_stream(q + (int64_t)s * sstride + P);
+        noise_accumulate<false>(acc, fw, bw, C, cut);
+    }
+    noise_store(acc, p, thr, germ_val, germ_state, count, nrec);
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise model, twin groups: the reference keys records by "chrom_pos" text, so every row of every
+// slot of a duplicated position feeds ONE estimate (EE:1241-1245), in the order file, then row.
+// ------------------------------------------------------------------------------------------------
+__global__ void twin_heads_kernel(const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head,
+                                  int64_t p0, int64_t p1, int32_t* __restrict__ heads, uint32_t* __restrict__ n_heads) {
+    const int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= p1) return;
+    if (twin_head[p] == (int32_t)p && twin_next[p] >= 0) heads[atomicAdd(n_heads, 1u)] = (int32_t)p;
+}
+
+__device__ __forceinline__ uint32_t shfl_down_u32(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ unsigned long long shfl_down_u64(unsigned long long v, int d) {
+    return __shfl_down_sync(0xffffffffu, v, d);
+}
+__device__ __forceinline__ double shfl_down_f64(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ void noise_shfl_down(NoiseAcc& r, const NoiseAcc& a, int d) {
+    r.nrec = shfl_down_u32(a.nrec, d);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        r.b[i].s_b_fw = shfl_down_u64(a.b[i].s_b_fw, d); r.b[i].s_b_bw = shfl_down_u64(a.b[i].s_b_bw, d);
+        r.b[i].s_d_fw = shfl_down_u64(a.b[i].s_d_fw, d); r.b[i].s_d_bw = shfl_down_u64(a.b[i].s_d_bw, d);
+        r.b[i].s_p_fw = shfl_down_f64(a.b[i].s_p_fw, d); r.b[i].s_p_bw = shfl_down_f64(a.b[i].s_p_bw, d);
+        r.b[i].count = shfl_down_u32(a.b[i].count, d);
+        r.b[i].g_n = shfl_down_u32(a.b[i].g_n, d);
+        r.b[i].g_first_x = shfl_down_u32(a.b[i].g_first_x, d); r.b[i].g_first_rd = shfl_down_u32(a.b[i].g_first_rd, d);
+        r.b[i].g_x = shfl_down_u32(a.b[i].g_x, d); r.b[i].g_rd = shfl_down_u32(a.b[i].g_rd, d);
+    }
+}
+
+// One warp per group.  Lane l takes the contiguous sample range [l*per, (l+1)*per); the partial states
+// are merged in lane order by an order-preserving tree, which keeps the Germ_Max "first qualifying
+// record is dropped" semantics (EE:1258-1262) exact.
+__global__ void __launch_bounds__(128)
+noise_twin_kernel(const uint4* __restrict__ counts, int S, int64_t P, const int32_t* __restrict__ twin_next,
+                  const int32_t* __restrict__ heads, const uint32_t* __restrict__ n_heads, float C, uint32_t cut,
+                  float* __restrict__ thr, float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
+                  uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n = *n_heads;
+    const int per = (S + 31) / 32;
+    const int64_t sstride = 2 * P;
+    for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n; g += warps) {
+        const int32_t head = heads[g];
+        NoiseAcc acc;
+        noise_init(acc);
+        const int s_lo = lane * per, s_hi = min(S, s_lo + per);
+        for (int s = s_lo; s < s_hi; ++s) {
+            for (int32_t t = head; t >= 0; t = twin_next[t]) {  // rows of one file: slot order = file order
+                const uint4 fw = ld_stream(counts + (int64_t)s * sstride + t);
+                const uint4 bw = ld_stream(counts + (int64_t)s * sstride + P + t);
+                noise_accumulate<true>(acc, fw, bw, C, cut);
+            }
+        }
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            NoiseAcc other;
+            noise_shfl_down(other, acc, d);
+            if ((lane & (2 * d - 1)) == 0) noise_merge(acc, other);
+        }
+        if (lane == 0)
+            for (int32_t t = head; t >= 0; t = twin_next[t]) noise_store(acc, t, thr, germ_val, germ_state, count, nrec);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// thresholds as the caller sees them (EE:1787 "%f" text -> VC:889-890 std::stof)
+// ------------------------------------------------------------------------------------------------
+__global__ void thr_view_kernel(const float* __restrict__ thr, float* __restrict__ view, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) view[i] = thr_caller_view(thr[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// caller
+// ------------------------------------------------------------------------------------------------
+struct CallSlotConst {
+    float e[8];    // thresholds of the slot as the caller parsed them: [base][fw,bw]
+    uint32_t ref;  // 0..3, > 3 = not callable (VC:3290-3293)
+};
+
+__device__ __forceinline__ void load_slot_const(CallSlotConst& c, const float* __restrict__ thr_view,
+                                                const uint8_t* __restrict__ ref, int64_t p) {
+    const float4 a = *reinterpret_cast<const float4*>(thr_view + p * 8);
+    const float4 b = *reinterpret_cast<const float4*>(thr_view + p * 8 + 4);
+    c.e[0] = a.x; c.e[1] = a.y; c.e[2] = a.z; c.e[3] = a.w;
+    c.e[4] = b.x; c.e[5] = b.y; c.e[6] = b.z; c.e[7] = b.w;
+    c.ref = ref[p];
+}
+
+// exact screen of SURVEY.md B.6(3): on the continued-fraction branch of VC:3728 (m >= k and m > 1) the
+// reference's Q never reaches 5 (p = P(X >= k) >= 1/2 for a Poisson mean m >= k; validated against the
+// compiled reference including the region where its 99-step cap leaves the fraction unconverged,
+// tests/test_screens.py), so such a strand test can only veto the call.
+__device__ __forceinline__ bool strand_can_pass(uint32_t k, uint32_t depth, float err) {
+    if (err == -1.0f) return false;  // VC:3844-3849: Q = -888
+    const double m = __dmul_rn((double)depth, (double)effective_err(err));
+    return !(m >= (double)k && m > 1.0);
+}
+
+__device__ __forceinline__ void emit_call(as_call* __restrict__ calls, unsigned long long* __restrict__ n_calls,
+                                          int64_t cap, bool is_call, int32_t sample, int32_t slot, int32_t alt,
+                                          int32_t ref, double p_fw, double p_bw) {
+    const unsigned active = __activemask();
+    const unsigned votes = __ballot_sync(active, is_call);
+    if (votes == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(votes) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_calls, (unsigned long long)__popc(votes));
+    base = __shfl_sync(active, base, leader);
+    if (is_call) {
+        const unsigned long long idx = base + __popc(votes & ((1u << lane) - 1u));
+        if ((int64_t)idx < cap) {
+            as_call c;
+            c.sample = sample; c.slot = slot; c.alt = alt; c.ref = ref;
+            c.p_fw = p_fw; c.p_bw = p_bw;
+            c.q_fw = q_from_p(p_fw); c.q_bw = q_from_p(p_bw);
+            calls[idx] = c;
+        }
+    }
+}
+
+// Straightforward version: one thread per (slot, sample chunk), strand tests evaluated in place.
+// Kept as the in-tree cross-check of the queued kernel (tests compare both with the oracle).
+__global__ void __launch_bounds__(AS_CALL_THREADS)
+call_naive_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
+                  const uint8_t* __restrict__ ref, const float* __restrict__ thr_view, uint32_t cut,
+                  as_call* __restrict__ calls, int64_t cap, unsigned long long* __restrict__ n_calls) {
+    const int64_t p = p0 + (int64_t)blockIdx.x * AS_CALL_THREADS + threadIdx.x;
+    if (p >= p1) return;
+    CallSlotConst sc;
+    load_slot_const(sc, thr_view, ref, p);
+    if (sc.ref > 3) return;
+    const int t0 = blockIdx.y * chunk, t1 = min(T, t0 + chunk);
+    const int64_t sstride = 2 * P;
+    for (int t = t0; t < t1; ++t) {
+        const uint4 fw = ld_stream(counts + (int64_t)t * sstride + p);
+        const uint4 bw = ld_stream(counts + (int64_t)t * sstride + P + p);
+        if ((int32_t)fw.x < 0) continue;
+        const uint32_t FW = fw.x + fw.y + fw.z + fw.w, BW = bw.x + bw.y + bw.z + bw.w;  // VC:760-770
+        if (!(FW >= cut && BW >= cut)) continue;                                        // VC:898
+        for (int b = 0; b < 4; ++b) {  // increasing base order = the alt order of VC:869-3288
+            if ((uint32_t)b == sc.ref) continue;
+            const uint32_t kf = comp(fw, b), kb = comp(bw, b);
+            const float ef = sc.e[2 * b], eb = sc.e[2 * b + 1];
+            bool is_call = false;
+            double pf = 1.0, pb = 1.0;
+            if (ef != -1.0f && eb != -1.0f) {
+                pf = poisson_p((int)kf, (int)FW, ef);  // VC:895
+                if (q_at_least_5(pf)) {
+                    pb = poisson_p((int)kb, (int)BW, eb);  // VC:896
+                    is_call = q_at_least_5(pb);
+                }
+            }
+            emit_call(calls, n_calls, cap, is_call, t, (int32_t)p, b, (int32_t)sc.ref, pf, pb);
+        }
+    }
+}
+
+// Queued version.  Stage 0 (the scan): integer-only test per record and base -- coverage gate, alt != ref,
+// alt reads > 0 on both strands (VC:3858-3861: k == 0 gives Q = 0).  Stage 1: candidates are compacted
+// into a per-warp queue; full warps apply the exact m >= k screen.  Stage 2: survivors are compacted
+// again and each takes TWO lanes (forward and reverse strand) for the fp64 series of VC:3785-3794.
+struct CallCand {
+    uint32_t k_fw, d_fw, k_bw, d_bw;
+    float e_fw, e_bw;
+    uint32_t sample_alt;  // sample | alt << 30
+    int32_t slot;
+};
+static_assert(sizeof(CallCand) == 32, "CallCand is two 16-byte words");
+
+#define AS_Q1_CAP 128 /* <= 31 left over + 32 lanes x 3 alts */
+#define AS_Q2_CAP 48  /* <= 15 left over + 32 */
+
+__device__ __forceinline__ void stage2_batch(const CallCand* __restrict__ q2, int n_pairs,
+                                             const uint8_t* __restrict__ ref, as_call* __restrict__ calls,
+                                             int64_t cap, unsigned long long* __restrict__ n_calls) {
+    const int lane = threadIdx.x & 31;
+    const int pair = lane >> 1, strand = lane & 1;
+    double p = 1.0;
+    CallCand c;
+    const bool have = pair < n_pairs;
+    if (have) {
+        c = q2[pair];
+        p = strand == 0 ? poisson_p((int)c.k_fw, (int)c.d_fw, c.e_fw) : poisson_p((int)c.k_bw, (int)c.d_bw, c.e_bw);
+    }
+    const double p_other = __shfl_xor_sync(0xffffffffu, p, 1);
+    const bool is_call = have && strand == 0 && q_at_least_5(p) && q_at_least_5(p_other);
+    const unsigned votes = __ballot_sync(0xffffffffu, is_call);
+    if (votes == 0) return;
+    const int leader = __ffs(votes) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_calls, (unsigned long long)__popc(votes));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (is_call) {
+        const unsigned long long idx = base + __popc(votes & ((1u << lane) - 1u));
+        if ((int64_t)idx < cap) {
+            as_call o;
+            o.sample = (int32_t)(c.sample_alt & 0x3fffffffu);
+            o.slot = c.slot;
+            o.alt = (int32_t)(c.sample_alt >> 30);
+            o.ref = ref[c.slot];
+            o.p_fw = p; o.p_bw = p_other;
+            o.q_fw = q_from_p(p); o.q_bw = q_from_p(p_other);
+            calls[idx] = o;
+        }
+    }
+}
+
+__device__ __forceinline__ void stage1_batch(const CallCand* __restrict__ q1, int n, CallCand* __restrict__ q2,
+                                             int& n2, const uint8_t* __restrict__ ref, as_call* __restrict__ calls,
+                                             int64_t cap, unsigned long long* __restrict__ n_calls) {
+    const int lane = threadIdx.x & 31;
+    CallCand c;
+    bool surv = false;
+    if (lane < n) {
+        c = q1[lane];
+        surv = strand_can_pass(c.k_fw, c.d_fw, c.e_fw) && strand_can_pass(c.k_bw, c.d_bw, c.e_bw);
+    }
+    const unsigned votes = __ballot_sync(0xffffffffu, surv);
+    if (surv) q2[n2 + __popc(votes & ((1u << lane) - 1u))] = c;
+    n2 += __popc(votes);
+    __syncwarp();
+    while (n2 >= 16) {
+        stage2_batch(q2 + (n2 - 16), 16, ref, calls, cap, n_calls);
+        n2 -= 16;
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(AS_CALL_THREADS)
+call_queued_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
+                   const uint8_t* __restrict__ ref, const float* __restrict__ thr_view, uint32_t cut,
+                   as_call* __restrict__ calls, int64_t cap, unsigned long long* __restrict__ n_calls) {
+    __shared__ __align__(16) CallCand q1_all[AS_CALL_THREADS / 32][AS_Q1_CAP];
+    __shared__ __align__(16) CallCand q2_all[AS_CALL_THREADS / 32][AS_Q2_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CallCand* q1 = q1_all[warp];
+    CallCand* q2 = q2_all[warp];
+    int n1 = 0, n2 = 0;  // warp-uniform
+
+    const int64_t p = p0 + (int64_t)blockIdx.x * AS_CALL_THREADS + threadIdx.x;
+    CallSlotConst sc;
+    sc.ref = 255;
+    if (p < p1) load_slot_const(sc, thr_view, ref, p);
+    const bool slot_ok = p < p1 && sc.ref <= 3;
+    // a warp whose lanes are all idle has nothing to scan (its queues stay empty)
+    if (__ballot_sync(0xffffffffu, slot_ok) == 0) return;
+    const int64_t pp = slot_ok ? p : p0;  // idle lanes read a valid address and discard it
+    const uint32_t notref = slot_ok ? (0xfu & ~(1u << sc.ref)) : 0u;
+    const int t0 = blockIdx.y * chunk, t1 = min(T, t0 + chunk);
+    const int64_t sstride = 2 * P;
+
+    for (int t = t0; t < t1; ++t) {
+        const uint4 fw = ld_stream(counts + (int64_t)t * sstride + pp);
+        const uint4 bw = ld_stream(counts + (int64_t)t * sstride + P + pp);
+        const uint32_t FW = fw.x + fw.y + fw.z + fw.w, BW = bw.x + bw.y + bw.z + bw.w;
+        uint32_t mask = 0;
+        if ((int32_t)fw.x >= 0 && FW >= cut && BW >= cut) {
+            mask = ((fw.x != 0 && bw.x != 0) ? 1u : 0u) | ((fw.y != 0 && bw.y != 0) ? 2u : 0u) |
+                   ((fw.z != 0 && bw.z != 0) ? 4u : 0u) | ((fw.w != 0 && bw.w != 0) ? 8u : 0u);
+            mask &= notref;
+        }
+        if (__ballot_sync(0xffffffffu, mask != 0) == 0) continue;
+        // exclusive prefix sum of popc(mask) over the lanes
+        const int mine = __popc(mask);
+        int incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int off = n1 + incl - mine;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (mask & (1u << b)) {
+                CallCand c;
+                c.k_fw = comp(fw, b); c.d_fw = FW; c.k_bw = comp(bw, b); c.d_bw = BW;
+                c.e_fw = sc.e[2 * b]; c.e_bw = sc.e[2 * b + 1];
+                c.sample_alt = (uint32_t)t | ((uint32_t)b << 30);
+                c.slot = (int32_t)p;
+                q1[off++] = c;
+            }
+        }
+        n1 += total;
+        __syncwarp();
+        while (n1 >= 32) {
+            stage1_batch(q1 + (n1 - 32), 32, q2, n2, ref, calls, cap, n_calls);
+            n1 -= 32;
+        }
+    }
+    if (n1 > 0) stage1_batch(q1, n1, q2, n2, ref, calls, cap, n_calls);
+    if (n2 > 0) stage2_batch(q2, n2, ref, calls, cap, n_calls);
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise evaluators (parity grids)
+// ------------------------------------------------------------------------------------------------
+__global__ void poisson_test_kernel(const int32_t* __restrict__ k, const int32_t* __restrict__ rd,
+                                    const float* __restrict__ err, int64_t n, double* __restrict__ p,
+                                    double* __restrict__ q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (err[i] == -1.0f) { p[i] = __longlong_as_double(0x7ff8000000000000ull); q[i] = -888.0; return; }  // VC:3844
+    const double pv = poisson_p(k[i], rd[i], err[i]);
+    p[i] = pv;
+    q[i] = q_from_p(pv);
+}
+
+__global__ void gammaq_kernel(const double* __restrict__ s, const double* __restrict__ z, int64_t n,
+                              double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = kf_gammaq(s[i], z[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic panels generated in HBM; not on the parity path
+// ------------------------------------------------------------------------------------------------
+__global__ void synth_kernel(uint4* __restrict__ counts, int n_samples, int64_t P, uint8_t* __restrict__ ref_out,
+                             as_synth_params prm) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const uint64_t gp = (uint64_t)(p + prm.slot_offset);
+    const uint64_t hs = key4(prm.seed, gp, 0x51, 0);
+    const uint32_t ref = (uint32_t)(hs & 3);
+    if (ref_out != nullptr && blockIdx.y == 0) ref_out[p] = (uint8_t)ref;
+    // per-amplicon depth multiplier, shared by all samples (125-slot amplicons)
+    const float amp = __expf(0.6f * gauss(key4(prm.seed, gp / 125, 0x52, 0)));
+    // per (slot, base, strand) error rate: 0 with probability 0.6, else log-normal around 3e-4, capped at 0.02
+    float e[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint64_t h = key4(prm.seed, gp, 0x53, j);
+        e[j] = (u01(h) < 0.6f) ? 0.0f : fminf(0.02f, 3e-4f * __expf(gauss(mix64(h))));
+    }
+    // germline SNP of the slot: alt base and which samples carry it (population frequency 0.2)
+    const bool snp = u01(key4(prm.seed, gp, 0x54, 0)) < prm.germline_rate;
+    const uint32_t snp_alt = (ref + 1 + (uint32_t)((hs >> 8) % 3)) & 3;
+
+    const int s_per = (n_samples + gridDim.y - 1) / gridDim.y;
+    const int s0 = blockIdx.y * s_per, s1 = min(n_samples, s0 + s_per);
+    for (int s = s0; s < s1; ++s) {
+        const uint64_t gs = (uint64_t)(s + prm.sample_offset);
+        const uint64_t h = key4(prm.seed, gp, 0x60, gs);
+        uint4 fw, bw;
+        const float depth = prm.mean_depth * amp * __expf(prm.depth_sigma * gauss(h));
+        if (u01(mix64(h ^ 0x1111)) < prm.absent_rate || depth < 20.0f) {
+            fw = bw = make_uint4(AS_ABSENT, AS_ABSENT, AS_ABSENT, AS_ABSENT);
+        } else {
+            const float half = 0.5f * depth;
+            const float dfw = fmaxf(0.0f, half + sqrtf(0.5f * half) * gauss(mix64(h ^ 0x2222)));
+            const float dbw = fmaxf(0.0f, depth - dfw);
+            float vaf[4] = {0.f, 0.f, 0.f, 0.f};  // true variant allele fractions on top of the noise
+            if (snp && u01(key4(prm.seed, gp, 0x55, gs)) < 0.2f)
+                vaf[snp_alt] = (key4(prm.seed, gp, 0x56, gs) & 1) ? 1.0f : 0.5f;
+            const uint64_t hm = key4(prm.seed, gp, 0x57, gs);
+            if (u01(hm) < prm.somatic_rate) {
+                const uint32_t alt = (ref + 1 + (uint32_t)((hm >> 3) % 3)) & 3;
+                vaf[alt] = fmaxf(vaf[alt], prm.somatic_vaf_lo + (prm.somatic_vaf_hi - prm.somatic_vaf_lo) * u01(mix64(hm)));
+            }
+            uint32_t c[8];
+            uint32_t alt_fw = 0, alt_bw = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if ((uint32_t)b == ref) { c[b] = c[4 + b] = 0; continue; }
+                const float rf = fminf(1.0f, e[b] + vaf[b]), rb = fminf(1.0f, e[4 + b] + vaf[b]);
+                c[b] = min(poisson_sample(dfw * rf, key4(prm.seed, gp, 0x70 + b, gs)), (uint32_t)dfw - alt_fw);
+                c[4 + b] = min(poisson_sample(dbw * rb, key4(prm.seed, gp, 0x78 + b, gs)), (uint32_t)dbw - alt_bw);
+                alt_fw += c[b]; alt_bw += c[4 + b];
+            }
+            c[ref] = (uint32_t)dfw - alt_fw;
+            c[4 + ref] = (uint32_t)dbw - alt_bw;
+            fw = make_uint4(c[0], c[1], c[2], c[3]);
+            bw = make_uint4(c[4], c[5], c[6], c[7]);
+        }
+        counts[(int64_t)s * 2 * P + p] = fw;
+        counts[(int64_t)s * 2 * P + P + p] = bw;
+    }
+}
+
+}  // namespace asdev
+
+// ================================================================================================
+// launchers (plain C++ signatures, used by as_capi.cu)
+// ================================================================================================
+using namespace asdev;
+
+static inline unsigned cdiv64(int64_t a, int64_t b) { return (unsigned)((a + b - 1) / b); }
+
+cudaError_t as_launch_noise_main(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                 const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base, float C,
+                                 uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
+                                 uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
+    if (p1 <= p0) return cudaSuccess;
+    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
+    noise_main_kernel<AS_NOISE_UNROLL><<<cdiv64(p1 - p0, AS_NOISE_THREADS), AS_NOISE_THREADS, 0, st>>>(
+        c, S, P, p0, p1, d_twin_next, d_twin_head, twin_base, C, cut, d_thr, d_germ_val, d_germ_state, d_count, d_nrec);
+    return cudaGetLastError();
+}
+
+// 3 launches (memset node + 2 kernels)
+cudaError_t as_launch_noise_twins(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                  const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
+                                  uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
+                                  uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
+    if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
+    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
+    cudaMemsetAsync(d_nheads_scratch, 0, sizeof(uint32_t), st);
+    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, d_heads_scratch,
+                                                           d_nheads_scratch);
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
+    noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_heads_scratch, d_nheads_scratch, C, cut, d_thr,
+                                            d_germ_val, d_germ_state, d_count, d_nrec);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_thr_view(const float* d_thr, float* d_view, int64_t n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    thr_view_kernel<<<cdiv64(n, 256), 256, 0, st>>>(d_thr, d_view, n);
+    return cudaGetLastError();
+}
+
+int as_call_chunk(int T, int64_t n_slots) {
+    // enough threads to fill the chip a few times over; at least 4 samples per thread
+    const int64_t target = 148ll * 2048 * 4;
+    int64_t chunks = (target + n_slots - 1) / (n_slots > 0 ? n_slots : 1);
+    if (chunks < 1) chunks = 1;
+    int64_t chunk = (T + chunks - 1) / chunks;
+    if (chunk < 4) chunk = 4;
+    if (chunk > T) chunk = T;
+    // gridDim.y limit
+    while ((T + chunk - 1) / chunk > 65535) chunk *= 2;
+    return (int)(chunk < 1 ? 1 : chunk);
+}
+
+cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
+                           const uint8_t* d_ref, const float* d_thr_view, uint32_t cut, as_call* d_calls, int64_t cap,
+                           unsigned long long* d_n_calls, cudaStream_t st) {
+    if (p1 <= p0 || T <= 0) return cudaSuccess;
+    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
+    const int chunk = as_call_chunk(T, p1 - p0);
+    dim3 grid(cdiv64(p1 - p0, AS_CALL_THREADS), (unsigned)((T + chunk - 1) / chunk));
+    if (variant == 0)
+        call_naive_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(c, T, P, p0, p1, chunk, d_ref, d_thr_view, cut, d_calls, cap,
+                                                            d_n_calls);
+    else
+        call_queued_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(c, T, P, p0, p1, chunk, d_ref, d_thr_view, cut, d_calls,
+                                                             cap, d_n_calls);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
+                                   double* q, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    poisson_test_kernel<<<cdiv64(n, 128), 128, 0, st>>>(k, rd, err, n, p, q);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    gammaq_kernel<<<cdiv64(n, 128), 128, 0, st>>>(s, z, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_synth(uint32_t* d_counts, int n_samples, int64_t P, uint8_t* d_ref, const as_synth_params* prm,
+                            cudaStream_t st) {
+    if (P <= 0 || n_samples <= 0) return cudaSuccess;
+    const int64_t target = 148ll * 2048 * 2;
+    int64_t ychunks = (target + P - 1) / P;
+    if (ychunks < 1) ychunks = 1;
+    if (ychunks > n_samples) ychunks = n_samples;
+    if (ychunks > 65535) ychunks = 65535;
+    dim3 grid(cdiv64(P, 128), (unsigned)ychunks);
+    synth_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<uint4*>(d_counts), n_samples, P, d_ref, *prm);
+    return cudaGetLastError();
+}

@@ -1,0 +1,31 @@
+// Internal: kernel launchers shared between as_kernels.cu and as_capi.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "../../include/amplisolve_b200.h"
+
+#define AS_NOISE_THREADS 128
+#define AS_NOISE_UNROLL 4
+#define AS_CALL_THREADS 128
+
+cudaError_t as_launch_noise_main(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                 const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base, float C,
+                                 uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
+                                 uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
+cudaError_t as_launch_noise_twins(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                  const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
+                                  uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
+                                  uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
+cudaError_t as_launch_thr_view(const float* d_thr, float* d_view, int64_t n, cudaStream_t st);
+int as_call_chunk(int T, int64_t n_slots);
+cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
+                           const uint8_t* d_ref, const float* d_thr_view, uint32_t cut, as_call* d_calls, int64_t cap,
+                           unsigned long long* d_n_calls, cudaStream_t st);
+cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
+                                   double* q, cudaStream_t st);
+cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);
+cudaError_t as_launch_synth(uint32_t* d_counts, int n_samples, int64_t P, uint8_t* d_ref, const as_synth_params* prm,
+                            cudaStream_t st);

@@ -1,0 +1,182 @@
+// Noise-model arithmetic (device side) -- the per-record filter/accumulate and the per-position
+// finalise of AmpliSolve's estimateThresholds and Germ_Max, restated for dense count tensors.
+//
+//   EE = source_codes/AmpliSolveErrorEstimation.cpp of the reference.
+//   record filter + sums      EE:1565-1631 (A) == 1816-1878 (C) == 2062-2125 (G) == 2309-2372 (T)
+//   0.338*N rule, float divide EE:1742-1797
+//   Germ_Max                  EE:1229-1232, EE:1251-1271 (A, floor -888), EE:1309-1329 (C/G/T, floor 0)
+//
+// Division-free exact forms (each is an identity, not an approximation -- DESIGN.md "noise kernel"):
+//   (double)(float(b)/float(D)) <= 0.05   <=>   b' <= (26843545 * D') >> 29
+//       0.05 lies between the floats 0x3D4CCCCC and 0x3D4CCCCD; their midpoint is 26843545/2^29 and the
+//       tie rounds to the even lower float, so RN(b'/D') <= 0x3D4CCCCC <=> b'/D' <= 26843545/2^29.
+//       b', D' are the operands after int->float conversion: equal to b, D below 2^24, and rounded to
+//       24 significant bits above (rare path, handled by round24()).
+//   running max of float(X)/float(RD): IEEE rounding is monotone, so the max quotient is the quotient
+//       of the max rational; rationals are compared by 64-bit cross multiplication and divided once.
+//   sum_nt = sum(b) + sum(float(D)*C): every partial sum of the reference is exact in fp64 for
+//       cut >= ~10 and C >= ~1e-4, so integer sums of b and D plus one fp64 sum of the
+//       fp32 products, added once at the end, give the same double in any order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace asdev {
+
+#define AS_AF_LIMIT_NUM 26843545ull /* 0.05 as the float-rounding boundary, times 2^29 */
+
+__device__ __forceinline__ uint32_t round24(uint32_t v) { /* the integer value of float(v) */
+    return __float2uint_rn(__uint2float_rn(v));
+}
+__device__ __forceinline__ uint32_t af_limit(uint32_t depth_as_float) {
+    return (uint32_t)((AS_AF_LIMIT_NUM * (unsigned long long)depth_as_float) >> 29);
+}
+
+struct NoiseBase {
+    unsigned long long s_b_fw, s_b_bw;  // sum of alt reads over kept records (EE:1617, EE:1619)
+    unsigned long long s_d_fw, s_d_bw;  // sum of strand depth over kept records (EE:1618, EE:1620)
+    double s_p_fw, s_p_bw;              // sum of float(depth)*float(C) over kept records
+    uint32_t count;                     // EE:1626
+    // Germ_Max: qualifying records seen, the first one (needed only when segments are merged) and the
+    // best rational among the others
+    uint32_t g_n, g_first_x, g_first_rd, g_x, g_rd;
+};
+
+struct NoiseAcc {
+    NoiseBase b[4];
+    uint32_t nrec;  // records of the position = Value_Hash.count() (EE:1742)
+};
+
+__device__ __forceinline__ void noise_init(NoiseAcc& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a.b[i].s_b_fw = a.b[i].s_b_bw = a.b[i].s_d_fw = a.b[i].s_d_bw = 0ull;
+        a.b[i].s_p_fw = a.b[i].s_p_bw = 0.0;
+        a.b[i].count = 0;
+        a.b[i].g_n = 0;
+        a.b[i].g_first_x = 0; a.b[i].g_first_rd = 1;
+        a.b[i].g_x = 0; a.b[i].g_rd = 1;
+    }
+    a.nrec = 0;
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4& v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
+// One (sample, slot) record.  TRACK_FIRST keeps the first qualifying Germ_Max record so that partial
+// states of consecutive sample segments can be merged (noise_merge); the single-pass kernel does not
+// need it because the reference drops that record anyway (EE:1258-1262).
+template <bool TRACK_FIRST>
+__device__ __forceinline__ void noise_accumulate(NoiseAcc& a, const uint4 fw, const uint4 bw, const float C,
+                                                 const uint32_t cut) {
+    if ((int32_t)fw.x < 0) return;  // AS_ABSENT: no ASEQ row for this (sample, slot)
+    a.nrec += 1;
+    const uint32_t FW = fw.x + fw.y + fw.z + fw.w;  // EE:1155-1176
+    const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
+    const uint32_t RD = FW + BW;
+    if (!(FW >= cut && BW >= cut)) return;  // EE:1615 (thresholds) and EE:1251 (Germ_Max) both need it
+
+    // operands as the reference's float conversions see them
+    uint4 tfw = fw, tbw = bw;
+    uint4 tx = make_uint4(fw.x + bw.x, fw.y + bw.y, fw.z + bw.z, fw.w + bw.w);  // totals A,C,G,T (EE:1229-1232)
+    uint32_t tFW = FW, tBW = BW, tRD = RD;
+    if (RD >= (1u << 24)) {  // > 16.7 M reads on one position: int->float is no longer exact
+        tfw = make_uint4(round24(fw.x), round24(fw.y), round24(fw.z), round24(fw.w));
+        tbw = make_uint4(round24(bw.x), round24(bw.y), round24(bw.z), round24(bw.w));
+        tx = make_uint4(round24(tx.x), round24(tx.y), round24(tx.z), round24(tx.w));
+        tFW = round24(FW); tBW = round24(BW); tRD = round24(RD);
+    }
+    const uint32_t lim_fw = af_limit(tFW), lim_bw = af_limit(tBW), lim_rd = af_limit(tRD);
+    const double p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);  // EE:1617: fp32 product, then widened
+    const double p_bw = (double)__fmul_rn(__uint2float_rn(BW), C);
+
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        NoiseBase& s = a.b[i];
+        const uint32_t bf = comp(fw, i), bb = comp(bw, i);
+        if (comp(tfw, i) <= lim_fw && comp(tbw, i) <= lim_bw) {  // EE:1613-1615
+            s.s_b_fw += bf; s.s_b_bw += bb;
+            s.s_d_fw += FW; s.s_d_bw += BW;
+            s.s_p_fw = __dadd_rn(s.s_p_fw, p_fw);
+            s.s_p_bw = __dadd_rn(s.s_p_bw, p_bw);
+            s.count += 1;
+        }
+        const uint32_t x = comp(tx, i);
+        if (x <= lim_rd) {  // EE:1251: (double)(float(X)/float(RD)) <= 0.05
+            if (s.g_n == 0) {
+                if (TRACK_FIRST) { s.g_first_x = x; s.g_first_rd = tRD; }
+            } else if ((unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * tRD) {  // EE:1263: value <= AF
+                s.g_x = x; s.g_rd = tRD;
+            }
+            s.g_n += 1;
+        }
+    }
+}
+
+// Merge the state R of a LATER record segment into L (earlier).  Associative.
+__device__ __forceinline__ void noise_merge(NoiseAcc& L, const NoiseAcc& R) {
+    L.nrec += R.nrec;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        NoiseBase& l = L.b[i];
+        const NoiseBase& r = R.b[i];
+        l.s_b_fw += r.s_b_fw; l.s_b_bw += r.s_b_bw;
+        l.s_d_fw += r.s_d_fw; l.s_d_bw += r.s_d_bw;
+        l.s_p_fw = __dadd_rn(l.s_p_fw, r.s_p_fw);
+        l.s_p_bw = __dadd_rn(l.s_p_bw, r.s_p_bw);
+        l.count += r.count;
+        if (r.g_n == 0) continue;
+        if (l.g_n == 0) {
+            l.g_n = r.g_n; l.g_first_x = r.g_first_x; l.g_first_rd = r.g_first_rd; l.g_x = r.g_x; l.g_rd = r.g_rd;
+            continue;
+        }
+        // R's first record is an ordinary later record from L's point of view
+        if ((unsigned long long)r.g_first_x * l.g_rd >= (unsigned long long)l.g_x * r.g_first_rd) {
+            l.g_x = r.g_first_x; l.g_rd = r.g_first_rd;
+        }
+        if (r.g_n >= 2 && (unsigned long long)r.g_x * l.g_rd >= (unsigned long long)l.g_x * r.g_rd) {
+            l.g_x = r.g_x; l.g_rd = r.g_rd;
+        }
+        l.g_n += r.g_n;
+    }
+}
+
+// Per-position finalise (EE:1742-1797) and store for one slot.
+__device__ __forceinline__ void noise_store(const NoiseAcc& a, int64_t slot, float* __restrict__ thr,
+                                            float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
+                                            uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
+    float t[8], g[4];
+    uint32_t c[4];
+    uint32_t gs = 0;
+    const double n_rule = __dmul_rn(0.338, (double)a.nrec);  // EE:1742
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const NoiseBase& s = a.b[i];
+        float q_fw, q_bw;
+        if ((double)s.count < n_rule) {
+            q_fw = q_bw = __int_as_float(0x7fc00000);  // "-1_-1"
+        } else {
+            const double nt_fw = __dadd_rn((double)s.s_b_fw, s.s_p_fw);
+            const double nt_bw = __dadd_rn((double)s.s_b_bw, s.s_p_bw);
+            q_fw = __fdiv_rn(__double2float_rn(nt_fw), __double2float_rn((double)s.s_d_fw));  // EE:1762
+            q_bw = __fdiv_rn(__double2float_rn(nt_bw), __double2float_rn((double)s.s_d_bw));  // EE:1763
+            if (isnan(q_fw) || isnan(q_bw)) q_fw = q_bw = __int_as_float(0x7fc00000);         // EE:1765-1770
+        }
+        t[2 * i] = q_fw; t[2 * i + 1] = q_bw;
+        c[i] = s.count;
+        const uint32_t st = s.g_n == 0 ? 0u : (s.g_n == 1 ? 1u : 2u);
+        gs |= st << (8 * i);
+        g[i] = st == 2 ? __fdiv_rn(__uint2float_rn(s.g_x), __uint2float_rn(s.g_rd))  // EE:1229-1232
+                       : (i == 0 ? -888.0f : 0.0f);                                     // EE:1260, EE:1318
+    }
+    float4* t4 = reinterpret_cast<float4*>(thr + slot * 8);
+    t4[0] = make_float4(t[0], t[1], t[2], t[3]);
+    t4[1] = make_float4(t[4], t[5], t[6], t[7]);
+    *reinterpret_cast<float4*>(germ_val + slot * 4) = make_float4(g[0], g[1], g[2], g[3]);
+    *reinterpret_cast<uint32_t*>(germ_state + slot * 4) = gs;
+    *reinterpret_cast<uint4*>(count + slot * 4) = make_uint4(c[0], c[1], c[2], c[3]);
+    nrec[slot] = a.nrec;
+}
+
+}  // namespace asdev

@@ -1,0 +1,452 @@
+#!/usr/bin/env python
+"""Benchmark of the AmpliSolve hot path on B200 (contract: see the task statement / DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (CUDA, one process per GPU)
+    python bench.py --impl reference [--gpus N] ...                # the reference's CPU path on the host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: the noise model over all normals
+of the panel shard (as_noise_estimate_dev), the "%f" hand-over of the thresholds, and the Poisson caller
+over all tumours (as_call_variants_dev).  Workload at every N: BASELINE.json configs[2] per GPU -- a
+500-gene-panel-sized shard of 2,000,000 slots x 100 normals x 500 tumours at ~2000x (weak scaling: the
+N-GPU job is N such shards = a slice of the exome-scale configs[3], position-sharded, no collective on
+the data path).  Metric: Poisson strand tests per second (6 per (tumour, slot) record), whole job.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = {"name": "c3: synthetic 500-gene panel shard per GPU", "slots": 2_000_000, "normals": 100, "tumours": 500,
+            "depth": 2000.0, "C_value": 0.002, "coverage_cutoff": 100, "seed": 20183}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--slots", type=int, default=WORKLOAD["slots"], help="slots per GPU (default: the named workload)")
+    ap.add_argument("--normals", type=int, default=WORKLOAD["normals"])
+    ap.add_argument("--tumours", type=int, default=WORKLOAD["tumours"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--call-kernel", type=int, default=1, help="1 = queued (default), 0 = straightforward")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own programs (oracle/_ref) on the host cores
+# ------------------------------------------------------------------------------------------------------
+def _write_aseq(path, chrom, pos, counts_s):
+    """counts_s uint32 [2][P][4] of one sample -> .PILEUP.ASEQ text; absent rows skipped."""
+    present = counts_s[0, :, 0] != 0xFFFFFFFF
+    fw = counts_s[0, present].astype(np.int64)
+    bw = counts_s[1, present].astype(np.int64)
+    tot = fw + bw
+    rd = tot.sum(axis=1)
+    cols = np.column_stack([tot, rd, bw])
+    lines = ["chr\tpos\tdbsnp\tMAF\tref\talt\tA\tC\tG\tT\tRD\tArs\tCrs\tGrs\tTrs"]
+    ch = np.asarray(chrom)[present]
+    po = np.asarray(pos)[present]
+    for i in range(cols.shape[0]):
+        lines.append(f"{ch[i]}\t{po[i]}\t.\t.\t.\t.\t" + "\t".join(map(str, cols[i])))
+    Path(path).write_text("\n".join(lines) + "\n")
+    return int(present.sum())
+
+
+def make_reference_sample(workdir, n_slots, n_normals, n_tumours, depth, seed):
+    """A bounded sample of the bench workload as the text inputs the reference reads."""
+    from tests import synth
+    workdir = Path(workdir)
+    n_amp = max(1, n_slots // 125)
+    bed, slots, pos_id, U = synth.make_panel(n_amp, amp_len=(125, 125), overlap_frac=0.17, seed=seed, chroms=("chr1",))
+    P = len(slots)
+    normals, ref = synth.make_counts(n_normals, P, depth=depth, seed=seed, pos_id=pos_id, absent_rate=0.0,
+                                     low_cov_rate=0.0, edge_rate=0.0)
+    tumours, _ = synth.make_counts(n_tumours, P, depth=depth, seed=seed + 1, ref=ref, pos_id=pos_id,
+                                   somatic_rate=2e-4, absent_rate=0.0, low_cov_rate=0.0, edge_rate=0.0)
+    chrom = [c for c, _ in slots]
+    pos = [p for _, p in slots]
+    (workdir / "N").mkdir()
+    (workdir / "T").mkdir()
+    with open(workdir / "panel.bed", "w") as fh:
+        for i, (c, s, e) in enumerate(bed):
+            fh.write(f"{c}\t{s}\t{e}\tAMP{i}\t.\tGENE\n")
+    seen = {}
+    with open(workdir / "rb_ref.txt", "w") as fh:
+        for (c, p), r in zip(slots, ref):
+            fh.write(f"{c}\t{p}\t{'ACGT'[r]}\n")
+            seen[(c, p)] = seen.get((c, p), 0) + 1
+    with open(workdir / "rb_dup.txt", "w") as fh:
+        for (c, p), n in sorted(seen.items()):
+            if n >= 2:
+                fh.write(f"{c}\t{p}\n")
+    rows_n = sum(_write_aseq(workdir / "N" / f"N{i}.PILEUP.ASEQ", chrom, pos, normals[i]) for i in range(n_normals))
+    rows_t = sum(_write_aseq(workdir / "T" / f"T{i}.PILEUP.ASEQ", chrom, pos, tumours[i]) for i in range(n_tumours))
+    return {"slots": P, "unique": U, "normal_rows": rows_n, "tumour_rows": rows_t, "normals": normals, "tumours": tumours,
+            "ref": ref, "pos_id": pos_id}
+
+
+def _ref_worker_cmds(workdir, out_tag):
+    ref_dir = ROOT / "oracle" / "_ref"
+    ee = [str(ref_dir / "ee_ref"), "panel.bed", "rb_ref.txt", "rb_dup.txt", "N", "0.002", "100", f"o{out_tag}",
+          f"o{out_tag}/list.txt"]
+    vc = [str(ref_dir / "AmpliSolveVariantCalling"), f"errorFile=o{out_tag}/positionSpecificNoise_0.0020.txt",
+          "tumour_dir=T", f"output_dir=v{out_tag}", "coverage_cutoff=100", "p_value=0.05"]
+    return ee, vc
+
+
+def run_reference_pass(workdir, cores, kind, sample):
+    """One pass of the reference's path on `cores` host cores (one single-threaded process per core, each
+    over the same bounded sample).  Returns (wall seconds, noise seconds of the slowest worker)."""
+    workdir = Path(workdir)
+    if kind == "reference":
+        t0 = time.perf_counter()
+        procs = []
+        for c in range(cores):
+            (workdir / f"o{c}").mkdir(exist_ok=True)
+            (workdir / f"v{c}").mkdir(exist_ok=True)
+            ee, vc = _ref_worker_cmds(workdir, c)
+            script = " ".join(ee) + " >/dev/null 2>&1 && date +%s.%N && " + " ".join(vc) + " >/dev/null 2>&1"
+            procs.append(subprocess.Popen(["bash", "-c", script], cwd=workdir, stdout=subprocess.PIPE, text=True))
+        mids = []
+        for p in procs:
+            out, _ = p.communicate()
+            if p.returncode != 0:
+                raise RuntimeError("reference worker failed")
+            mids.append(float(out.strip().splitlines()[-1]))
+        wall = time.perf_counter() - t0
+        t0_epoch = time.time() - wall
+        return wall, max(mids) - t0_epoch
+    # "port": the in-repo CPU restatement (oracle/liboracle.so), one process per core
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_port_worker, [sample] * cores)
+    return time.perf_counter() - t0, max(res)
+
+
+def _port_worker(sample):
+    from oracle import pyoracle
+    from tests import synth
+    t0 = time.perf_counter()
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(sample["normals"]), sample["pos_id"])
+    nz = pyoracle.noise_estimate(rows, off, sample["unique"], np.float32(0.002), 100)
+    t_noise = time.perf_counter() - t0
+    thr = pyoracle.thr_as_caller_sees(np.where(np.isnan(nz["thr"]), np.float32(0.01), nz["thr"]))
+    ref_u = np.zeros(sample["unique"], np.uint8)
+    ref_u[sample["pos_id"]] = sample["ref"]
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(sample["tumours"]), sample["pos_id"])
+    pyoracle.call_variants(rows, off, sample["unique"], ref_u, thr, 100)
+    return t_noise
+
+
+def cpu_reference(steps, warmup, sample_slots=1000, sample_normals=100, sample_tumours=500):
+    """Times the reference CPU path on all host cores over a bounded sample; returns the JSON fragments."""
+    cores = os.cpu_count() or 1
+    have_ref = (ROOT / "oracle" / "_ref" / "ee_ref").exists() and (ROOT / "oracle" / "_ref" / "AmpliSolveVariantCalling").exists()
+    kind = "reference" if have_ref else "port"
+    with tempfile.TemporaryDirectory(prefix="asb_", dir="/tmp") as td:
+        sample = make_reference_sample(td, sample_slots, sample_normals, sample_tumours, WORKLOAD["depth"], WORKLOAD["seed"])
+        walls, noises = [], []
+        for i in range(warmup + steps):
+            w, nz = run_reference_pass(td, cores, kind, sample)
+            if i >= warmup:
+                walls.append(w)
+                noises.append(nz)
+    wall = float(np.mean(walls))
+    tests = 6.0 * sample["tumour_rows"] * cores
+    desc = (f"{sample['slots']} slots x {sample_normals} normals x {sample_tumours} tumours at ~{int(WORKLOAD['depth'])}x, "
+            f"the same sample on each of {cores} cores (one single-threaded process per core); "
+            + ("oracle/_ref: reference sources compiled -O2, text in / text out" if kind == "reference"
+               else "oracle/liboracle.so port (reference binaries not present)"))
+    return {"value": tests / wall, "unit": "Poisson tests/s", "cores": cores, "kind": kind, "sample": desc,
+            "noise_positions_per_s": sample["slots"] * cores / float(np.mean(noises)), "ms_per_step": wall * 1e3}
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        self.th.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def hbm_peak():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from amplisolve_b200 import CALL_DTYPE, Context
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    ctx = Context(local)
+    ctx.set_call_kernel(args.call_kernel)
+    P, S, T = args.slots, args.normals, args.tumours
+    C, cut = WORKLOAD["C_value"], WORKLOAD["coverage_cutoff"]
+
+    # synthetic inputs generated in HBM, untimed; rank r owns global slots [r*P, (r+1)*P)
+    normals, ref = ctx.synth_counts_dev(S, P, seed=WORKLOAD["seed"], mean_depth=WORKLOAD["depth"], slot_offset=rank * P)
+    tumours, _ = ctx.synth_counts_dev(T, P, seed=WORKLOAD["seed"], mean_depth=WORKLOAD["depth"], somatic_rate=2e-4,
+                                      sample_offset=1 << 20, slot_offset=rank * P, want_ref=False)
+    out = ctx.alloc_noise_outputs(P)
+    view = torch.empty_like(out["thr"])
+    cap = max(1 << 16, int(T * P * 0.004))
+    calls = torch.empty(cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    n_calls = torch.zeros(1, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def step(marks=None):
+        if marks is not None:
+            marks[0].record()
+        ctx.estimate_thresholds_dev(normals, C, cut, out)
+        if marks is not None:
+            marks[1].record()
+        ctx.thresholds_caller_view_dev(out["thr"], view)
+        n_calls.zero_()
+        if marks is not None:
+            marks[2].record()
+        ctx.call_variants_dev(tumours, ref, view, cut, calls, n_calls)
+        if marks is not None:
+            marks[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    marks = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    e0, e1 = ev(), ev()
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(marks[i])
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches - launches0 + args.steps  # + the n_calls.zero_() fill kernel of each step
+    t_noise = float(np.mean([m[0].elapsed_time(m[1]) for m in marks]))
+    t_call = float(np.mean([m[2].elapsed_time(m[3]) for m in marks]))
+    found = int(n_calls.item())
+    if found > cap:
+        raise RuntimeError(f"call list overflow in the benchmark: {found} > {cap}")
+
+    tmax = torch.tensor([total_ms, t_noise, t_call], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms, t_noise_max, t_call_max = [float(x) for x in tmax.tolist()]
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, ctx, normals, tumours, ref, rank, world, barrier)
+
+    result = None
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        tests_per_step = 6.0 * T * P * world
+        peak, peak_src = hbm_peak()
+        call_bytes = T * P * 32 + P * 33 + found * CALL_DTYPE.itemsize
+        noise_bytes = P * (32 * S + 72)
+        result = {
+            "metric": "Poisson tests/sec", "value": tests_per_step / (ms_per_step * 1e-3), "unit": "Poisson tests/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 scan + f64 incomplete gamma",
+            "data": "synthetic (seeded generator in HBM, SURVEY.md 8d)",
+            "config": {"workload": WORKLOAD["name"] if P == WORKLOAD["slots"] else "custom", "slots_per_gpu": P,
+                       "normals": S, "tumours": T, "depth": WORKLOAD["depth"], "C_value": C, "coverage_cutoff": cut,
+                       "sharding": f"positions x{world}, no collective on the data path",
+                       "l2": "inputs (6.4 GB normals + 32 GB tumours per step) far larger than the 126 MB L2",
+                       "calls_per_step_rank0": found, "call_kernel": "queued" if args.call_kernel else "straightforward"},
+            "noise_positions_per_s": P * world / (t_noise_max * 1e-3),
+            "kernel_ms": {"noise_model": t_noise_max, "caller": t_call_max},
+            "roofline": {"bound": "hbm", "kernel": "call_queued_kernel" if args.call_kernel else "call_naive_kernel",
+                         "achieved": call_bytes / (t_call * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": call_bytes},
+            "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
+                               "peak": peak, "unit": "GB/s", "frac": noise_bytes / (t_noise * 1e-3) / 1e9 / peak,
+                               "traffic": None, "algorithmic_bytes": noise_bytes},
+            "gpu_launches": int(launches * world), "clocks": clocks,
+        }
+        if e2e is not None:
+            result["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference(steps=1, warmup=0)
+            result["cpu_baseline"] = cb
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def run_e2e(args, ctx, d_normals, d_tumours, d_ref, rank, world, barrier):
+    """Same step through as_noise_estimate_host / as_call_variants_host: inputs start in pinned HOST memory;
+    H2D of all counts and D2H of the noise table and the calls are inside the timed region."""
+    import ctypes as C
+
+    import psutil
+    import torch
+
+    from amplisolve_b200 import CALL_DTYPE, lib
+    P, S, T = args.slots, args.normals, args.tumours
+    # keep the pinned footprint of all ranks below a third of the free host memory
+    need = (S + T) * P * 32
+    avail = psutil.virtual_memory().available / max(1, world) / 3
+    Pe = P
+    while (S + T) * Pe * 32 > avail and Pe > 50_000:
+        Pe //= 2
+    L = lib()
+
+    def pinned(nbytes):
+        p = C.c_void_p()
+        rc = L.as_host_alloc(C.byref(p), nbytes)
+        if rc != 0:
+            raise RuntimeError(L.as_last_error().decode())
+        return p
+
+    bn, bt = S * 2 * Pe * 16, T * 2 * Pe * 16
+    hp_n, hp_t = pinned(bn), pinned(bt)
+    h_norm = np.ctypeslib.as_array(C.cast(hp_n, C.POINTER(C.c_uint32)), shape=(S, 2, Pe, 4))
+    h_tum = np.ctypeslib.as_array(C.cast(hp_t, C.POINTER(C.c_uint32)), shape=(T, 2, Pe, 4))
+    # untimed: bring the synthetic inputs to the host (slot prefix of the device tensors)
+    t_n = torch.from_numpy(h_norm.view(np.int32))
+    t_t = torch.from_numpy(h_tum.view(np.int32))
+    t_n.copy_(d_normals[:, :, :Pe, :])
+    t_t.copy_(d_tumours[:, :, :Pe, :])
+    h_ref = d_ref[:Pe].cpu().numpy()
+    torch.cuda.synchronize()
+    cut, Cv = WORKLOAD["coverage_cutoff"], WORKLOAD["C_value"]
+    cap = max(1 << 16, int(T * Pe * 0.004))
+    stats = {}
+
+    def one():
+        noise = ctx.estimate_thresholds(h_norm, Cv, cut)
+        view = ctx.thresholds_caller_view_dev(torch.from_numpy(noise["thr"]).cuda()).cpu().numpy()
+        calls = ctx.call_variants(h_tum, h_ref, view, cut, cap=cap)
+        stats["calls"] = len(calls)
+
+    one()  # warm-up (allocates the tile buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        one()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    import torch.distributed as dist
+    if world > 1:
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    L.as_host_free(hp_n)
+    L.as_host_free(hp_t)
+    return {"value": 6.0 * T * Pe * world / dt, "unit": "Poisson tests/s", "ms_per_step": dt * 1e3,
+            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + Pe * 32), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
+            "slots_per_gpu": Pe, "api": "as_noise_estimate_host + as_thresholds_caller_view_dev + as_call_variants_host, pinned host buffers",
+            "timer": "host wall clock around the blocking C-ABI calls, max over ranks"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb = cpu_reference(steps=args.steps, warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "Poisson tests/sec", "value": cb["value"], "unit": "Poisson tests/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32 + f64/x87 (CPU)",
+                "data": "synthetic (bounded sample of the bench workload, written as ASEQ text)",
+                "config": {"workload": WORKLOAD["name"], "sample": cb["sample"]},
+                "noise_positions_per_s": cb["noise_positions_per_s"],
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "Poisson tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+    res = run_ours(args)
+    if res is not None:
+        print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,168 @@
+/* amplisolve_b200 -- C ABI of the B200-native AmpliSolve hot path (libamplisolve_b200.so).
+ *
+ * The reference (dkleftogi/AmpliSolve) has no library or FFI surface: its boundary is the process
+ * boundary of two single-file programs.  This header is the boundary a maintainer would bind
+ * instead; every entry point names the reference code it replaces
+ *   EE = source_codes/AmpliSolveErrorEstimation.cpp, VC = source_codes/AmpliSolveVariantCalling.cpp.
+ * The two drop-in executables (amplisolve_b200/bin/AmpliSolveErrorEstimation, ...VariantCalling)
+ * and the Python mirror (amplisolve_b200/api.py) are thin callers of exactly these functions.
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success or a negative AS_E* code, with a
+ *     human-readable message available from as_last_error() (thread-local).
+ *   - there is NO CPU fallback: every compute entry point fails with AS_ECUDA when no sm_100
+ *     device / driver is available.
+ *   - "_host" entry points take host pointers (pinned or pageable) and do H2D, kernels and D2H
+ *     themselves, tiling over slots with double-buffered streams; "_dev" entry points take
+ *     device pointers (inputs resident in HBM) and only enqueue kernels on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *
+ * Data layout ("count tensor"): uint32 counts[sample][strand][slot][base]
+ *     strand 0 = forward, 1 = reverse; base 0..3 = A,C,G,T; one 16-byte word per (sample,strand,slot),
+ *     so the tensor base must be 16-byte aligned.
+ *     slot   = index into the BED enumeration of the panel (both ends inclusive, duplicated
+ *              positions kept as separate slots: EE:637, EE:2606).
+ *     A (sample,slot) with no ASEQ row is ABSENT: all eight words = AS_ABSENT (0xFFFFFFFF).  This is
+ *     not the same as a row of zeros: absence changes N in the 0.338*N rule (EE:1742).  Valid counts
+ *     are < 2^31 (the reference reads them with %d).
+ *     Derivation from an ASEQ row (EE:1149-1176, VC:752-770): fw[b] = X - X_rs, bw[b] = X_rs; the RD
+ *     column must equal the sum of the eight words (true of every row the reference's own pileup
+ *     step writes; the loader rejects files where it is not).
+ *   Twin slots: a position enumerated by two overlapping amplicons owns several slots.  The
+ *     reference keys records by "chrom_pos" text, so all rows of all twins feed one noise estimate
+ *     (EE:1241-1245).  twin_next[slot] = next slot of the same position (or -1); twin_head[slot] =
+ *     first slot of the position (== slot for singletons).  Both may be NULL (no duplicated position).
+ */
+#ifndef AMPLISOLVE_B200_H
+#define AMPLISOLVE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AS_ABSENT 0xFFFFFFFFu
+
+enum {
+    AS_OK = 0,
+    AS_EINVAL = -1,   /* bad argument */
+    AS_ECUDA = -2,    /* CUDA error, or no usable sm_100 device */
+    AS_ENOMEM = -3,
+    AS_EIO = -4,      /* file could not be opened / parsed */
+    AS_EOVERFLOW = -5 /* call list capacity exceeded (n_calls still reports the true count) */
+};
+
+typedef struct as_ctx as_ctx; /* one context per device; not thread-safe, use one per thread */
+
+/* A called variant as the device emits it.  Replaces the decision of VC:898 plus the two strand
+ * tests of VC:895-896.  48 bytes. */
+typedef struct {
+    int32_t sample; /* index into the tumour axis of the count tensor */
+    int32_t slot;   /* panel slot */
+    int32_t alt;    /* 0..3 = A,C,G,T */
+    int32_t ref;    /* 0..3 */
+    double p_fw;    /* the double p-value of VC:3858-3866, forward strand */
+    double p_bw;    /* reverse strand */
+    double q_fw;    /* Qscore_fw of VC:3868-3882 evaluated in fp64 (100 when p < 1e-10) */
+    double q_bw;
+} as_call;
+
+/* ---- context ------------------------------------------------------------------------------ */
+const char* as_last_error(void);
+const char* as_version(void);
+int as_device_count(int* n);
+int as_create(int device, as_ctx** out);
+void as_destroy(as_ctx* ctx);
+/* Pinned host memory for the _host entry points (cudaHostAlloc / cudaFreeHost). */
+int as_host_alloc(void** out, size_t bytes);
+int as_host_free(void* p);
+/* 0 = straightforward caller kernel (cross-check), 1 = queued caller kernel (default). */
+int as_set_call_kernel(as_ctx* ctx, int variant);
+/* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
+int64_t as_kernel_launches(const as_ctx* ctx);
+
+/* ---- noise model: replaces storeGermlineStatistics (Germ_Max part, EE:1247-1467) and
+ *      estimateThresholds (EE:1484-2544) ------------------------------------------------------
+ * Inputs : counts of the S normals in the reference's file-iteration order (EE:1081; Germ_Max
+ *          depends on it), twin_next/twin_head [P] or NULL, C = the float C_value (EE:329), cut >= 1.
+ *          Slots [slot_begin, slot_end) of the tensor are processed; a twin group is processed when
+ *          its head lies in the range (all of its members must be resident).
+ * Outputs (per slot, indexed by slot; twins receive identical values):
+ *   thr        float  [P][4][2]  fw,bw threshold per base; NaN = the "-1_-1" text (EE:1742-1770)
+ *   germ_val   float  [P][4]     Germ_Max value: the maximal float(X)/float(RD) when germ_state == 2,
+ *                                the floor (-888 for A, 0 for C,G,T; EE:1260, EE:1318) when 1
+ *   germ_state uint8  [P][4]     0 = no entry ("-"), 1 = one qualifying record only, 2 = germ_val
+ *   count      uint32 [P][4]     records that passed the filter (EE:1626)
+ *   nrec       uint32 [P]        records of the position = Value_Hash.count() (EE:1742)          */
+int as_noise_estimate_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int64_t P, int64_t slot_begin,
+                          int64_t slot_end, const int32_t* d_twin_next, const int32_t* d_twin_head, float C,
+                          int32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count,
+                          uint32_t* d_nrec, void* stream);
+int as_noise_estimate_host(as_ctx* ctx, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
+                           const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
+                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec);
+
+/* The noise table crosses to the caller as "%f" text (EE:1787 -> std::stof at VC:889-890) with
+ * "-1_-1" replaced by "0.01_0.01" (EE:2680-2684).  This applies exactly that mapping to thr
+ * [n] floats in place of the text round trip: NaN -> 0.01f, v -> strtof(sprintf("%f", v)). */
+int as_thresholds_caller_view_dev(as_ctx* ctx, const float* d_thr, float* d_thr_view, int64_t n, void* stream);
+
+/* ---- caller: replaces the row loop of callVariants (VC:723-3296: strand counts, threshold
+ *      lookup, 3 alts x 2 strands of mutationRulesPoissonQualityScore VC:3834-3884 over the kfunc
+ *      incomplete gamma VC:3720-3830, and the decision VC:898) --------------------------------
+ * Inputs : tumour counts [T][2][P][4]; ref [P] (0..3, anything else = not callable, VC:3290);
+ *          thr_view [P][4][2] = thresholds as the caller parsed them; cut >= 1.
+ * Outputs: calls (unordered on the _dev path; sorted by (sample, slot, alt) = the reference's row
+ *          order on the _host path), n_calls = true number found (the _dev path ADDS to
+ *          *d_n_calls: zero it first).  Returns AS_EOVERFLOW when n_calls > cap (the first cap
+ *          entries are valid).                                                                   */
+int as_call_variants_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t T, int64_t P, int64_t slot_begin,
+                         int64_t slot_end, const uint8_t* d_ref, const float* d_thr_view, int32_t cut,
+                         as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, void* stream);
+int as_call_variants_host(as_ctx* ctx, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
+                          const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls);
+
+/* Element-wise Poisson test on the device: p[i] = the double p-value of VC:3858-3866 and
+ * q[i] = the Q score of VC:3868-3882 for (k[i], rd[i], err[i]).  Host pointers.  Used by the
+ * parity tests to compare the device incomplete gamma with the reference's on arbitrary grids. */
+int as_poisson_test_host(as_ctx* ctx, const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
+                         double* q);
+/* kf_gammaq(s, z) of VC:3726 evaluated on the device, element-wise.  Host pointers. */
+int as_kf_gammaq_host(as_ctx* ctx, const double* s, const double* z, int64_t n, double* out);
+
+/* ---- synthetic count tensors generated directly in HBM (benchmark inputs) ------
+ * Fills d_counts [n_samples][2][P][4] with the seeded synthetic panel model: log-normal depth,
+ * per-slot strand-specific error rates, germline SNPs, spiked somatic SNVs (tumours only) and
+ * absent rows.  d_ref [P] receives the reference base of each slot when non-NULL. */
+typedef struct {
+    uint64_t seed;
+    float mean_depth;     /* e.g. 2000 */
+    float depth_sigma;    /* log-normal sigma of per-(sample,slot) depth, e.g. 0.5 */
+    float germline_rate;  /* fraction of slots carrying a germline SNP, e.g. 1e-3 */
+    float somatic_rate;   /* spiked SNVs per (sample,slot); 0 for normals */
+    float somatic_vaf_lo; /* e.g. 0.01 */
+    float somatic_vaf_hi; /* e.g. 0.2 */
+    float absent_rate;    /* fraction of (sample,slot) records dropped */
+    int32_t sample_offset; /* global index of the first sample (decorrelates normals and tumours) */
+    int64_t slot_offset;   /* global index of the first slot (position sharding across GPUs) */
+} as_synth_params;
+int as_synth_counts_dev(as_ctx* ctx, uint32_t* d_counts, int32_t n_samples, int64_t P, uint8_t* d_ref,
+                        const as_synth_params* prm, void* stream);
+
+/* ---- host side of the two programs (text formats; amplisolve_b200/csrc/as_host.cpp) ---------- */
+/* Iteration order of a libstdc++ std::unordered_map<std::string,std::string> after inserting keys
+ * in the given sequence: the order in which the reference walks its file lists (EE:1081, VC:672).
+ * order_out[i] = index into keys of the i-th visited entry.  Returns the number of entries. */
+int as_hash_iteration_order(const char* const* keys, int32_t n, int32_t* order_out);
+
+/* Whole programs, argv-compatible with the reference (EE:241-520, VC:199-360).  Exit status is
+ * the return value; like the reference, usage errors print the usage text and return 0. */
+int as_error_estimation_main(int argc, char** argv);
+int as_variant_calling_main(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMPLISOLVE_B200_H */

@@ -1,0 +1,279 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle on the same seeded inputs.
+
+Bars (BASELINE.json north_star): noise tables and call sets bit-exact (thresholds compared as float bit
+patterns, counts/states as integers, call keys as integers); p-values within 1e-12 relative where the
+reference's own 1-(1-x) arithmetic is conditioned to that (p >= 1e-4), and within two
+quanta of 2^-53 below.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+P_REL_TOL = 1e-12     # relative tolerance on p where well conditioned (p >= 1e-4)
+P_ABS_QUANTA = 2.3e-16  # two quanta of the 1-(1-x) grid
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def oracle_noise(counts, pos_id, U, C, cut):
+    rows, row_off = pyoracle.dense_to_rows(synth.to_oracle_layout(counts), pos_id)
+    return pyoracle.noise_estimate(rows, row_off, U, C, cut)
+
+
+def check_noise(got, want, pos_id):
+    thr_w = want["thr"][pos_id]          # per slot
+    assert np.array_equal(np.isnan(got["thr"]), np.isnan(thr_w))
+    m = ~np.isnan(thr_w)
+    assert np.array_equal(bits(got["thr"])[m], bits(thr_w)[m]), "threshold floats differ"
+    assert np.array_equal(got["count"].astype(np.int64), want["count"][pos_id].astype(np.int64))
+    assert np.array_equal(got["nrec"].astype(np.int64), want["nrec"][pos_id].astype(np.int64))
+    present_w = want["germ_present"][pos_id]
+    assert np.array_equal(got["germ_state"] > 0, present_w > 0)
+    mm = present_w > 0
+    # the oracle keeps the reference's double (a widened float, -888 or 0): compare as float bit patterns
+    assert np.array_equal(bits(got["germ_val"])[mm], bits(want["germ_val"][pos_id].astype(np.float32))[mm])
+
+
+@pytest.mark.parametrize("S,n_amp,depth,C,cut,seed", [
+    (5, 30, 700, 0.002, 100, 11),
+    (40, 20, 5000, 0.002, 100, 12),
+    (33, 25, 2000, 0.001, 100, 13),
+    (7, 12, 300, 0.005, 50, 14),
+    (1, 10, 1500, 0.002, 100, 15),
+    (100, 8, 2000, 0.0035, 150, 16),
+    (20, 10, 160, 0.002, 100, 17),   # marginal coverage: the 0.338*N rule decides
+])
+def test_noise_matches_oracle(ctx, S, n_amp, depth, C, cut, seed):
+    _, slots, pos_id, U = synth.make_panel(n_amp, seed=seed)
+    P = len(slots)
+    counts, _ = synth.make_counts(S, P, depth=depth, seed=seed, pos_id=pos_id)
+    nxt, head = ctx_twins(pos_id)
+    got = ctx.estimate_thresholds(counts, C, cut, nxt, head)
+    want = oracle_noise(counts, pos_id, U, np.float32(C), cut)
+    check_noise(got, want, pos_id)
+
+
+def ctx_twins(pos_id):
+    from amplisolve_b200 import twin_links
+    return twin_links(pos_id)
+
+
+def test_noise_no_twins_ragged_and_empty(ctx):
+    for P in (1, 31, 127, 129, 1000):
+        pos_id = np.arange(P, dtype=np.int32)
+        counts, _ = synth.make_counts(9, P, depth=900, seed=P)
+        got = ctx.estimate_thresholds(counts, 0.002, 100)
+        check_noise(got, oracle_noise(counts, pos_id, P, np.float32(0.002), 100), pos_id)
+    # all rows absent: N = 0 -> 0 < 0 is false -> 0/0 -> NaN -> "-1_-1" (EE:1765-1770)
+    counts = np.full((4, 2, 50, 4), 0xFFFFFFFF, dtype=np.uint32)
+    got = ctx.estimate_thresholds(counts, 0.002, 100)
+    assert np.isnan(got["thr"]).all() and (got["nrec"] == 0).all() and (got["germ_state"] == 0).all()
+    # no normals at all
+    got = ctx.estimate_thresholds(np.zeros((0, 2, 10, 4), np.uint32), 0.002, 100)
+    assert np.isnan(got["thr"]).all()
+
+
+def test_noise_counts_beyond_2_pow_24(ctx):
+    """int -> float conversion is inexact above 2^24: the division-free filter must round like float()."""
+    P = 400
+    pos_id = np.arange(P, dtype=np.int32)
+    counts, _ = synth.make_counts(6, P, depth=3000, seed=77, big_rate=0.5)
+    got = ctx.estimate_thresholds(counts, 0.002, 100)
+    check_noise(got, oracle_noise(counts, pos_id, P, np.float32(0.002), 100), pos_id)
+
+
+def test_noise_filter_boundary_exhaustive(ctx):
+    """Every (alt, depth) pair around the 5 % boundary for depths 100..4000: one slot per pair, one normal,
+    so count is 0 or 1 and tells whether the record passed (EE:1613-1615)."""
+    depths = np.arange(100, 4001)
+    cases = []
+    for D in depths:
+        k0 = D // 20
+        for k in (k0 - 1, k0, k0 + 1):
+            if 0 <= k <= D:
+                cases.append((D, k))
+    cases = np.array(cases)
+    P = len(cases)
+    counts = np.zeros((1, 2, P, 4), dtype=np.uint32)
+    counts[0, 0, :, 0] = cases[:, 0] - cases[:, 1]   # ref A
+    counts[0, 0, :, 2] = cases[:, 1]                 # alt G on the forward strand
+    counts[0, 1, :, 0] = 500                         # clean reverse strand
+    pos_id = np.arange(P, dtype=np.int32)
+    got = ctx.estimate_thresholds(counts, 0.002, 100)
+    check_noise(got, oracle_noise(counts, pos_id, P, np.float32(0.002), 100), pos_id)
+    assert 0 < got["count"][:, 2].sum() < P
+
+
+def test_thresholds_caller_view_all_six_decimal_values(ctx):
+    """The noise table crosses to the caller as "%f" text: every threshold is n/10^6 after the round trip.
+    Exhaustive over the floats nearest to every n in 0..60000 plus random floats, against the oracle's
+    sprintf/strtof."""
+    import torch
+    n = np.arange(0, 60001)
+    base = (n / 1e6).astype(np.float32)
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([base, np.nextafter(base, np.float32(1)), np.nextafter(base, np.float32(-1)),
+                           ((n + 0.5) / 1e6).astype(np.float32),
+                           rng.uniform(0, 1.0, 200000).astype(np.float32), np.array([np.nan], np.float32)])
+    view = ctx.thresholds_caller_view_dev(torch.from_numpy(vals).cuda()).cpu().numpy()
+    want = pyoracle.thr_as_caller_sees(np.where(np.isnan(vals), np.float32(0.01), vals))
+    assert np.array_equal(bits(view), bits(want))
+
+
+def test_kf_gammaq_grid(ctx):
+    rng = np.random.default_rng(3)
+    s = np.concatenate([np.arange(1, 200), rng.integers(200, 60000, 3000)]).astype(np.float64)
+    ratio = rng.choice([0.01, 0.1, 0.5, 0.9, 0.99, 1.0, 1.000001, 1.01, 1.5, 3.0, 10.0], size=s.size)
+    z = s * ratio
+    got = ctx.kf_gammaq(s, z)
+    want = np.array([pyoracle.kf_gammaq(a, b) for a, b in zip(s, z)])
+    fin = np.isfinite(want)
+    assert np.array_equal(np.isfinite(got), fin)
+    # libdevice exp/log vs glibc: < 1 ulp each on an exponent of magnitude <= ~1e3 -> relative 1e-12
+    assert np.allclose(got[fin], want[fin], rtol=2e-12, atol=1e-300)
+
+
+def test_poisson_pvalues_grid(ctx):
+    rng = np.random.default_rng(4)
+    n = 20000
+    rd = rng.integers(100, 50000, n).astype(np.int32)
+    err = rng.choice(np.array([0.001, 0.002, 0.0035, 0.005, 0.01, 0.0, 0.000123], np.float32), n)
+    lam = rd * np.where(err == 0, 0.0010008, err)
+    k = np.maximum(0, np.rint(lam * rng.choice([0.0, 0.5, 1.0, 1.2, 1.5, 2.0, 3.0, 6.0], n))).astype(np.int32)
+    p, q = ctx.mutation_rules_poisson_quality_score(k, rd, err)
+    pw = np.array([pyoracle.poisson_p(a, b, c) for a, b, c in zip(k, rd, err)])
+    qw = np.array([pyoracle.poisson_q(a, b, c) for a, b, c in zip(k, rd, err)])
+    well = pw >= 1e-4
+    assert np.all(np.abs(p[well] - pw[well]) <= P_REL_TOL * pw[well])
+    assert np.all(np.abs(p[~well] - pw[~well]) <= P_ABS_QUANTA + P_REL_TOL * np.abs(pw[~well]))
+    assert np.allclose(q, qw, rtol=1e-9, atol=1e-9)
+    # err == -1 -> Q = -888 (VC:3844-3849)
+    _, q2 = ctx.mutation_rules_poisson_quality_score([5], [1000], [-1.0])
+    assert q2[0] == -888.0
+
+
+def oracle_calls(counts, pos_id, U, ref_u, thr_u, cut):
+    rows, row_off = pyoracle.dense_to_rows(synth.to_oracle_layout(counts), pos_id)
+    return pyoracle.call_variants(rows, row_off, U, ref_u, thr_u, cut), rows, row_off
+
+
+def check_calls(got, want, rows_slot):
+    """want: oracle calls (sample, row, pos_id, alt); rows_slot[sample][row] = slot of that file row."""
+    key_w = np.array([(c["sample"], rows_slot[c["sample"]][c["row"]], c["alt"]) for c in want], dtype=np.int64).reshape(-1, 3)
+    key_g = np.stack([got["sample"], got["slot"], got["alt"]], axis=1).astype(np.int64).reshape(-1, 3)
+    order = np.lexsort((key_w[:, 2], key_w[:, 1], key_w[:, 0]))
+    key_w, want = key_w[order], want[order]
+    assert key_g.shape == key_w.shape and np.array_equal(key_g, key_w), "call sets differ"
+    assert np.array_equal(got["ref"], want["ref"].astype(np.int32))
+    for side in ("fw", "bw"):
+        pg, pw = got["p_" + side], want["p_" + side]
+        well = pw >= 1e-4
+        assert np.all(np.abs(pg[well] - pw[well]) <= P_REL_TOL * pw[well])
+        assert np.all(np.abs(pg[~well] - pw[~well]) <= P_ABS_QUANTA + P_REL_TOL * pw[~well])
+        assert np.allclose(got["q_" + side], want["q_" + side], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("T,n_amp,depth,cut,seed", [
+    (3, 30, 1800, 100, 21),
+    (24, 16, 5000, 100, 22),
+    (150, 6, 2000, 100, 23),
+    (8, 10, 50000, 100, 24),
+    (5, 10, 400, 50, 25),
+])
+def test_calls_match_oracle(ctx, variant, T, n_amp, depth, cut, seed):
+    _, slots, pos_id, U = synth.make_panel(n_amp, seed=seed)
+    P = len(slots)
+    normals, ref = synth.make_counts(12, P, depth=depth, seed=seed, pos_id=pos_id)
+    tumours, _ = synth.make_counts(T, P, depth=depth, seed=seed + 1000, ref=ref, pos_id=pos_id, somatic_rate=0.01)
+    ref = ref.copy()
+    ref[::97] = 4   # 'N' / lower-case reference bases are never called (VC:3290-3293)
+    # thresholds from the oracle's noise model, through the "%f" hand-over
+    nz = oracle_noise(normals, pos_id, U, np.float32(0.002), 100)
+    thr_u = pyoracle.thr_as_caller_sees(np.where(np.isnan(nz["thr"]), np.float32(0.01), nz["thr"]))
+    thr_u[::53, 1, :] = 0.0    # err == 0 -> 0.0010008 (VC:3852-3856)
+    thr_u[::71, 2, 0] = -1.0   # err == -1 -> Q = -888, never a call (VC:3844-3849)
+    ref_u = np.zeros(U, np.uint8)
+    ref_u[pos_id] = ref
+    ref_slots = ref_u[pos_id]
+    ctx.set_call_kernel(variant)
+    try:
+        got = ctx.call_variants(tumours, ref_slots, thr_u[pos_id], cut)
+    finally:
+        ctx.set_call_kernel(1)
+    want, rows, row_off = oracle_calls(tumours, pos_id, U, ref_u, thr_u, cut)
+    present = tumours[:, 0, :, 0] != 0xFFFFFFFF
+    rows_slot = [np.nonzero(present[s])[0] for s in range(T)]
+    assert len(want) > 0
+    check_calls(got, want, rows_slot)
+
+
+def test_device_pipeline_matches_host_entry_points(ctx):
+    """_dev entry points (inputs resident in HBM, torch tensors) == _host entry points, incl. slot ranges."""
+    import torch
+    from amplisolve_b200 import calls_from_device
+    _, slots, pos_id, U = synth.make_panel(24, seed=31)
+    P = len(slots)
+    normals, ref = synth.make_counts(10, P, depth=2500, seed=31, pos_id=pos_id)
+    tumours, _ = synth.make_counts(7, P, depth=2500, seed=32, ref=ref, pos_id=pos_id, somatic_rate=0.01)
+    nxt, head = ctx_twins(pos_id)
+    host = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head)
+    d_norm = torch.from_numpy(normals.view(np.int32)).cuda()
+    out = ctx.alloc_noise_outputs(P)
+    ctx.estimate_thresholds_dev(d_norm, 0.002, 100, out, torch.from_numpy(nxt).cuda(), torch.from_numpy(head).cuda())
+    torch.cuda.synchronize()
+    for k in host:
+        a, b = out[k].cpu().numpy(), host[k]
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), k
+    view = ctx.thresholds_caller_view_dev(out["thr"])
+    host_view = pyoracle.thr_as_caller_sees(np.where(np.isnan(host["thr"]), np.float32(0.01), host["thr"]))
+    assert np.array_equal(bits(view.cpu().numpy()), bits(host_view))
+    want = ctx.call_variants(tumours, ref, host_view, 100)
+    d_tum = torch.from_numpy(tumours.view(np.int32)).cuda()
+    calls = torch.zeros(48 * 100000, dtype=torch.uint8, device="cuda")
+    n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    mid = P // 2
+    for rng_ in ((0, mid), (mid, P)):
+        ctx.call_variants_dev(d_tum, torch.from_numpy(ref).cuda(), view, 100, calls, n, slot_range=rng_)
+    got = calls_from_device(calls, n)
+    assert len(got) == len(want) > 0
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+
+
+def test_synthetic_generator_round_trip(ctx):
+    """The HBM generator (bench input) feeds both kernels; a slice is checked against the oracle."""
+    import torch
+    P, S, T = 3000, 20, 16
+    normals, ref = ctx.synth_counts_dev(S, P, seed=20181, mean_depth=2000.0, absent_rate=0.02)
+    tumours, _ = ctx.synth_counts_dev(T, P, seed=20181, mean_depth=2000.0, somatic_rate=2e-4, sample_offset=1 << 20,
+                                      absent_rate=0.02, want_ref=False)
+    out = ctx.alloc_noise_outputs(P)
+    ctx.estimate_thresholds_dev(normals, 0.002, 100, out)
+    view = ctx.thresholds_caller_view_dev(out["thr"])
+    calls = torch.zeros(48 * 200000, dtype=torch.uint8, device="cuda")
+    n = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ctx.call_variants_dev(tumours, ref, view, 100, calls, n)
+    from amplisolve_b200 import calls_from_device
+    got_calls = calls_from_device(calls, n)
+    h_norm = normals.cpu().numpy().view(np.uint32)
+    h_tum = tumours.cpu().numpy().view(np.uint32)
+    h_ref = ref.cpu().numpy()
+    pos_id = np.arange(P, dtype=np.int32)
+    want = oracle_noise(h_norm, pos_id, P, np.float32(0.002), 100)
+    got = {k: v.cpu().numpy() for k, v in out.items()}
+    got["count"] = got["count"].view(np.uint32)
+    got["nrec"] = got["nrec"].view(np.uint32)
+    check_noise(got, want, pos_id)
+    thr_u = pyoracle.thr_as_caller_sees(np.where(np.isnan(want["thr"]), np.float32(0.01), want["thr"]))
+    wcalls, _, _ = oracle_calls(h_tum, pos_id, P, h_ref, thr_u, 100)
+    present = h_tum[:, 0, :, 0] != 0xFFFFFFFF
+    check_calls(got_calls, wcalls, [np.nonzero(present[s])[0] for s in range(T)])
+    # sanity of the synthetic model itself: depth and sparsity in the intended range
+    rd = h_norm.astype(np.int64).sum(axis=(1, 3))[h_norm[:, 0, :, 0] != 0xFFFFFFFF]
+    assert 1200 < np.median(rd) < 3000

@@ -44,7 +44,8 @@ struct DevBuf {  // grow-only device scratch
 
 struct as_ctx {
     int device = 0;
-    int call_variant = 1;
+    int call_variant = AS_DEFAULT_CALL_KERNEL;   // 0 straightforward, 1 queued (direct loads), >= 2 TMA-staged (K, stages) variants
+    int noise_cfg = AS_DEFAULT_NOISE_KERNEL;      // 0 direct loads, >= 1 TMA-staged (K, stages) variants
     int64_t launches = 0;
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
@@ -119,8 +120,13 @@ int as_host_free(void* p) {
 }
 
 int as_set_call_kernel(as_ctx* c, int variant) {
-    if (!c || variant < 0 || variant > 1) return fail(AS_EINVAL, "bad call kernel variant");
-    c->call_variant = variant;
+    if (!c || variant < -1 || variant > 9) return fail(AS_EINVAL, "bad call kernel variant");
+    c->call_variant = variant < 0 ? AS_DEFAULT_CALL_KERNEL : variant;
+    return AS_OK;
+}
+int as_set_noise_kernel(as_ctx* c, int variant) {
+    if (!c || variant < -1 || variant > 6) return fail(AS_EINVAL, "bad noise kernel variant");
+    c->noise_cfg = variant < 0 ? AS_DEFAULT_NOISE_KERNEL : variant;
     return AS_OK;
 }
 int64_t as_kernel_launches(const as_ctx* c) { return c ? c->launches : 0; }
@@ -146,7 +152,7 @@ int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_
     if ((d_twin_next == nullptr) != (d_twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    CU(as_launch_noise_main(d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
+    CU(as_launch_noise_main(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
                             d_germ_state, d_count, d_nrec, st));
     c->launches += 1;
     if (d_twin_next) {
@@ -229,7 +235,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
         CU(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
         char* o = (char*)c->out[bsel].p;
         if (twin_next) CU(cudaMemsetAsync(o, 0, lay.total, c->exec_stream));  // twin members are filled in pass 2
-        CU(as_launch_noise_main((const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th, p0, C, (uint32_t)cut,
+        CU(as_launch_noise_main(c->noise_cfg, (const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th, p0, C, (uint32_t)cut,
                                 (float*)(o + lay.thr), (float*)(o + lay.germ_val), (uint8_t*)(o + lay.germ_state),
                                 (uint32_t*)(o + lay.count), (uint32_t*)(o + lay.nrec), c->exec_stream));
         c->launches += 1;

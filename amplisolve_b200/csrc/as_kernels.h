@@ -10,8 +10,10 @@
 #define AS_NOISE_THREADS 128
 #define AS_NOISE_UNROLL 4
 #define AS_CALL_THREADS 128
+#define AS_DEFAULT_CALL_KERNEL 3  /* TMA-staged, 4 samples per stage, 2 stages: best of the measured sweep */
+#define AS_DEFAULT_NOISE_KERNEL 1 /* TMA-staged, 4 samples per stage, 3 stages */
 
-cudaError_t as_launch_noise_main(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                  const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base, float C,
                                  uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
                                  uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);

@@ -114,6 +114,98 @@ __device__ __forceinline__ void noise_accumulate(NoiseAcc& a, const uint4 fw, co
     }
 }
 
+// ---- fast path of the single-pass kernel -----------------------------------------------------------
+// Same arithmetic as noise_accumulate<false> for records whose depth is below 2^24 (int -> float exact),
+// arranged for the issue budget: the depth sums ride the otherwise idle fp64 pipe (exact: integers below
+// 2^53), the alt-read sums are 32-bit (b <= 0.05 * 2^24, folded into the fp64 sum every AS_FOLD_EVERY
+// samples), the coverage gate is folded into the compare chains.  A record with depth >= 2^24 only
+// raises `big`; the caller then redoes the slot with the general code.
+#define AS_FOLD_EVERY 4096
+
+struct FastBase {
+    uint32_t s_b_fw, s_b_bw;  // 32-bit partial sums of alt reads
+    double s_d_fw, s_d_bw;    // sum of strand depth (exact in fp64)
+    double s_p_fw, s_p_bw;    // sum of float(depth)*float(C), plus the folded alt-read sums
+    uint32_t count, g_n, g_x, g_rd;
+};
+struct FastAcc {
+    FastBase b[4];
+    uint32_t nrec, big;
+};
+
+__device__ __forceinline__ void fast_init(FastAcc& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a.b[i].s_b_fw = a.b[i].s_b_bw = 0u;
+        a.b[i].s_d_fw = a.b[i].s_d_bw = a.b[i].s_p_fw = a.b[i].s_p_bw = 0.0;
+        a.b[i].count = a.b[i].g_n = a.b[i].g_x = 0u;
+        a.b[i].g_rd = 1u;
+    }
+    a.nrec = 0; a.big = 0;
+}
+
+__device__ __forceinline__ double u32_to_double(uint32_t v) {  // exact, one DADD instead of a conversion-unit op
+    return __dsub_rn(__hiloint2double(0x43300000, (int)v), 4503599627370496.0);
+}
+
+__device__ __forceinline__ void fast_fold(FastAcc& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a.b[i].s_p_fw = __dadd_rn(a.b[i].s_p_fw, u32_to_double(a.b[i].s_b_fw));
+        a.b[i].s_p_bw = __dadd_rn(a.b[i].s_p_bw, u32_to_double(a.b[i].s_b_bw));
+        a.b[i].s_b_fw = a.b[i].s_b_bw = 0u;
+    }
+}
+
+__device__ __forceinline__ void fast_accumulate(FastAcc& a, const uint4 fw, const uint4 bw, const float C,
+                                                const uint32_t cut) {
+    if ((int32_t)fw.x < 0) return;  // AS_ABSENT
+    a.nrec += 1;
+    const uint32_t FW = fw.x + fw.y + fw.z + fw.w;
+    const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
+    const uint32_t RD = FW + BW;
+    a.big |= RD;
+    const bool cov = min(FW, BW) >= cut;
+    const uint32_t lim_fw = af_limit(FW), lim_bw = af_limit(BW), lim_rd = af_limit(RD);
+    const double d_fw = u32_to_double(FW), d_bw = u32_to_double(BW);
+    const double p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);
+    const double p_bw = (double)__fmul_rn(__uint2float_rn(BW), C);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        FastBase& s = a.b[i];
+        const uint32_t bf = comp(fw, i), bb = comp(bw, i);
+        const bool keep = cov && bf <= lim_fw && bb <= lim_bw;
+        if (keep) {
+            s.s_b_fw += bf; s.s_b_bw += bb;
+            s.s_d_fw = __dadd_rn(s.s_d_fw, d_fw); s.s_d_bw = __dadd_rn(s.s_d_bw, d_bw);
+            s.s_p_fw = __dadd_rn(s.s_p_fw, p_fw); s.s_p_bw = __dadd_rn(s.s_p_bw, p_bw);
+            s.count += 1;
+        }
+        const uint32_t x = bf + bb;
+        const bool qual = cov && x <= lim_rd;
+        // bitwise &, not &&: both products are always formed so that the update is predicated, not branched
+        const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * RD;
+        const bool upd = qual & (s.g_n != 0) & ge;
+        s.g_x = upd ? x : s.g_x;
+        s.g_rd = upd ? RD : s.g_rd;
+        s.g_n += qual ? 1u : 0u;
+    }
+}
+
+__device__ __forceinline__ void fast_to_general(const FastAcc& f, NoiseAcc& a) {
+    a.nrec = f.nrec;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const FastBase& s = f.b[i];
+        NoiseBase& d = a.b[i];
+        d.s_b_fw = s.s_b_fw; d.s_b_bw = s.s_b_bw;
+        d.s_d_fw = (unsigned long long)__double2ll_rn(s.s_d_fw); d.s_d_bw = (unsigned long long)__double2ll_rn(s.s_d_bw);
+        d.s_p_fw = s.s_p_fw; d.s_p_bw = s.s_p_bw;
+        d.count = s.count; d.g_n = s.g_n; d.g_x = s.g_x; d.g_rd = s.g_rd;
+        d.g_first_x = 0; d.g_first_rd = 1;
+    }
+}
+
 // Merge the state R of a LATER record segment into L (earlier).  Associative.
 __device__ __forceinline__ void noise_merge(NoiseAcc& L, const NoiseAcc& R) {
     L.nrec += R.nrec;

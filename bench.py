@@ -45,7 +45,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--call-kernel", type=int, default=1, help="1 = queued (default), 0 = straightforward")
+    ap.add_argument("--call-kernel", type=int, default=3, help="include/amplisolve_b200.h as_set_call_kernel")
+    ap.add_argument("--noise-kernel", type=int, default=1, help="include/amplisolve_b200.h as_set_noise_kernel")
     return ap.parse_args()
 
 
@@ -249,6 +250,7 @@ def run_ours(args):
     dev = torch.device(f"cuda:{local}")
     ctx = Context(local)
     ctx.set_call_kernel(args.call_kernel)
+    ctx.set_noise_kernel(args.noise_kernel)
     P, S, T = args.slots, args.normals, args.tumours
     C, cut = WORKLOAD["C_value"], WORKLOAD["coverage_cutoff"]
 
@@ -335,14 +337,14 @@ def run_ours(args):
                        "normals": S, "tumours": T, "depth": WORKLOAD["depth"], "C_value": C, "coverage_cutoff": cut,
                        "sharding": f"positions x{world}, no collective on the data path",
                        "l2": "inputs (6.4 GB normals + 32 GB tumours per step) far larger than the 126 MB L2",
-                       "calls_per_step_rank0": found, "call_kernel": "queued" if args.call_kernel else "straightforward"},
+                       "calls_per_step_rank0": found, "call_kernel_variant": args.call_kernel, "noise_kernel_variant": args.noise_kernel},
             "noise_positions_per_s": P * world / (t_noise_max * 1e-3),
             "kernel_ms": {"noise_model": t_noise_max, "caller": t_call_max},
-            "roofline": {"bound": "hbm", "kernel": "call_queued_kernel" if args.call_kernel else "call_naive_kernel",
+            "roofline": {"bound": "hbm", "kernel": {0: "call_naive_kernel", 1: "call_queued_kernel"}.get(args.call_kernel, "call_staged_kernel"),
                          "achieved": call_bytes / (t_call * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": call_bytes},
-            "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
+            "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel" if args.noise_kernel == 0 else "noise_staged_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": noise_bytes / (t_noise * 1e-3) / 1e9 / peak,
                                "traffic": None, "algorithmic_bytes": noise_bytes},
             "gpu_launches": int(launches * world), "clocks": clocks,

@@ -78,8 +78,12 @@ void as_destroy(as_ctx* ctx);
 /* Pinned host memory for the _host entry points (cudaHostAlloc / cudaFreeHost). */
 int as_host_alloc(void** out, size_t bytes);
 int as_host_free(void* p);
-/* 0 = straightforward caller kernel (cross-check), 1 = queued caller kernel (default). */
+/* Kernel variants (the tests cross-check them against each other and the oracle; -1 = default):
+ *   caller: 0 = straightforward, 1 = per-warp queues over direct loads, 2..9 = TMA-staged with
+ *           (samples per stage, stages) = (4,3), (4,2) default, (4,4), (8,2), (8,3), (2,2), (2,3), (2,4)
+ *   noise : 0 = direct loads, 1..6 = TMA-staged with (4,3) default, (4,4), (2,4), (8,2), (8,3), (4,2) */
 int as_set_call_kernel(as_ctx* ctx, int variant);
+int as_set_noise_kernel(as_ctx* ctx, int variant);
 /* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
 int64_t as_kernel_launches(const as_ctx* ctx);
 

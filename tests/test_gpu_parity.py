@@ -49,12 +49,17 @@ def check_noise(got, want, pos_id):
     (100, 8, 2000, 0.0035, 150, 16),
     (20, 10, 160, 0.002, 100, 17),   # marginal coverage: the 0.338*N rule decides
 ])
-def test_noise_matches_oracle(ctx, S, n_amp, depth, C, cut, seed):
+@pytest.mark.parametrize("variant", [1, 0, 3, 4])
+def test_noise_matches_oracle(ctx, variant, S, n_amp, depth, C, cut, seed):
     _, slots, pos_id, U = synth.make_panel(n_amp, seed=seed)
     P = len(slots)
     counts, _ = synth.make_counts(S, P, depth=depth, seed=seed, pos_id=pos_id)
     nxt, head = ctx_twins(pos_id)
-    got = ctx.estimate_thresholds(counts, C, cut, nxt, head)
+    ctx.set_noise_kernel(variant)
+    try:
+        got = ctx.estimate_thresholds(counts, C, cut, nxt, head)
+    finally:
+        ctx.set_noise_kernel(-1)
     want = oracle_noise(counts, pos_id, U, np.float32(C), cut)
     check_noise(got, want, pos_id)
 
@@ -179,7 +184,7 @@ def check_calls(got, want, rows_slot):
         assert np.allclose(got["q_" + side], want["q_" + side], rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("variant", [1, 0])
+@pytest.mark.parametrize("variant", [3, 2, 1, 0, 5, 7])
 @pytest.mark.parametrize("T,n_amp,depth,cut,seed", [
     (3, 30, 1800, 100, 21),
     (24, 16, 5000, 100, 22),
@@ -206,7 +211,7 @@ def test_calls_match_oracle(ctx, variant, T, n_amp, depth, cut, seed):
     try:
         got = ctx.call_variants(tumours, ref_slots, thr_u[pos_id], cut)
     finally:
-        ctx.set_call_kernel(1)
+        ctx.set_call_kernel(-1)
     want, rows, row_off = oracle_calls(tumours, pos_id, U, ref_u, thr_u, cut)
     present = tumours[:, 0, :, 0] != 0xFFFFFFFF
     rows_slot = [np.nonzero(present[s])[0] for s in range(T)]

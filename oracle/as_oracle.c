@@ -198,6 +198,17 @@ long double aso_poisson_q_ld(int k, int rd, float err) {
 
 double aso_poisson_q(int k, int rd, float err) { return (double)aso_poisson_q_ld(k, rd, err); }
 
+/* The long double Q the reference derives from a double p (VC:3868-3882), and its comparison with 5 (VC:898). */
+static long double q_from_p_ld(double p) {
+    long double pvalue = p;
+    long double p_limit = 0.0000000001;
+    if (pvalue < p_limit) return -10 * log10l(p_limit);
+    if (pvalue == 1) return 0;
+    return -10 * log10l(pvalue);
+}
+int aso_q_at_least(double p, int threshold) { return q_from_p_ld(p) >= threshold; }
+double aso_q_from_p(double p) { return (double)q_from_p_ld(p); }
+
 /* two-sided Fisher exact test as VC:3797-3814, over the stand-in hypergeometric pdf */
 static double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
 static double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {

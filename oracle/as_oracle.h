@@ -55,6 +55,8 @@ double aso_poisson_p(int k, int rd, float err);            /* the double p of VC
 long double aso_poisson_q_ld(int k, int rd, float err);    /* VC:3834-3884 */
 double aso_poisson_q(int k, int rd, float err);            /* (double) of the above */
 double aso_fisher(int a, int b, int c, int d);             /* VC:3797-3814 over the Boost stand-in pdf */
+int aso_q_at_least(double p, int threshold);               /* (long double)Q(p) >= threshold, VC:3868-3882 + VC:898 / VC:1023 */
+double aso_q_from_p(double p);                             /* (double) of that long double Q */
 
 typedef struct {
     int32_t sample;   /* index into the sample list as given */

@@ -42,6 +42,10 @@ def lib():
             f = getattr(L, name)
             f.restype = C.c_double
             f.argtypes = [C.c_int, C.c_int, C.c_float]
+        L.aso_q_at_least.restype = C.c_int
+        L.aso_q_at_least.argtypes = [C.c_double, C.c_int]
+        L.aso_q_from_p.restype = C.c_double
+        L.aso_q_from_p.argtypes = [C.c_double]
         L.aso_fisher.restype = C.c_double
         L.aso_fisher.argtypes = [C.c_int] * 4
         L.aso_thr_as_caller_sees.restype = C.c_float
@@ -138,6 +142,14 @@ def poisson_p(k, rd, err):
 
 def poisson_q(k, rd, err):
     return lib().aso_poisson_q(int(k), int(rd), float(np.float32(err)))
+
+
+def q_at_least(p, threshold=5) -> bool:
+    return bool(lib().aso_q_at_least(float(p), int(threshold)))
+
+
+def q_from_p(p) -> float:
+    return lib().aso_q_from_p(float(p))
 
 
 def fisher(a, b, c, d):

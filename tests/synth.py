@@ -47,6 +47,10 @@ def make_counts(n_samples, P, *, depth=2000, seed=2, ref=None, pos_id=None, soma
     rng = np.random.default_rng(seed)
     if ref is None:
         ref = rng.integers(0, 4, size=P).astype(np.uint8)
+        if pos_id is not None:  # one reference base per position: twin slots share it
+            first_of: dict = {}
+            for p in range(P):
+                ref[p] = ref[first_of.setdefault(int(pos_id[p]), p)]
     err = np.where(rng.random((P, 2, 4)) < 0.6, 0.0, np.minimum(0.02, 3e-4 * np.exp(rng.normal(size=(P, 2, 4)))))
     snp = rng.random(P) < 0.01
     snp_alt = (ref + 1 + rng.integers(0, 3, size=P)) % 4
@@ -67,7 +71,9 @@ def make_counts(n_samples, P, *, depth=2000, seed=2, ref=None, pos_id=None, soma
             som = rng.random(P) < somatic_rate
             alt = (ref + 1 + rng.integers(0, 3, size=P)) % 4
             vaf[som, alt[som]] = np.maximum(vaf[som, alt[som]], rng.uniform(0.01, 0.2, size=int(som.sum())))
-        rate = np.minimum(1.0, err + vaf[:, None, :])         # [P][2][4]
+        # a third of the variants are strand-biased (exercises the Fisher flag, VC:902-910)
+        strand_f = np.where(rng.random((P, 2, 1)) < 0.33, rng.uniform(0.25, 1.0, (P, 2, 1)), 1.0)
+        rate = np.minimum(1.0, err + vaf[:, None, :] * strand_f)   # [P][2][4]
         rate[np.arange(P), :, ref] = 0.0
         c = np.zeros((2, P, 4), dtype=np.int64)
         for t in range(2):

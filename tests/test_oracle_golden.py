@@ -1,0 +1,169 @@
+"""CPU tests: the oracle (oracle/liboracle.so) against the golden vectors generated from the real reference
+(tests/golden/make_golden.py), and, where oracle/_ref exists (dev container), against the reference live."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle, refrun
+from tests import golden_util as gu
+
+ROOT = Path(__file__).resolve().parent.parent
+P_STAR = np.frombuffer(np.uint64(0x3FD43D136248490E).tobytes(), dtype=np.float64)[0]
+
+
+@pytest.fixture(scope="module")
+def grid():
+    return np.load(gu.GOLDEN / "vc_function_grid.npz")
+
+
+def test_kf_gammaq_bitwise(grid):
+    got = np.array([pyoracle.kf_gammaq(s, z) for s, z in zip(grid["gq_s"], grid["gq_z"])])
+    assert np.array_equal(got.view(np.uint64), grid["gq"].view(np.uint64))
+
+
+def test_q_score_bitwise(grid):
+    got = np.array([pyoracle.poisson_q(k, rd, e) for k, rd, e in zip(grid["q_k"], grid["q_rd"], grid["q_err"])])
+    assert np.array_equal(got.view(np.uint64), grid["q"].view(np.uint64))
+    assert (grid["q"] == -888).sum() > 100 and (grid["q"] == 100).sum() > 100 and (grid["q"] == 0).sum() > 100
+
+
+def test_call_decisions_and_the_p_star_threshold(grid):
+    """VC:898 as a predicate on the double p: Q >= 5 <=> p <= P_STAR (what the device evaluates)."""
+    g = grid
+    want = g["d_call"].astype(bool)
+    dec = np.empty(len(want), bool)
+    for i in range(len(want)):
+        pf = pyoracle.poisson_p(g["d_kfw"][i], g["d_fw"][i], g["d_efw"][i])
+        pb = pyoracle.poisson_p(g["d_kbw"][i], g["d_bw"][i], g["d_ebw"][i])
+        dec[i] = (g["d_fw"][i] >= 100 and g["d_bw"][i] >= 100 and pf <= P_STAR and pb <= P_STAR)
+    assert np.array_equal(dec, want)
+    # the threshold itself: P_STAR is the largest double whose x87 long double Q is >= 5
+    assert pyoracle.q_at_least(P_STAR, 5) and not pyoracle.q_at_least(np.nextafter(P_STAR, 1.0), 5)
+    # plain fp64 log10 would accept one more double: the reason the device compares p, not Q
+    assert -10 * np.log10(np.nextafter(P_STAR, 1.0)) >= 5
+
+
+def test_fisher_standin(grid):
+    got = np.array([pyoracle.fisher(a, b, c, d) for a, b, c, d in zip(grid["f_a"], grid["f_b"], grid["f_c"], grid["f_d"])])
+    assert np.allclose(got, grid["f_p"], rtol=1e-12, atol=0)
+
+
+def oracle_on_case(case):
+    from tests import synth
+    normals = case["normals"][case["normal_order"]]
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(normals), case["pos_id"])
+    nz = pyoracle.noise_estimate(rows, off, case["U"], np.float32(case["c_value"]), int(case["cutoff"]))
+    return nz
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_noise_table_text_identical(name):
+    case = gu.load(name)
+    nz = oracle_on_case(case)
+    pid = case["pos_id"]
+    lines = gu.noise_table_lines(case, nz["thr"][pid], nz["germ_val"][pid], nz["germ_present"][pid])
+    want = case["noise_table"].splitlines()
+    assert len(lines) == len(want)
+    bad = [i for i, (a, b) in enumerate(zip(lines, want)) if a != b]
+    assert not bad, (bad[:5], lines[bad[0]], want[bad[0]])
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_call_rows_identical(name):
+    from tests import synth
+    case = gu.load(name)
+    order = case["tumour_order"]
+    tumours = case["tumours"][order]
+    thr_slots = gu.parse_noise_thresholds(case)
+    thr_u = np.zeros((case["U"], 4, 2), np.float32)
+    thr_u[case["pos_id"]] = thr_slots
+    ref_u = np.full(case["U"], 255, np.uint8)
+    ref_u[case["pos_id"]] = case["ref_code"]
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(tumours), case["pos_id"])
+    calls = pyoracle.call_variants(rows, off, case["U"], ref_u, thr_u, int(case["cutoff"]))
+    want = gu.golden_call_rows(case)
+    assert len(calls) == len(want)
+    present = tumours[:, 0, :, 0] != 0xFFFFFFFF
+    rows_slot = [np.nonzero(present[s])[0] for s in range(len(order))]
+    first = True
+    for c, w in zip(calls, want):
+        slot = rows_slot[c["sample"]][c["row"]]
+        chrom, pos = case["slots"][slot]
+        got = (case["tumour_names"][order[c["sample"]]], chrom, pos, "ACGT"[c["ref"]], "ACGT"[c["alt"]],
+               int(c["FW"] + c["BW"]), int(c["FW"]), int(c["BW"]), int(c["k_fw"]), int(c["k_bw"]),
+               gu.fmt_g(c["q_fw"]), gu.fmt_g(c["q_bw"]), gu.fmt_g(c["fisher_p"], 6 if first else 4))
+        assert got == w
+        first = False
+
+
+def test_hash_iteration_order_matches_observed_toy_order():
+    """with germline_dir=N the reference visits N5,N3,N2,N4,N1; with tumour_dir=T: T3,T2,T1."""
+    n = [f"N/N{i}.PILEUP.ASEQ" for i in range(1, 6)]
+    assert [n[i][2:4] for i in pyoracle.hash_iteration_order(n)] == ["N5", "N3", "N2", "N4", "N1"]
+    t = [f"T/T{i}.PILEUP.ASEQ" for i in range(1, 4)]
+    assert [t[i][2:4] for i in pyoracle.hash_iteration_order(t)] == ["T3", "T2", "T1"]
+
+
+needs_ref = pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "libvc_ref_funcs.so").exists(),
+                               reason="oracle/_ref is only built where /root/reference exists")
+
+
+@needs_ref
+def test_live_reference_grids():
+    """Larger random grids against the compiled reference itself (dev container only)."""
+    L = C.CDLL(str(ROOT / "oracle" / "_ref" / "libvc_ref_funcs.so"))
+    rng = np.random.default_rng(99)
+    n = 200000
+    s = rng.integers(1, 30000, n).astype(np.float64)
+    z = s * np.exp(rng.normal(scale=0.5, size=n))
+    want = np.empty(n)
+    L.ref_kf_gammaq_vec(s.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), want.ctypes.data_as(C.c_void_p), C.c_long(n))
+    kf = pyoracle.lib().aso_kf_gammaq
+    got = np.array([kf(a, b) for a, b in zip(s[:40000], z[:40000])])
+    assert np.array_equal(got.view(np.uint64), want[:40000].view(np.uint64))
+
+
+@needs_ref
+def test_screen_continued_fraction_branch_never_calls():
+    """SURVEY.md B.6(3), the screen both caller kernels rely on: whenever kf_gammaq takes the continued-fraction
+    branch (m >= k and m > 1, VC:3728) the reference's Q stays below 5 -- including where the 99-step cap leaves
+    the fraction unconverged.  Checked against the compiled reference on a dense grid."""
+    L = C.CDLL(str(ROOT / "oracle" / "_ref" / "libvc_ref_funcs.so"))
+    rng = np.random.default_rng(7)
+    ks = np.unique(np.concatenate([np.arange(1, 400), np.geomspace(400, 2_000_000, 1500).astype(np.int64),
+                                   rng.integers(1, 200000, 3000)]))
+    ratios = np.concatenate([[1.0, 1.0 + 1e-12, 1.0 + 1e-9, 1.0 + 1e-7, 1.00001, 1.0001, 1.001, 1.003, 1.01, 1.02, 1.05,
+                              1.1, 1.2, 1.5, 2.0, 3.0, 10.0, 100.0], 1.0 + np.geomspace(1e-6, 1.0, 40)])
+    s = np.repeat(ks.astype(np.float64), len(ratios))
+    z = s * np.tile(ratios, len(ks))
+    keep = (z >= s) & (z > 1.0)
+    s, z = s[keep], z[keep]
+    out = np.empty(len(s))
+    L.ref_kf_gammaq_vec(s.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_long(len(s)))
+    p = 1.0 - out
+    assert len(s) > 250000
+    assert np.all(p > P_STAR), (s[p <= P_STAR][:5], z[p <= P_STAR][:5])
+    assert p.min() > 0.49
+
+
+@needs_ref
+def test_toy_data_end_to_end_against_reference(tmp_path):
+    """BASELINE.json configs[0]: the whole of Toy_data through the compiled reference and through the oracle."""
+    from tests import aseq_io, synth
+    info = refrun.stage_toy(tmp_path)
+    noise_path, _ = refrun.run_ee_ref(tmp_path, "panel.bed", info["ref"], info["dup"], "N", "0.002", "100")
+    want = noise_path.read_text().splitlines()
+    slots = info["slots"]
+    where, pos_id, U = aseq_io.slot_index(slots)
+    P = len(slots)
+    names = sorted(p.name for p in (tmp_path / "N").glob("*.ASEQ"))
+    order = pyoracle.hash_iteration_order([f"N/{n}" for n in names])
+    normals = np.stack([aseq_io.read_aseq_dense(tmp_path / "N" / names[i], where, P)[0] for i in order])
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(normals), pos_id)
+    nz = pyoracle.noise_estimate(rows, off, U, np.float32(0.002), 100)
+    case = {"slots": slots, "ref_letters": "".join(info["refmap"][k] for k in slots)}
+    lines = gu.noise_table_lines(case, nz["thr"][pos_id], nz["germ_val"][pos_id], nz["germ_present"][pos_id])
+    assert lines == want
+    assert len(want) == 41487

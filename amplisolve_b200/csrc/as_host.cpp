@@ -1,11 +1,475 @@
-// Host side of the two programs: text formats, libstdc++ hash-order emulation, per-call annotations
-// and the argv-compatible mains.  (Round 1: hash order only; loaders/writers/mains follow.)
+// Host side of the two drop-in programs: text formats in and out, the libstdc++ hash-order emulation the
+// reference's outputs depend on, per-call annotations (Fisher strand bias, 10-mers, homopolymer, flags)
+// and the argv-compatible mains.  All arithmetic of the hot path (noise model, Poisson tests, call
+// decision) happens on the GPU through the C ABI in as_capi.cu; nothing here evaluates it on the CPU.
+//
+//   EE = source_codes/AmpliSolveErrorEstimation.cpp, VC = source_codes/AmpliSolveVariantCalling.cpp
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <dirent.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <clocale>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
 #include <string>
+#include <thread>
 #include <unordered_map>
+#include <vector>
 
 #include "../../include/amplisolve_b200.h"
+
+namespace {
+
+const char* GREEN = "\x1b[32m";
+const char* RED = "\x1b[31m";
+const char* YELLOW = "\x1b[33m";
+const char* RESET = "\x1b[0m";
+const char* STARS =
+    "************************************************************************************************************************************";
+
+// ---------------------------------------------------------------------------------------------------
+// panel: the slots of the BED enumeration (EE) or of the noise table (VC), with twin links
+// ---------------------------------------------------------------------------------------------------
+struct Panel {
+    std::vector<std::string> chroms;
+    std::unordered_map<std::string, int32_t> chrom_idx;
+    std::vector<int32_t> slot_chrom, slot_pos;
+    std::vector<std::string> pos_text;  // VC prints the position text of the ASEQ row; kept for the noise-table route
+    std::vector<std::string> ref;       // reference text per slot
+    std::vector<uint8_t> dup;           // position enumerated at least twice (EE:664) / flagged YES (VC:514)
+    std::vector<int32_t> twin_next, twin_head;
+    std::unordered_map<uint64_t, int32_t> first_slot;
+    bool has_twins = false;
+
+    int32_t chrom_id(const std::string& c) {
+        auto it = chrom_idx.find(c);
+        if (it != chrom_idx.end()) return it->second;
+        const int32_t id = (int32_t)chroms.size();
+        chroms.push_back(c);
+        chrom_idx.emplace(c, id);
+        return id;
+    }
+    int32_t find_chrom(const char* c, size_t n) const {
+        auto it = chrom_idx.find(std::string(c, n));
+        return it == chrom_idx.end() ? -1 : it->second;
+    }
+    static uint64_t key(int32_t chrom, int32_t pos) { return ((uint64_t)(uint32_t)chrom << 32) | (uint32_t)pos; }
+    int64_t size() const { return (int64_t)slot_pos.size(); }
+    void add_slot(int32_t chrom, int32_t pos) {
+        slot_chrom.push_back(chrom);
+        slot_pos.push_back(pos);
+    }
+    // twin links: slots of the same position chained in panel order
+    void link() {
+        const int64_t P = size();
+        twin_next.assign(P, -1);
+        twin_head.resize(P);
+        std::unordered_map<uint64_t, int32_t> last;
+        last.reserve(P * 2);
+        first_slot.reserve(P * 2);
+        for (int64_t i = 0; i < P; ++i) {
+            const uint64_t k = key(slot_chrom[i], slot_pos[i]);
+            auto it = last.find(k);
+            if (it == last.end()) {
+                twin_head[i] = (int32_t)i;
+                first_slot.emplace(k, (int32_t)i);
+                last.emplace(k, (int32_t)i);
+            } else {
+                twin_next[it->second] = (int32_t)i;
+                twin_head[i] = twin_head[it->second];
+                it->second = (int32_t)i;
+                has_twins = true;
+            }
+        }
+    }
+    int32_t lookup(int32_t chrom, int32_t pos) const {
+        auto it = first_slot.find(key(chrom, pos));
+        return it == first_slot.end() ? -1 : it->second;
+    }
+};
+
+bool read_file(const std::string& path, std::string& out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = n > 0 ? fread(&out[0], 1, (size_t)n, f) : 0;
+    fclose(f);
+    out.resize(got);
+    return true;
+}
+
+inline const char* skip_ws(const char* p, const char* e) {
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\r')) ++p;
+    return p;
+}
+inline const char* token_end(const char* p, const char* e) {
+    while (p < e && *p != ' ' && *p != '\t' && *p != '\r' && *p != '\n') ++p;
+    return p;
+}
+
+// BED: chrom start end [...], whitespace separated, both ends inclusive (EE:633-637, EE:2595-2606)
+bool load_bed(const std::string& path, Panel& panel, int& n_amplicons) {
+    std::string text;
+    if (!read_file(path, text)) return false;
+    n_amplicons = 0;
+    const char* p = text.data();
+    const char* e = p + text.size();
+    while (p < e) {
+        const char* eol = (const char*)memchr(p, '\n', e - p);
+        if (!eol) eol = e;
+        const char* q = skip_ws(p, eol);
+        const char* t = token_end(q, eol);
+        if (t > q) {
+            std::string chrom(q, t);
+            char* endp = nullptr;
+            const long s = strtol(t, &endp, 10);
+            const long en = strtol(endp, &endp, 10);
+            if (endp > t) {
+                ++n_amplicons;
+                const int32_t c = panel.chrom_id(chrom);
+                for (long idx = s; idx <= en; ++idx) panel.add_slot(c, (int32_t)idx);
+            }
+        }
+        p = eol + 1;
+    }
+    return true;
+}
+
+// Reference bases straight from the .fai-indexed FASTA: the base samtools faidx <fa> chr:p-p prints (EE:644),
+// without one fork per position.
+struct FaiEntry { long long len, off, linebases, linewidth; };
+bool annotate_reference(const std::string& fasta, Panel& panel, std::string& err) {
+    std::string fai;
+    if (!read_file(fasta + ".fai", fai)) { err = "cannot open " + fasta + ".fai (index the FASTA with samtools faidx)"; return false; }
+    std::unordered_map<std::string, FaiEntry> idx;
+    {
+        const char* p = fai.data();
+        const char* e = p + fai.size();
+        while (p < e) {
+            const char* eol = (const char*)memchr(p, '\n', e - p);
+            if (!eol) eol = e;
+            const char* t = (const char*)memchr(p, '\t', eol - p);
+            if (t) {
+                FaiEntry en;
+                if (sscanf(t + 1, "%lld\t%lld\t%lld\t%lld", &en.len, &en.off, &en.linebases, &en.linewidth) == 4 && en.linebases > 0)
+                    idx.emplace(std::string(p, t), en);
+            }
+            p = eol + 1;
+        }
+    }
+    const int fd = open(fasta.c_str(), O_RDONLY);
+    if (fd < 0) { err = "cannot open " + fasta; return false; }
+    const int64_t P = panel.size();
+    panel.ref.resize(P);
+    for (int64_t i = 0; i < P; ++i) {
+        const std::string& c = panel.chroms[panel.slot_chrom[i]];
+        auto it = idx.find(c);
+        const long long pos = panel.slot_pos[i];
+        if (it == idx.end() || pos < 1 || pos > it->second.len) {
+            close(fd);
+            err = "region " + c + ":" + std::to_string(pos) + " is not in " + fasta;
+            return false;
+        }
+        const FaiEntry& en = it->second;
+        const long long off = en.off + (pos - 1) / en.linebases * en.linewidth + (pos - 1) % en.linebases;
+        char b = 'N';
+        if (pread(fd, &b, 1, (off_t)off) != 1) { close(fd); err = "short read in " + fasta; return false; }
+        panel.ref[i] = std::string(1, b);
+    }
+    close(fd);
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// file lists in the reference's order: `ls <dir>/*.ASEQ` (EE:556, VC:391) inserted into an unordered_map
+// keyed by the listed path (EE:832), then iterated (EE:1081, VC:672)
+// ---------------------------------------------------------------------------------------------------
+struct CountFile { std::string path, sample; };
+
+bool list_count_files(const std::string& dir, std::vector<CountFile>& files, std::vector<std::string>& listed) {
+    DIR* d = opendir(dir.c_str());
+    if (!d) return false;
+    std::vector<std::string> names;
+    while (dirent* en = readdir(d)) {
+        const std::string n = en->d_name;
+        if (n.size() >= 5 && n.compare(n.size() - 5, 5, ".ASEQ") == 0 && n[0] != '.') names.push_back(n);
+    }
+    closedir(d);
+    setlocale(LC_COLLATE, "");
+    std::sort(names.begin(), names.end(), [](const std::string& a, const std::string& b) {
+        const int c = strcoll(a.c_str(), b.c_str());
+        return c != 0 ? c < 0 : a < b;
+    });
+    std::unordered_map<std::string, std::string> hash;  // exactly the container of EE:832 / VC:615
+    for (const std::string& n : names) {
+        const std::string path = dir + "/" + n;
+        listed.push_back(path);
+        // sample name = listed path minus "<dir>/" and the 12 characters of ".PILEUP.ASEQ" (EE:831)
+        std::string sample = n.size() > 12 ? n.substr(0, n.size() - 12) : std::string();
+        hash.insert(std::make_pair(path, sample));
+    }
+    for (auto it = hash.begin(); it != hash.end(); ++it) files.push_back(CountFile{it->first, it->second});
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// .PILEUP.ASEQ -> dense counts of one sample (EE:1114-1176, VC:723-770)
+// ---------------------------------------------------------------------------------------------------
+struct AseqStats { int64_t rows = 0, outside = 0, extra = 0, bad_rd = 0; bool ok = true; };
+
+inline bool parse_int(const char*& p, const char* e, long long& v) {
+    p = skip_ws(p, e);
+    bool neg = false;
+    if (p < e && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+    if (p >= e || *p < '0' || *p > '9') return false;
+    long long x = 0;
+    while (p < e && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+    v = neg ? -x : x;
+    return true;
+}
+
+// counts: this sample's plane pair, [2][P][4]; row_of (optional) [P] file row index of each filled slot
+AseqStats load_aseq(const std::string& path, const Panel& panel, uint32_t* counts, int32_t* row_of) {
+    AseqStats st;
+    std::string text;
+    if (!read_file(path, text)) { st.ok = false; return st; }
+    const int64_t P = panel.size();
+    std::vector<uint8_t> seen;  // occurrences of a twinned position in this file
+    if (panel.has_twins) seen.assign(P, 0);
+    const char* p = text.data();
+    const char* e = p + text.size();
+    const char* eol = (const char*)memchr(p, '\n', e - p);  // first line is the header (EE:1113)
+    p = eol ? eol + 1 : e;
+    int32_t last_chrom = -1;
+    std::string last_name;
+    while (p < e) {
+        eol = (const char*)memchr(p, '\n', e - p);
+        if (!eol) eol = e;
+        const char* q = skip_ws(p, eol);
+        const char* t = token_end(q, eol);
+        if (t > q) {
+            const int64_t row = st.rows++;
+            if (last_chrom < 0 || last_name.size() != (size_t)(t - q) || memcmp(last_name.data(), q, t - q) != 0) {
+                last_name.assign(q, t);
+                last_chrom = panel.find_chrom(q, t - q);
+                if (last_chrom < 0) last_chrom = -2;
+            }
+            const char* r = t;
+            long long pos = 0, v[9];
+            bool ok = parse_int(r, eol, pos);
+            for (int k = 0; k < 4 && ok; ++k) { r = skip_ws(r, eol); r = token_end(r, eol); }  // dbsnp MAF ref alt
+            for (int k = 0; k < 9 && ok; ++k) ok = parse_int(r, eol, v[k]);
+            if (ok) {
+                int32_t slot = last_chrom >= 0 ? panel.lookup(last_chrom, (int32_t)pos) : -1;
+                if (slot >= 0 && panel.has_twins && panel.twin_next[slot] >= 0) {
+                    const int k = seen[slot]++;
+                    for (int j = 0; j < k && slot >= 0; ++j) slot = panel.twin_next[slot];
+                    if (slot < 0) ++st.extra;
+                } else if (slot >= 0 && counts[(int64_t)slot * 4] != AS_ABSENT) {
+                    slot = -1;  // a second row for a position that owns one slot
+                    ++st.extra;
+                } else if (slot < 0) {
+                    ++st.outside;
+                }
+                if (slot >= 0) {
+                    // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
+                    if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
+                    uint32_t* fw = counts + (int64_t)slot * 4;
+                    uint32_t* bw = counts + ((int64_t)P + slot) * 4;
+                    for (int b = 0; b < 4; ++b) {
+                        fw[b] = (uint32_t)(v[b] - v[5 + b]);
+                        bw[b] = (uint32_t)v[5 + b];
+                    }
+                    if (row_of) row_of[slot] = (int32_t)row;
+                }
+            }
+        }
+        p = eol + 1;
+    }
+    return st;
+}
+
+// all samples, in the given order, into one pinned tensor [n][2][P][4]
+bool load_all(const std::vector<CountFile>& files, const Panel& panel, uint32_t* counts, int32_t* row_of,
+              std::vector<AseqStats>& stats) {
+    const int n = (int)files.size();
+    const int64_t P = panel.size();
+    stats.assign(n, AseqStats());
+    std::atomic<int> next(0);
+    auto work = [&]() {
+        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
+            uint32_t* plane = counts + (int64_t)i * 2 * P * 4;
+            memset(plane, 0xFF, (size_t)P * 32);
+            stats[i] = load_aseq(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr);
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n)));
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    for (const AseqStats& s : stats)
+        if (!s.ok) return false;
+    return true;
+}
+
+bool make_dir(const std::string& path) {  // mkdir -p (EE:3079)
+    std::string cur;
+    for (size_t i = 0; i <= path.size(); ++i) {
+        if (i == path.size() || path[i] == '/') {
+            if (!cur.empty() && cur != "." && cur != "..") mkdir(cur.c_str(), 0777);
+        }
+        if (i < path.size()) cur.push_back(path[i]);
+    }
+    struct stat sb;
+    return stat(path.c_str(), &sb) == 0 && S_ISDIR(sb.st_mode);
+}
+
+std::string arg_value(const char* arg, const char* key) {  // sscanf(arg, "key=%s", out) of EE:300-326
+    const size_t n = strlen(key);
+    if (strncmp(arg, key, n) != 0) return std::string();
+    const char* p = arg + n;
+    while (*p == ' ' || *p == '\t' || *p == '\n') ++p;
+    const char* q = p;
+    while (*q && *q != ' ' && *q != '\t' && *q != '\n') ++q;
+    return std::string(p, q);
+}
+
+struct Pinned {
+    void* p = nullptr;
+    ~Pinned() { if (p) as_host_free(p); }
+    bool alloc(size_t bytes) { return as_host_alloc(&p, bytes ? bytes : 16) == AS_OK; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// per-call annotations (host only: these run for called variants, a vanishing fraction of the records)
+// ---------------------------------------------------------------------------------------------------
+// two-sided Fisher exact test as VC:3797-3814.  Boost.Math 1.61 is not part of the reference tree
+// (.MISSING_LARGE_BLOBS); the pdf is C(r,k) C(N-r,n-k) / C(N,n) through lgamma, like the oracle's stand-in.
+double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {
+    return exp(log_choose(r, k) + log_choose((double)N - r, (double)n - k) - log_choose(N, n));
+}
+double fisher_test(int a, int b, int c, int d) {
+    const unsigned N = a + b + c + d, r = a + c, n = c + d;
+    const unsigned hi = std::min(r, n);
+    const int lo_i = (int)(r + n - N);
+    const unsigned lo = lo_i > 0 ? (unsigned)lo_i : 0u;
+    const double cutoff = hyper_pdf(r, n, N, (unsigned)c);
+    double acc = 0.0;
+    for (int k = (int)lo; k < (int)hi + 1; ++k) {
+        const double p = hyper_pdf(r, n, N, (unsigned)k);
+        if (p <= cutoff) acc += p;
+    }
+    return acc;
+}
+
+// 10-mers from the noise table's reference column (VC:3307-3611): a missing neighbour contributes "-|",
+// except at offsets -6, -3, -1 and +10 where it contributes "-".
+std::string kmer(const Panel& panel, int32_t chrom, int32_t pos, bool down) {
+    std::string out;
+    for (int i = 0; i < 10; ++i) {
+        const int off = down ? -(10 - i) : (i + 1);
+        const int32_t s = panel.lookup(chrom, pos + off);
+        if (s >= 0) {
+            out += panel.ref[s];
+        } else {
+            const bool bare = down ? (off == -6 || off == -3 || off == -1) : (off == 10);
+            out += bare ? "-" : "-|";
+        }
+    }
+    return out;
+}
+
+int homopolymer_test(const std::string& down, const std::string& up, char sub) {  // VC:3615-3718
+    int n[4] = {0, 0, 0, 0};
+    const char* L = "ACGT";
+    for (int b = 0; b < 4; ++b)
+        if (sub == L[b]) n[b] = 1;
+    for (const std::string* s : {&down, &up})
+        for (char ch : *s)
+            for (int b = 0; b < 4; ++b)
+                if (ch == L[b]) ++n[b];
+    for (int i = 0; i < 4; ++i)
+        for (int j = i + 1; j < 4; ++j)
+            if (n[i] + n[j] > 18) return 1;
+    return 0;
+}
+
+// the long double Q of VC:3868-3882 from the double p the device produced
+long double q_from_p(double p) {
+    long double pvalue = p;
+    long double p_limit = 0.0000000001;
+    if (pvalue < p_limit) return -10 * log10l(p_limit);
+    if (pvalue == 1) return 0;
+    return -10 * log10l(pvalue);
+}
+
+int report_gpu_error(const char* what) {
+    std::cout << RED << "Error: " << what << ": " << as_last_error() << RESET << std::endl;
+    return 1;
+}
+
+void usage_ee() {
+    std::cout << "Please type the following: " << std::endl;
+    std::cout << "\n./AmpliSolveErrorEstimation" << GREEN << " panel_design=" << RESET << "/your/panel/design/file/in/bed/format" << GREEN
+              << " reference_genome=" << RESET << "/your/reference/genome/in/fasta/format/indexed" << GREEN << " germline_dir=" << RESET
+              << "/dir/with/normal/count/files" << GREEN << " C_value=" << RESET << "/C/value/of/the/error/model" << GREEN
+              << " coverage_cutoff=" << RESET << "/coverage/per/strand" << GREEN << " default_error=" << RESET
+              << "/platform/specific/error/used/without/normals" << GREEN << " output_dir=" << RESET << "/dir/to/store/all/outputs"
+              << std::endl;
+    std::cout << "\nExecution example:" << std::endl;
+    std::cout << "./AmpliSolveErrorEstimation panel_design=panel.bed reference_genome=hg19.fasta germline_dir=NORMAL_ASEQ_DIR "
+                 "C_value=0.002 coverage_cutoff=100 default_error=0.01 output_dir=ErrorEstimation_Testing"
+              << std::endl;
+    std::cout << "\n\tIt is important to give the arguments in this order. Otherwise the program will crach !" << std::endl;
+    std::cout << STARS << std::endl;
+}
+
+void usage_vc() {
+    std::cout << "Please type the following: " << std::endl;
+    std::cout << "\n./AmpliSolveVariantCalling" << GREEN << " errorFile=" << RESET << "/the/file/produced/by/AmpliSolveErrorEstimation" << GREEN
+              << " tumour_dir=" << RESET << "/your/dir/with/tumour/read/count/files " << GREEN << "output_dir=" << RESET
+              << "/dir/to/store/all/outputs" << GREEN << " coverage_cutoff=" << RESET << "/coverage/per/strand/required/to/do/predictions"
+              << GREEN << " p_value=" << RESET << "/Fisher's/exact/test/p/value/for/strand/bias" << std::endl;
+    std::cout << "\nExecution example:" << std::endl;
+    std::cout << "./AmpliSolveVariantCalling errorFile=positionSpecificNoise_0.0020.txt tumour_dir=TUMOUR_ASEQ_DIR "
+                 "output_dir=VariantCalling_Testing coverage_cutoff=100 p_value=0.05"
+              << std::endl;
+    std::cout << "\n\tIt is important to give the arguments in this order. Otherwise the program will crach !" << std::endl;
+    std::cout << STARS << std::endl;
+}
+
+void write_list_file(const std::string& path, const std::vector<std::string>& listed) {
+    std::ofstream f(path.c_str());
+    for (const std::string& s : listed) f << s << "\n";
+}
+
+void report_load(const std::vector<CountFile>& files, const std::vector<AseqStats>& stats) {
+    for (size_t i = 0; i < files.size(); ++i) {
+        const AseqStats& s = stats[i];
+        for (int64_t k = 0; k < s.bad_rd; ++k) std::cout << "malakia paizei edo" << std::endl;  // EE:1178-1181, VC:762-765
+        if (s.extra)
+            std::cout << "Warning: " << files[i].path << " has " << s.extra
+                      << " row(s) beyond the number of panel slots of their position; ignored" << std::endl;
+    }
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -23,6 +487,476 @@ int as_hash_iteration_order(const char* const* keys, int32_t n, int32_t* order_o
     int32_t j = 0;
     for (auto it = m.begin(); it != m.end(); ++it) order_out[j++] = first[it->first];
     return j;
+}
+
+// ===================================================================================================
+// AmpliSolveErrorEstimation (EE:241-520)
+// ===================================================================================================
+int as_error_estimation_main(int argc, char** argv) {
+    if (argc != 8) {
+        std::cout << STARS << std::endl;
+        std::cout << RED << "                                        Your input arguments are not correct !" << RESET << std::endl;
+        std::cout << "                         amplisolve_b200 (B200-native AmpliSolveErrorEstimation, argv-compatible)\n" << std::endl;
+        usage_ee();
+        return 0;
+    }
+    const std::string panel_design = arg_value(argv[1], "panel_design=");
+    const std::string reference_genome = arg_value(argv[2], "reference_genome=");
+    const std::string germline_dir = arg_value(argv[3], "germline_dir=");
+    const std::string C_value = arg_value(argv[4], "C_value=");
+    const std::string coverage_cutoff = arg_value(argv[5], "coverage_cutoff=");
+    const std::string default_error = arg_value(argv[6], "default_error=");
+    const std::string output_dir = arg_value(argv[7], "output_dir=");
+    float C_value_float = (float)atof(C_value.c_str());  // EE:329
+    int cut = atoi(coverage_cutoff.c_str());
+    const bool with_germlines = germline_dir != "not_available";  // EE:349
+    float default_error_float = 0.01f;
+
+    std::cout << STARS << "\n" << std::endl;
+    std::cout << "                                Error estimation required for AmpliSolveVariantCalling program \n" << std::endl;
+    std::cout << "                        amplisolve_b200: B200-native implementation (" << as_version() << ")\n" << std::endl;
+    std::cout << "Execution started under the following parameters:" << std::endl;
+    std::cout << "\t1. Panel design                                   : " << GREEN << panel_design << RESET << std::endl;
+    std::cout << "\t2. Reference genome                               : " << GREEN << reference_genome << RESET << std::endl;
+    if (!with_germlines) {
+        default_error_float = (float)atof(default_error.c_str());
+        if (default_error_float > 0) {
+            std::cout << "\t3. Germline count dir                             : " << RED << "NO germline count files available" << RESET
+                      << ". Estimation of error is based on platform-specific error level given by user equal to "
+                      << default_error_float << std::endl;
+        } else {
+            default_error_float = 0.01f;  // EE:359-362
+            std::cout << "\t3. Germline count dir                             : " << RED << "NO germline count files available" << RESET
+                      << ". User gave wrong platform-specific error level and the estimation will be based on Error="
+                      << default_error_float << std::endl;
+        }
+    } else {
+        std::cout << "\t3. Germline count dir                             : " << GREEN << germline_dir << RESET << std::endl;
+    }
+    if (C_value_float <= 0) {
+        C_value_float = 0.002f;  // EE:372-376
+        std::cout << "\t4. C value                                         : " << RED << "User gave: " << C_value << RESET
+                  << ". The value is converted to 0.002" << std::endl;
+    } else {
+        std::cout << "\t4. C value                                        : " << GREEN << C_value_float << RESET << std::endl;
+    }
+    if (cut <= 0) {
+        cut = 100;  // EE:383-387
+        std::cout << "\t5. Coverage cutoff                                  : " << RED << "User gave: " << coverage_cutoff << RESET
+                  << ". The value is converted 100" << std::endl;
+    } else {
+        std::cout << "\t5. Coverage cutoff                                : " << GREEN << cut << RESET << std::endl;
+    }
+    std::cout << "\t6. Output dir                                     : " << GREEN << output_dir << RESET << std::endl;
+
+    const std::string interm = output_dir + "/AmpliSolveErrorEstimation_interm_files";
+    if (!make_dir(interm)) {
+        std::cout << "Error: cannot create " << interm << std::endl;
+        return 0;
+    }
+    srand((unsigned)time(nullptr));
+    const int seed = rand() % 1000;  // EE:581-584
+    const std::string stem = interm + "/" + std::to_string(seed);
+
+    // panel enumeration, reference bases, duplicated positions (replaces generateReferenceBases, EE:578-670)
+    std::cout << "\nRunning function generateReferenceBases: ";
+    Panel panel;
+    int n_amplicons = 0;
+    if (!load_bed(panel_design, panel, n_amplicons)) {
+        printf("Error from generateReferenceBases: Cannot open file: %s\n", panel_design.c_str());
+        return 0;
+    }
+    panel.link();
+    std::string err;
+    if (!annotate_reference(reference_genome, panel, err)) {
+        std::cout << "Error from generateReferenceBases: " << err << std::endl;
+        return 0;
+    }
+    const int64_t P = panel.size();
+    panel.dup.assign(P, 0);
+    for (int64_t i = 0; i < P; ++i)
+        if (panel.twin_next[i] >= 0 || panel.twin_head[i] != (int32_t)i) panel.dup[i] = 1;
+    {
+        std::ofstream refs((stem + "_panelReferenceBases.txt").c_str());
+        for (int64_t i = 0; i < P; ++i)
+            refs << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i] << "\n";
+        std::ofstream dups((stem + "_ampliconDuplicatedPositions.txt").c_str());
+        for (int64_t i = 0; i < P; ++i)
+            if (panel.dup[i] && panel.twin_head[i] == (int32_t)i)
+                dups << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\n";
+    }
+    std::cout << "Reference bases and amplicon duplicated positions have generated" << "\n\t\t --> Parsed in total " << n_amplicons
+              << " amplicons and annotated " << P << " positions." << std::endl;
+    std::cout << "Running function storeReference: panel reference bases stored with success " << GREEN << panel.first_slot.size()
+              << RESET << std::endl;
+
+    const char* header =
+        "chrom\tposition\treference\tduplicate\tThres_A\tThres_C\tThres_G\tThres_T\tGerm_Max_A\tGerm_Max_C\tGerm_Max_G\tGerm_Max_T";
+    if (!with_germlines) {
+        // generateFinalOutput_default (EE:2948-3043)
+        const std::string out_name = output_dir + "/positionSpecificNoise_default.txt";
+        std::ofstream output(out_name.c_str());
+        output << header << std::endl;
+        char value[64];
+        snprintf(value, sizeof value, "%.4f_%.4f", default_error_float, default_error_float);
+        for (int64_t i = 0; i < P; ++i) {
+            output << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i];
+            output << "\t" << (panel.dup[i] ? "YES" : "NO");
+            output << "\t" << value << "\t" << value << "\t" << value << "\t" << value << "\t-\t-\t-\t-" << std::endl;
+        }
+        std::cout << "\nAmpliSolveErrorEstimation execution was successful. Results can be found at: " << YELLOW << out_name << RESET
+                  << std::endl;
+        std::cout << "\n" << STARS << std::endl;
+        return 0;
+    }
+
+    // normals in the reference's file order
+    std::vector<CountFile> files;
+    std::vector<std::string> listed;
+    if (!list_count_files(germline_dir, files, listed)) {
+        std::cout << "Error: cannot list " << germline_dir << "/*.ASEQ" << std::endl;
+        return 0;
+    }
+    write_list_file(stem + "_germline_count_list_original.txt", listed);
+    std::cout << "\nRunning function storeList: " << GREEN << stem << "_germline_count_list_original.txt" << RESET
+              << " stored with success. It contains " << GREEN << files.size() << RESET << " samples" << std::endl;
+    const int S = (int)files.size();
+    as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
+    if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
+    Pinned counts;
+    if (!counts.alloc((size_t)S * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
+    std::cout << "Running function storeGermlineStatistics:" << std::endl;
+    std::vector<AseqStats> stats;
+    if (!load_all(files, panel, (uint32_t*)counts.p, nullptr, stats)) {
+        for (int i = 0; i < S; ++i)
+            if (!stats[i].ok) printf("Error: Cannot open %s\n", files[i].path.c_str());
+        return 0;
+    }
+    report_load(files, stats);
+
+    std::cout << "Running function estimateThresholds: ";
+    std::vector<float> thr((size_t)P * 8), germ_val((size_t)P * 4);
+    std::vector<uint8_t> germ_state((size_t)P * 4);
+    std::vector<uint32_t> count((size_t)P * 4), nrec((size_t)P);
+    const int rc = as_noise_estimate_host(ctx, (const uint32_t*)counts.p, S, P, panel.has_twins ? panel.twin_next.data() : nullptr,
+                                          panel.has_twins ? panel.twin_head.data() : nullptr, C_value_float, cut, thr.data(),
+                                          germ_val.data(), germ_state.data(), count.data(), nrec.data());
+    as_destroy(ctx);
+    if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
+    std::cout << "thresholds for " << panel.first_slot.size() << " positions estimated on the GPU" << std::endl;
+
+    // generateFinalOutput (EE:2546-2944)
+    char out_name[4096];
+    snprintf(out_name, sizeof out_name, "%s/positionSpecificNoise_%.4f.txt", output_dir.c_str(), C_value_float);
+    {
+        std::ofstream output(out_name);
+        output << header << std::endl;
+        const char* L = "ACGT";
+        char cell[128];
+        for (int64_t i = 0; i < P; ++i) {
+            output << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i];
+            output << "\t" << (panel.dup[i] ? "YES" : "NO");
+            for (int b = 0; b < 4; ++b) {
+                const float tf = thr[(size_t)i * 8 + b * 2], tb = thr[(size_t)i * 8 + b * 2 + 1];
+                if (panel.ref[i].size() == 1 && panel.ref[i][0] == L[b]) {
+                    output << "\t-2_-2";  // EE:2668-2673
+                } else if (std::isnan(tf) || std::isnan(tb)) {
+                    output << "\t0.01_0.01";  // "-1_-1" -> EE:2680-2684
+                } else {
+                    snprintf(cell, sizeof cell, "%f_%f", (double)tf, (double)tb);  // EE:1787
+                    output << "\t" << cell;
+                }
+            }
+            for (int b = 0; b < 4; ++b) {
+                if (germ_state[(size_t)i * 4 + b] == 0)
+                    output << "\t" << "-";  // EE:2807-2849
+                else
+                    output << "\t" << (double)germ_val[(size_t)i * 4 + b];
+            }
+            output << std::endl;
+        }
+    }
+    char msg_name[4096];
+    snprintf(msg_name, sizeof msg_name, "%s/positionSpecific_%.4f.txt", output_dir.c_str(), C_value_float);  // sic, EE:458
+    std::cout << "\nAmpliSolveErrorEstimation execution was successful. Results can be found at: " << YELLOW << msg_name << RESET
+              << std::endl;
+    std::cout << "\n" << STARS << std::endl;
+    return 0;
+}
+
+// ===================================================================================================
+// AmpliSolveVariantCalling (VC:199-360, VC:430-576, VC:633-3304)
+// ===================================================================================================
+int as_variant_calling_main(int argc, char** argv) {
+    if (argc != 6) {
+        std::cout << STARS << std::endl;
+        std::cout << RED << "                                        Your input arguments are not correct !" << RESET << std::endl;
+        std::cout << "                         amplisolve_b200 (B200-native AmpliSolveVariantCalling, argv-compatible)\n" << std::endl;
+        usage_vc();
+        return 0;
+    }
+    const std::string error_file = arg_value(argv[1], "errorFile=");
+    const std::string tumour_dir = arg_value(argv[2], "tumour_dir=");
+    const std::string output_dir = arg_value(argv[3], "output_dir=");
+    const std::string coverage_cutoff = arg_value(argv[4], "coverage_cutoff=");
+    const std::string p_value = arg_value(argv[5], "p_value=");
+    float p_value_float = (float)atof(p_value.c_str());  // VC:263
+    int cut = atoi(coverage_cutoff.c_str());
+
+    std::cout << STARS << "\n" << std::endl;
+    std::cout << "                          AmpliSolve variant calling for batch execution of multiple samples\n" << std::endl;
+    std::cout << "                        amplisolve_b200: B200-native implementation (" << as_version() << ")\n" << std::endl;
+    std::cout << "Execution started under the following parameters:" << std::endl;
+    std::cout << "\t1. Error estimation                               : " << GREEN << error_file << RESET << std::endl;
+    std::cout << "\t2. Tumour count dir                               : " << GREEN << tumour_dir << RESET << std::endl;
+    std::cout << "\t3. Output dir                                     : " << GREEN << output_dir << RESET << std::endl;
+    if (cut <= 0) {
+        cut = 100;  // VC:277-281
+        std::cout << "\t4. Coverage cutoff                                  : " << RED << "User gave: " << coverage_cutoff << RESET
+                  << ". The value is converted to default 100" << std::endl;
+    } else {
+        std::cout << "\t4. Coverage cutoff                                : " << GREEN << cut << RESET << std::endl;
+    }
+    if (p_value_float <= 0 || p_value_float > 1) {
+        p_value_float = 0.05f;  // VC:289-293
+        std::cout << "\t5. p-value                                         : " << RED << "User gave: " << p_value << RESET
+                  << ". The value is converted to default 0.05" << std::endl;
+    } else {
+        std::cout << "\t5. p-value                                        : " << GREEN << p_value_float << RESET << std::endl;
+    }
+    std::cout << std::endl;
+
+    const std::string interm = output_dir + "/AmpliSolveVariantCalling_interm_files";
+    if (!make_dir(interm)) {
+        std::cout << "Error: cannot create " << interm << std::endl;
+        return 0;
+    }
+
+    // ---- noise table (storeInputFile, VC:430-576): one slot per row; also re-emits the dummy VCF (VC:564)
+    Panel panel;
+    std::vector<float> thr_view;              // [P][4][2] through std::stof (VC:889-890)
+    std::vector<std::string> germ_text;       // [P][4]
+    {
+        std::string text;
+        if (!read_file(error_file, text)) {
+            printf("Error from storeInputFile function: Cannot open %s\n", error_file.c_str());
+            return 0;
+        }
+        std::ofstream dummy((interm + "/dummyVCF_1.vcf").c_str());
+        const char* p = text.data();
+        const char* e = p + text.size();
+        const char* eol = (const char*)memchr(p, '\n', e - p);  // header
+        p = eol ? eol + 1 : e;
+        while (p < e) {
+            eol = (const char*)memchr(p, '\n', e - p);
+            if (!eol) eol = e;
+            std::string f[12];
+            const char* q = p;
+            int nf = 0;
+            for (; nf < 12; ++nf) {
+                q = skip_ws(q, eol);
+                const char* t = token_end(q, eol);
+                if (t == q) break;
+                f[nf].assign(q, t);
+                q = t;
+            }
+            if (nf >= 1) {
+                const int32_t c = panel.chrom_id(f[0]);
+                panel.add_slot(c, atoi(f[1].c_str()));
+                panel.pos_text.push_back(f[1]);
+                panel.ref.push_back(f[2]);
+                panel.dup.push_back(f[3] == "YES" ? 1 : 0);
+                for (int b = 0; b < 4; ++b) {
+                    const std::string& cellv = f[4 + b];
+                    const size_t us = cellv.find('_');
+                    float a = 0.f, bwv = 0.f;
+                    if (us != std::string::npos) {
+                        a = strtof(cellv.substr(0, us).c_str(), nullptr);
+                        const std::string rest = cellv.substr(us + 1);
+                        bwv = strtof(rest.substr(0, rest.find('_')).c_str(), nullptr);
+                    }
+                    thr_view.push_back(a);
+                    thr_view.push_back(bwv);
+                    germ_text.push_back(f[8 + b]);
+                }
+                dummy << f[0] << "\t" << f[1] << "\t.\t.\t.\t.\t.\t." << std::endl;
+            }
+            p = eol + 1;
+        }
+    }
+    panel.link();
+    const int64_t P = panel.size();
+    // rows of a duplicated position: the hashes keep the FIRST row's reference, thresholds, Germ_Max (insert does
+    // not overwrite, VC:505-560) and flag it if ANY row says YES
+    for (int64_t i = 0; i < P; ++i) {
+        const int32_t h = panel.twin_head[i];
+        if (h != (int32_t)i) {
+            if (panel.dup[i]) panel.dup[h] = 1;
+        }
+    }
+    for (int64_t i = 0; i < P; ++i) {
+        const int32_t h = panel.twin_head[i];
+        if (h != (int32_t)i) {
+            panel.dup[i] = panel.dup[h];
+            panel.ref[i] = panel.ref[h];
+            for (int k = 0; k < 8; ++k) thr_view[(size_t)i * 8 + k] = thr_view[(size_t)h * 8 + k];
+            for (int k = 0; k < 4; ++k) germ_text[(size_t)i * 4 + k] = germ_text[(size_t)h * 4 + k];
+        }
+    }
+    std::cout << "Running function storeInputFile: the error levels have stored with success " << P << RESET << std::endl;
+    std::vector<uint8_t> ref_code((size_t)P, 255);
+    for (int64_t i = 0; i < P; ++i) {
+        const std::string& r = panel.ref[i];
+        if (r == "A") ref_code[i] = 0;
+        else if (r == "C") ref_code[i] = 1;
+        else if (r == "G") ref_code[i] = 2;
+        else if (r == "T") ref_code[i] = 3;
+    }
+
+    // ---- tumour files in the reference's order
+    srand((unsigned)time(nullptr));
+    const int seed = rand() % 1000;  // VC:328-331
+    std::vector<CountFile> files;
+    std::vector<std::string> listed;
+    if (!list_count_files(tumour_dir, files, listed)) {
+        std::cout << "Error: cannot list " << tumour_dir << "/*.ASEQ" << std::endl;
+        return 0;
+    }
+    const std::string list_name = interm + "/" + std::to_string(seed) + "_tumour_count_list_original.txt";
+    write_list_file(list_name, listed);
+    std::cout << "\nRunning function storeList: " << GREEN << list_name << RESET << " stored with success. It contains " << GREEN
+              << files.size() << RESET << " samples" << std::endl;
+    const int T = (int)files.size();
+    as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
+    if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
+    Pinned counts;
+    if (!counts.alloc((size_t)T * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
+    std::vector<int32_t> row_of((size_t)T * (size_t)P, -1);
+    std::vector<AseqStats> stats;
+    std::cout << "\nRunning function callVariants...." << std::endl;
+    if (!load_all(files, panel, (uint32_t*)counts.p, row_of.data(), stats)) {
+        for (int i = 0; i < T; ++i)
+            if (!stats[i].ok) printf("\tError from callVariants:  Cannot open %s\n", files[i].path.c_str());
+        return 0;
+    }
+    report_load(files, stats);
+    for (int i = 0; i < T; ++i)
+        for (int64_t k = 0; k < stats[i].outside; ++k) std::cout << "mistake..." << std::endl;  // VC:847-852
+
+    // ---- the hot path on the GPU
+    std::vector<as_call> calls;
+    int64_t n_calls = 0;
+    if (T > 0 && P > 0) {
+        int64_t cap = std::max<int64_t>(4096, (int64_t)T * P / 16);
+        int rc;
+        for (;;) {
+            calls.resize((size_t)cap);
+            rc = as_call_variants_host(ctx, (const uint32_t*)counts.p, T, P, ref_code.data(), thr_view.data(), cut, calls.data(), cap,
+                                       &n_calls);
+            if (rc != AS_EOVERFLOW) break;
+            cap = n_calls;
+        }
+        if (rc != AS_OK) return report_gpu_error("as_call_variants_host");
+        calls.resize((size_t)n_calls);
+        // the reference emits calls in file-row order, then in alt order A,C,G,T (VC:869-3288)
+        std::sort(calls.begin(), calls.end(), [&](const as_call& a, const as_call& b) {
+            if (a.sample != b.sample) return a.sample < b.sample;
+            const int32_t ra = row_of[(size_t)a.sample * P + a.slot], rb = row_of[(size_t)b.sample * P + b.slot];
+            if (ra != rb) return ra < rb;
+            return a.alt < b.alt;
+        });
+    }
+    as_destroy(ctx);
+
+    // ---- writers (VC:662-688, VC:1040-1066)
+    const std::string summary_name = output_dir + "/Summary_Variant_Info.txt";
+    std::ofstream output(summary_name.c_str());
+    output << "Filename\tChrom\tPosition\tSubtitution\tRD\tRD_fw\tRD_bw\tAF\tReads_fw\tReads_bw\tAF_fw\tAF_bw\tAmpliconEdge_"
+              "StrandBias\tFisherPvalue\tQscore_fw\tQscore_bw\tReadTier\tGermlineInfo\tMaxGermlineAF\t10merDownstream\t10merUpstream\tHo"
+              "mopolymerFlag"
+           << std::endl;
+    const char* L = "ACGT";
+    size_t ci = 0;
+    const uint32_t* cnt = (const uint32_t*)counts.p;
+    for (int t = 0; t < T; ++t) {
+        const std::string vcf_name = output_dir + "/" + files[t].sample + ".vcf";
+        std::ofstream vcf(vcf_name.c_str());
+        time_t now = time(nullptr);
+        char* dt = ctime(&now);
+        vcf << "##fileformat=VCF-like\n##fileDate=" << dt
+            << "##source=AmpliSolveVariantCalling\n##reference=Not_Specified_here\n##phasing=Not_Specified_here\n##FILTER=<ID="
+               "XXXXXXXXX,Description='XXXXXXXXX'>\n##FILTER=<ID=XXXXXXXXX,Description='XXXXXXXXX'>\n##FILTER=<ID=XXXXXXXXX,"
+               "Description='XXXXXXXXX'>\n##FILTER=<ID=XXXXXXXXX,Description='XXXXXXXXX'>\n##INFO=<ID=RD,Number=1,Type=Integer,"
+               "Description='Total Read Depth'>\n##SAMPLE=<ID=Not_Specified_here,SampleName="
+            << files[t].sample
+            << ">\n##INFO=<ID=AF,Number=.,Type=Float,Description='Allele Frequency'>\n##INFO=<ID=SR,Number=1,Type=String,"
+               "Description='Supporting Reads'>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"
+            << std::endl;
+        if ((t + 1) % 50 == 0)
+            std::cout << "\tParsed successfully " << GREEN << (t + 1) << "/" << T << RESET << "  samples" << std::endl;
+        for (; ci < calls.size() && calls[ci].sample == t; ++ci) {
+            const as_call& c = calls[ci];
+            const int64_t s = c.slot;
+            const uint32_t* fw = cnt + ((size_t)t * 2 * P + s) * 4;
+            const uint32_t* bw = cnt + ((size_t)t * 2 * P + P + s) * 4;
+            const int FW = (int)(fw[0] + fw[1] + fw[2] + fw[3]), BW = (int)(bw[0] + bw[1] + bw[2] + bw[3]);
+            const int RD = FW + BW;
+            const int a = c.alt;
+            const int k_fw = (int)fw[a], k_bw = (int)bw[a];
+            const float AF = float(k_fw + k_bw) / float(RD);                    // VC:814-817
+            const float AF_fw = FW == 0 ? 0.f : float(k_fw) / float(FW);        // VC:776-795
+            const float AF_bw = BW == 0 ? 0.f : float(k_bw) / float(BW);        // VC:797-812
+            const long double Q_fw = q_from_p(c.p_fw), Q_bw = q_from_p(c.p_bw);  // VC:895-896
+            const double p = fisher_test(FW, BW, k_fw, k_bw);                   // VC:902
+            const char* flag_fisher = (p <= p_value_float) ? "YES" : "NO";      // VC:903-910
+            const char* flag_dup = panel.dup[s] ? "YES" : "NO";
+            const bool high = !(k_fw < 5 || k_bw < 5);                          // VC:912-919
+            const char* tier = high ? "HighQual" : "LowQual";
+            const std::string& max_germ_text = germ_text[(size_t)s * 4 + a];    // VC:943-954
+            const double max_germ = atof(max_germ_text.c_str());                // VC:972
+            const std::string chrom = panel.chroms[panel.slot_chrom[s]];
+            const std::string down = kmer(panel, panel.slot_chrom[s], panel.slot_pos[s], true);   // VC:964
+            const std::string up = kmer(panel, panel.slot_chrom[s], panel.slot_pos[s], false);    // VC:965
+            const int homo = homopolymer_test(down, up, L[a]);
+            const double Q = double(Q_fw + Q_bw) / 2.000;                       // VC:967
+            const std::string cat = std::string(flag_dup) + "_" + flag_fisher;
+            // FILTER: keys of an unordered_map in ITS iteration order (VC:993-1059)
+            std::unordered_map<std::string, std::string> flags;
+            int not_pass = 0;
+            if (cat == "YES_NO") { flags.insert(std::make_pair(std::string("AmpliconEdge"), std::string("AmpliconEdge"))); not_pass = 1; }
+            if (cat == "YES_YES") { flags.insert(std::make_pair(std::string("AmpliconEdge;StrandBias"), std::string("AmpliconEdge;StrandBias"))); not_pass = 1; }
+            if (cat == "NO_YES") { flags.insert(std::make_pair(std::string("StrandBias"), std::string("StrandBias"))); not_pass = 1; }
+            if (AF < max_germ && cat == "NO_NO" && !high) { flags.insert(std::make_pair(std::string("PositionWithHighNoise"), std::string("PositionWithHighNoise"))); not_pass = 1; }
+            if (homo == 1) { flags.insert(std::make_pair(std::string("HomoPolymerRegion"), std::string("HomoPolymerRegion"))); not_pass = 1; }
+            if (Q_fw < 20 || Q_bw < 20) { flags.insert(std::make_pair(std::string("LowQ"), std::string("LowQ"))); not_pass = 1; }
+            if (!high) { flags.insert(std::make_pair(std::string("LowSupportingReads"), std::string("LowSupportingReads"))); not_pass = 1; }
+            const std::string& pos_text = panel.pos_text[s];
+            const char* id = ".";
+            std::string filter = "PASS";
+            if (not_pass) {
+                filter.clear();
+                int first = 0;
+                for (auto it = flags.begin(); it != flags.end(); ++it) {
+                    filter = first == 0 ? it->first : filter + ";" + it->first;
+                    ++first;
+                }
+                if (c.ref == 1 && a == 2) id = "-";  // the reference writes ID "-" for non-PASS C->G rows (VC:1856)
+            }
+            vcf << chrom << "\t" << pos_text << "\t" << id << "\t" << L[c.ref] << "\t" << L[a] << "\t" << Q << "\t" << filter << "\t"
+                << AF << ";" << RD << ";" << k_fw + k_bw << std::endl;
+            // summary row; setprecision(4) is sticky on this stream exactly as in VC:1066
+            output << files[t].sample << "\t" << chrom << "\t" << pos_text << "\t" << L[c.ref] << "->" << L[a] << "\t" << RD << "\t"
+                   << FW << "\t" << BW << "\t" << AF << "\t" << k_fw << "\t" << k_bw << "\t" << AF_fw << "\t" << AF_bw << "\t"
+                   << flag_dup << "_" << flag_fisher << "\t" << p << "\t" << std::setprecision(4) << Q_fw << "\t"
+                   << std::setprecision(4) << Q_bw << "\t" << tier << "\t" << "-" << "\t" << max_germ_text << "\t" << down << "\t"
+                   << up << "\t" << homo << std::endl;
+        }
+    }
+    output.close();
+    std::cout << "\nAmpliSolveVariantCalling execution was successful. The results can be found at : " << YELLOW << summary_name
+              << RESET << std::endl;
+    std::cout << "\n" << STARS << std::endl;
+    return 0;
 }
 
 }  // extern "C"

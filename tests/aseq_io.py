@@ -109,9 +109,41 @@ def stage_case(workdir, case):
 def load_case(npz_path):
     z = np.load(npz_path, allow_pickle=False)
     case = {k: z[k] for k in z.files}
-    for k in ("bed", "ref_letters", "noise_table", "summary"):
+    for k in ("bed", "ref_letters", "noise_table", "summary", "default_table"):
         case[k] = str(case[k])
     case["normal_names"] = [str(x) for x in case["normal_names"]]
     case["tumour_names"] = [str(x) for x in case["tumour_names"]]
     case["vcfs"] = {nm: str(v) for nm, v in zip(case["tumour_names"], case["vcf_bodies"])}
     return case
+
+
+def write_fasta(workdir, slots, ref_letters, name="ref.fa"):
+    """A .fai-indexed FASTA holding the given base at every panel position (sparse file: one line per
+    chromosome, only the panel positions are written, everything else reads as NUL)."""
+    workdir = Path(workdir)
+    top: dict = {}
+    for (c, p) in slots:
+        top[c] = max(top.get(c, 0), p)
+    offsets = {}
+    off = 0
+    fai = []
+    for c, length in top.items():
+        off += len(c) + 2                   # ">chrom\n"
+        offsets[c] = off
+        fai.append(f"{c}\t{length}\t{off}\t{length}\t{length + 1}")
+        off += length + 1
+    with open(workdir / name, "wb") as fh:
+        fh.truncate(off)
+        pos = 0
+        for c, length in top.items():
+            fh.seek(pos)
+            fh.write(f">{c}\n".encode())
+            pos = offsets[c] + length
+            fh.seek(pos)
+            fh.write(b"\n")
+            pos += 1
+        for (c, p), r in zip(slots, ref_letters):
+            fh.seek(offsets[c] + p - 1)
+            fh.write(r.encode())
+    (workdir / (name + ".fai")).write_text("\n".join(fai) + "\n")
+    return name

@@ -90,10 +90,11 @@ def save_case(name, bed_text, ref_letters, normal_names, normals, tumour_names, 
     with tempfile.TemporaryDirectory(prefix="asg_", dir="/tmp") as td:
         aseq_io.stage_case(td, case)
         noise, summary, vcfs = run_reference(Path(td), c_value, cutoff)
+        default_table = refrun.run_ee_ref_default(Path(td), "panel.bed", "rb_ref.txt", "rb_dup.txt", "0.02").read_text()
     np.savez_compressed(HERE / f"{name}.npz", bed=np.array(bed_text), ref_letters=np.array("".join(ref_letters)),
                         normal_names=np.array(normal_names), normals=normals, tumour_names=np.array(tumour_names),
                         tumours=tumours, c_value=np.float32(float(c_value)), cutoff=np.int32(int(cutoff)),
-                        noise_table=np.array(noise), summary=np.array(summary),
+                        noise_table=np.array(noise), summary=np.array(summary), default_table=np.array(default_table),
                         vcf_bodies=np.array([vcfs[n] for n in tumour_names]))
     ncalls = len(summary.splitlines()) - 1
     print(f"{name}.npz: {normals.shape[2]} slots, {len(normal_names)} normals, {len(tumour_names)} tumours, {ncalls} calls,"

@@ -1,0 +1,81 @@
+"""GPU tests against the golden fixtures generated from the compiled reference (tests/golden/):
+the CUDA path through the C ABI, and the two drop-in programs end to end, byte for byte."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests import aseq_io
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "amplisolve_b200" / "bin"
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_noise_table_from_cuda_is_text_identical(ctx, name):
+    from amplisolve_b200 import twin_links
+    case = gu.load(name)
+    normals = np.ascontiguousarray(case["normals"][case["normal_order"]])
+    nxt, head = twin_links(case["pos_id"])
+    got = ctx.estimate_thresholds(normals, float(case["c_value"]), int(case["cutoff"]), nxt, head)
+    lines = gu.noise_table_lines(case, got["thr"], got["germ_val"].astype(np.float64), got["germ_state"])
+    want = case["noise_table"].splitlines()
+    bad = [i for i, (a, b) in enumerate(zip(lines, want)) if a != b]
+    assert len(lines) == len(want) and not bad, (bad[:5], lines[bad[0]] if bad else "", want[bad[0]] if bad else "")
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_calls_from_cuda_match_reference_rows(ctx, name):
+    case = gu.load(name)
+    order = case["tumour_order"]
+    tumours = np.ascontiguousarray(case["tumours"][order])
+    thr_view = gu.parse_noise_thresholds(case)
+    calls = ctx.call_variants(tumours, case["ref_code"], thr_view, int(case["cutoff"]))
+    want = gu.golden_call_rows(case)
+    assert len(calls) == len(want) > 0
+    for c, w in zip(calls, want):
+        chrom, pos = case["slots"][c["slot"]]
+        cnt = tumours[c["sample"], :, c["slot"], :].astype(np.int64)
+        FW, BW = int(cnt[0].sum()), int(cnt[1].sum())
+        got = (case["tumour_names"][order[c["sample"]]], chrom, pos, "ACGT"[c["ref"]], "ACGT"[c["alt"]], FW + BW, FW, BW,
+               int(cnt[0, c["alt"]]), int(cnt[1, c["alt"]]), gu.fmt_g(pyoracle.q_from_p(c["p_fw"])),
+               gu.fmt_g(pyoracle.q_from_p(c["p_bw"])))
+        assert got == w[:12]
+        assert gu.fmt_g(c["q_fw"]) == w[10] and gu.fmt_g(c["q_bw"]) == w[11]   # the device's own fp64 Q prints alike
+
+
+def run(prog, args, cwd):
+    r = subprocess.run([str(BIN / prog)] + args, cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    return r.stdout
+
+
+def vcf_body(path):
+    return "".join(l for l in open(path) if not l.startswith("##fileDate="))
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_programs_end_to_end_byte_identical(name, tmp_path):
+    """BASELINE.json configs[0]/[1] shape: AmpliSolveErrorEstimation on N/ + BED, then AmpliSolveVariantCalling on T/
+    with the table just written; every output file equals the reference's (VCF minus its ##fileDate line)."""
+    case = gu.load(name)
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    c_text = "%g" % float(case["c_value"])
+    out = run("AmpliSolveErrorEstimation", ["panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N",
+                                            f"C_value={c_text}", f"coverage_cutoff={int(case['cutoff'])}",
+                                            "default_error=0.01", "output_dir=o"], tmp_path)
+    tables = sorted((tmp_path / "o").glob("positionSpecificNoise_*.txt"))
+    assert len(tables) == 1 and tables[0].name == "positionSpecificNoise_%.4f.txt" % float(case["c_value"]), out[-2000:]
+    assert tables[0].read_text() == case["noise_table"]
+    run("AmpliSolveVariantCalling", [f"errorFile=o/{tables[0].name}", "tumour_dir=T", "output_dir=v",
+                                     f"coverage_cutoff={int(case['cutoff'])}", "p_value=0.05"], tmp_path)
+    assert (tmp_path / "v" / "Summary_Variant_Info.txt").read_text() == case["summary"]
+    for nm in case["tumour_names"]:
+        assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == case["vcfs"][nm], nm
+    dummy = (tmp_path / "v" / "AmpliSolveVariantCalling_interm_files" / "dummyVCF_1.vcf").read_text().splitlines()
+    assert len(dummy) == len(slots) and dummy[0] == f"{slots[0][0]}\t{slots[0][1]}\t.\t.\t.\t.\t.\t."

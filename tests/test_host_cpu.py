@@ -1,0 +1,97 @@
+"""CPU tests of the product's host side: the C-ABI library loads and exports every symbol the header
+declares, the parts of the two programs that need no GPU (usage text, default-error mode, hash order) behave
+like the reference, and compute entry points fail loudly without a GPU."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from tests import aseq_io
+from tests import golden_util as gu
+
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "amplisolve_b200" / "bin"
+
+
+def test_library_exports_every_declared_symbol():
+    import ctypes as C
+    from amplisolve_b200 import api
+    L = api.lib()
+    header = (ROOT / "include" / "amplisolve_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(as_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/amplisolve_b200.h but not exported"
+    assert set(api.EXPORTS) == set(declared)
+    assert C.sizeof(api.SynthParams) == 48 and api.CALL_DTYPE.itemsize == 48
+
+
+def test_no_cpu_fallback():
+    import torch
+    from amplisolve_b200 import AmpliSolveError, Context
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(AmpliSolveError, match="no CPU fallback|CUDA"):
+        Context(0)
+
+
+def test_hash_iteration_order_equals_libstdcxx_model():
+    from amplisolve_b200 import hash_iteration_order
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 3, 5, 12, 13, 29, 30, 97, 200):
+        keys = [f"dir{n}/S{int(x):05d}_{i}.PILEUP.ASEQ" for i, x in enumerate(rng.integers(0, 99999, n))]
+        assert hash_iteration_order(keys) == pyoracle.hash_iteration_order(keys)
+    n5 = [f"N/N{i}.PILEUP.ASEQ" for i in range(1, 6)]
+    assert [n5[i][2:4] for i in hash_iteration_order(n5)] == ["N5", "N3", "N2", "N4", "N1"]
+
+
+def test_twin_links():
+    from amplisolve_b200 import twin_links
+    nxt, head = twin_links([0, 1, 2, 1, 3, 0, 1])
+    assert nxt.tolist() == [5, 3, -1, 6, -1, -1, -1]
+    assert head.tolist() == [0, 1, 2, 1, 4, 0, 1]
+
+
+@pytest.mark.parametrize("prog,n", [("AmpliSolveErrorEstimation", 8), ("AmpliSolveVariantCalling", 6)])
+def test_usage_on_wrong_argc_returns_zero(prog, n):
+    """EE:266-273, VC:216-223: wrong argc prints the usage text and returns 0."""
+    r = subprocess.run([str(BIN / prog), "x=1"], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert "Your input arguments are not correct" in r.stdout and "Please type the following" in r.stdout
+
+
+@pytest.mark.parametrize("name", gu.CASES)
+def test_default_error_mode_is_byte_identical(name, tmp_path):
+    """germline_dir=not_available (EE:349, EE:472-506, EE:2948-3043): BED enumeration, reference bases read from
+    the .fai-indexed FASTA, duplicated positions -- no GPU involved."""
+    case = gu.load(name)
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    r = subprocess.run([str(BIN / "AmpliSolveErrorEstimation"), "panel_design=panel.bed", "reference_genome=ref.fa",
+                        "germline_dir=not_available", "C_value=0.002", "coverage_cutoff=100", "default_error=0.02",
+                        "output_dir=od"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    got = (tmp_path / "od" / "positionSpecificNoise_default.txt").read_text()
+    assert got == case["default_table"]
+    interm = list((tmp_path / "od" / "AmpliSolveErrorEstimation_interm_files").glob("*_panelReferenceBases.txt"))
+    assert len(interm) == 1 and interm[0].read_text() == (tmp_path / "rb_ref.txt").read_text()
+    dups = list((tmp_path / "od" / "AmpliSolveErrorEstimation_interm_files").glob("*_ampliconDuplicatedPositions.txt"))
+    assert sorted(dups[0].read_text().splitlines()) == sorted((tmp_path / "rb_dup.txt").read_text().splitlines())
+
+
+def test_noise_mode_without_gpu_fails_loudly(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    case = gu.load("synth_small")
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    r = subprocess.run([str(BIN / "AmpliSolveErrorEstimation"), "panel_design=panel.bed", "reference_genome=ref.fa",
+                        "germline_dir=N", "C_value=0.0035", "coverage_cutoff=150", "default_error=0.01", "output_dir=o"],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stdout
+    assert not list((tmp_path / "o").glob("positionSpecificNoise_0*.txt"))

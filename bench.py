@@ -311,6 +311,20 @@ def run_ours(args):
     if found > cap:
         raise RuntimeError(f"call list overflow in the benchmark: {found} > {cap}")
 
+    # the only cross-GPU traffic of the job: one final gather of the compacted calls on rank 0 (outside the math path)
+    gather_ms = None
+    if world > 1:
+        from amplisolve_b200 import calls_from_device
+        from amplisolve_b200.shard import gather_calls
+        local_calls = calls_from_device(calls, n_calls)
+        barrier()
+        tg = time.perf_counter()
+        merged = gather_calls(local_calls, rank * P, device=dev)
+        barrier()
+        gather_ms = (time.perf_counter() - tg) * 1e3
+        if rank == 0 and len(merged) < found:
+            raise RuntimeError("gathered call list is shorter than rank 0's own")
+        n_merged = len(merged) if rank == 0 else 0
     tmax = torch.tensor([total_ms, t_noise, t_call], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -349,6 +363,8 @@ def run_ours(args):
                                "traffic": None, "algorithmic_bytes": noise_bytes},
             "gpu_launches": int(launches * world), "clocks": clocks,
         }
+        if gather_ms is not None:
+            result["calls_gather"] = {"ms": gather_ms, "calls_total": n_merged, "transport": "NCCL all_gather of the compacted call lists, once per job"}
         if e2e is not None:
             result["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -464,7 +464,6 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     constexpr int CAND_CAP = K * 32 * 3;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES];
-    __shared__ __align__(16) float e_tab[AS_TILE_SLOTS][8];
     __shared__ uint16_t cand_all[AS_CONSUMER_WARPS][CAND_CAP];
     __shared__ __align__(16) CallCand q2_all[AS_CONSUMER_WARPS][AS_Q2_CAP];
     StageRing<K, STAGES> ring;
@@ -481,13 +480,9 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     const int64_t p = tile0 + tid;
     uint32_t notref = 0;
     if (tid < n_slots) {
-        CallSlotConst sc;
-        load_slot_const(sc, thr_view, ref, p);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) e_tab[tid][i] = sc.e[i];
-        if (sc.ref <= 3) notref = 0xfu & ~(1u << sc.ref);
+        const uint32_t r = ref[p];
+        if (r <= 3) notref = 0xfu & ~(1u << r);
     }
-    __syncwarp();  // e_tab rows of this warp are only read by this warp
     uint16_t* cand = cand_all[warp];
     CallCand* q2 = q2_all[warp];
     int n2 = 0;
@@ -535,7 +530,7 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
             // ---- revisit the candidates with full warps: exact m >= k screen, survivors to the series queue
             for (int base = 0; base < total; base += 32) {
                 const int i = base + lane;
-                CallCand c;
+                uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);  // the CallCand as two 16-byte words
                 bool surv = false;
                 if (i < total) {
                     const uint32_t e = cand[i];
@@ -543,15 +538,19 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                     const int col = warp * 32 + src;
                     const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + col];
                     const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + col];
-                    c.k_fw = comp(fw, b); c.k_bw = comp(bw, b);
-                    c.d_fw = fw.x + fw.y + fw.z + fw.w; c.d_bw = bw.x + bw.y + bw.z + bw.w;
-                    c.e_fw = e_tab[col][2 * b]; c.e_bw = e_tab[col][2 * b + 1];
-                    c.sample_alt = (uint32_t)(t + j) | ((uint32_t)b << 30);
-                    c.slot = (int32_t)(tile0 + col);
-                    surv = strand_can_pass(c.k_fw, c.d_fw, c.e_fw) && strand_can_pass(c.k_bw, c.d_bw, c.e_bw);
+                    // thresholds of the candidate's slot: a rare read, served by L2
+                    const float2 ee = *reinterpret_cast<const float2*>(thr_view + (tile0 + col) * 8 + 2 * b);
+                    w0 = make_uint4(comp(fw, b), fw.x + fw.y + fw.z + fw.w, comp(bw, b), bw.x + bw.y + bw.z + bw.w);
+                    w1 = make_uint4(__float_as_uint(ee.x), __float_as_uint(ee.y), (uint32_t)(t + j) | ((uint32_t)b << 30),
+                                    (uint32_t)(tile0 + col));
+                    surv = strand_can_pass(w0.x, w0.y, ee.x) && strand_can_pass(w0.z, w0.w, ee.y);
                 }
                 const unsigned votes = __ballot_sync(0xffffffffu, surv);
-                if (surv) q2[n2 + __popc(votes & ((1u << lane) - 1u))] = c;
+                if (surv) {
+                    uint4* dst = reinterpret_cast<uint4*>(q2 + n2 + __popc(votes & ((1u << lane) - 1u)));
+                    dst[0] = w0;
+                    dst[1] = w1;
+                }
                 n2 += __popc(votes);
                 __syncwarp();
                 while (n2 >= 16) {
@@ -765,6 +764,9 @@ cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t
         case 7: return launch_call_staged<2, 2>(grid, AS_CALL_ARGS, st);
         case 8: return launch_call_staged<2, 3>(grid, AS_CALL_ARGS, st);
         case 9: return launch_call_staged<2, 4>(grid, AS_CALL_ARGS, st);
+        case 10: return launch_call_staged<3, 3>(grid, AS_CALL_ARGS, st);
+        case 11: return launch_call_staged<3, 2>(grid, AS_CALL_ARGS, st);
+        case 12: return launch_call_staged<6, 2>(grid, AS_CALL_ARGS, st);
         default: return launch_call_staged<4, 3>(grid, AS_CALL_ARGS, st);
     }
 #undef AS_CALL_ARGS

@@ -126,7 +126,10 @@ struct FastBase {
     uint32_t s_b_fw, s_b_bw;  // 32-bit partial sums of alt reads
     double s_d_fw, s_d_bw;    // sum of strand depth (exact in fp64)
     double s_p_fw, s_p_bw;    // sum of float(depth)*float(C), plus the folded alt-read sums
-    uint32_t count, g_n, g_x, g_rd;
+    uint32_t count;
+    // Germ_Max without a counter: g_rd == 0 no qualifying record yet (g_x = 1 makes every comparison fail),
+    // g_rd == 1 exactly one (it is dropped, EE:1258-1262; real depths are >= 2 * cut), else the best rational
+    uint32_t g_x, g_rd;
 };
 struct FastAcc {
     FastBase b[4];
@@ -138,8 +141,9 @@ __device__ __forceinline__ void fast_init(FastAcc& a) {
     for (int i = 0; i < 4; ++i) {
         a.b[i].s_b_fw = a.b[i].s_b_bw = 0u;
         a.b[i].s_d_fw = a.b[i].s_d_bw = a.b[i].s_p_fw = a.b[i].s_p_bw = 0.0;
-        a.b[i].count = a.b[i].g_n = a.b[i].g_x = 0u;
-        a.b[i].g_rd = 1u;
+        a.b[i].count = 0u;
+        a.b[i].g_x = 1u;
+        a.b[i].g_rd = 0u;
     }
     a.nrec = 0; a.big = 0;
 }
@@ -165,8 +169,11 @@ __device__ __forceinline__ void fast_accumulate(FastAcc& a, const uint4 fw, cons
     const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
     const uint32_t RD = FW + BW;
     a.big |= RD;
+    // coverage gate folded into the limits: a limit of -1 fails every (signed) comparison; counts are < 2^31
     const bool cov = min(FW, BW) >= cut;
-    const uint32_t lim_fw = af_limit(FW), lim_bw = af_limit(BW), lim_rd = af_limit(RD);
+    const int32_t lim_fw = cov ? (int32_t)af_limit(FW) : -1;
+    const int32_t lim_bw = cov ? (int32_t)af_limit(BW) : -1;
+    const int32_t lim_rd = cov ? (int32_t)af_limit(RD) : -1;
     const double d_fw = u32_to_double(FW), d_bw = u32_to_double(BW);
     const double p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);
     const double p_bw = (double)__fmul_rn(__uint2float_rn(BW), C);
@@ -174,21 +181,20 @@ __device__ __forceinline__ void fast_accumulate(FastAcc& a, const uint4 fw, cons
     for (int i = 0; i < 4; ++i) {
         FastBase& s = a.b[i];
         const uint32_t bf = comp(fw, i), bb = comp(bw, i);
-        const bool keep = cov && bf <= lim_fw && bb <= lim_bw;
-        if (keep) {
+        if (((int32_t)bf <= lim_fw) & ((int32_t)bb <= lim_bw)) {
             s.s_b_fw += bf; s.s_b_bw += bb;
             s.s_d_fw = __dadd_rn(s.s_d_fw, d_fw); s.s_d_bw = __dadd_rn(s.s_d_bw, d_bw);
             s.s_p_fw = __dadd_rn(s.s_p_fw, p_fw); s.s_p_bw = __dadd_rn(s.s_p_bw, p_bw);
             s.count += 1;
         }
         const uint32_t x = bf + bb;
-        const bool qual = cov && x <= lim_rd;
-        // bitwise &, not &&: both products are always formed so that the update is predicated, not branched
-        const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * RD;
-        const bool upd = qual & (s.g_n != 0) & ge;
-        s.g_x = upd ? x : s.g_x;
-        s.g_rd = upd ? RD : s.g_rd;
-        s.g_n += qual ? 1u : 0u;
+        const bool qual = (int32_t)x <= lim_rd;
+        // bitwise &: both products are always formed so that the update is predicated, not branched
+        const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * RD;  // EE:1263: value <= AF
+        const bool first = qual & (s.g_rd == 0u);
+        const bool upd = qual & ge;
+        s.g_x = first ? 0u : (upd ? x : s.g_x);
+        s.g_rd = first ? 1u : (upd ? RD : s.g_rd);
     }
 }
 
@@ -201,7 +207,9 @@ __device__ __forceinline__ void fast_to_general(const FastAcc& f, NoiseAcc& a) {
         d.s_b_fw = s.s_b_fw; d.s_b_bw = s.s_b_bw;
         d.s_d_fw = (unsigned long long)__double2ll_rn(s.s_d_fw); d.s_d_bw = (unsigned long long)__double2ll_rn(s.s_d_bw);
         d.s_p_fw = s.s_p_fw; d.s_p_bw = s.s_p_bw;
-        d.count = s.count; d.g_n = s.g_n; d.g_x = s.g_x; d.g_rd = s.g_rd;
+        d.count = s.count;
+        d.g_n = s.g_rd == 0u ? 0u : (s.g_rd == 1u ? 1u : 2u);
+        d.g_x = s.g_x; d.g_rd = s.g_rd == 0u ? 1u : s.g_rd;
         d.g_first_x = 0; d.g_first_rd = 1;
     }
 }

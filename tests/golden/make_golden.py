@@ -6,6 +6,7 @@
 
   vc_function_grid.npz   kf_gammaq / mutationRulesPoissonQualityScore / call decision / fisherTest /
                          homopolymerTest of AmpliSolveVariantCalling.cpp evaluated on seeded grids
+  toy_full.npz           the whole of Toy_data (BASELINE.json configs[0]; used by the GPU end-to-end test)
   toy_slice.npz          a slice of Toy_data (BED lines, the 5 normals and 3 tumours as dense counts) with the
                          reference's positionSpecificNoise table, Summary_Variant_Info.txt and VCF bodies
   synth_small.npz        a small synthetic panel (tests/synth.py) with the same outputs
@@ -101,10 +102,12 @@ def save_case(name, bed_text, ref_letters, normal_names, normals, tumour_names, 
           f" noise table {len(noise)} bytes")
 
 
-def toy_slice(n_bed_lines=(0, 22), extra=(150, 160, 330, 345)):
+def toy_slice(name="toy_slice", n_bed_lines=(0, 22), extra=(150, 160, 330, 345)):
     toy = Path("/root/reference/Toy_data")
     bed_lines = (toy / "AmpliSeq_30genes_Designed-1.bed").read_bytes().decode().splitlines()
     sel = bed_lines[n_bed_lines[0]:n_bed_lines[1]] + bed_lines[extra[0]:extra[1]] + bed_lines[extra[2]:extra[3]]
+    if name == "toy_full":      # BASELINE.json configs[0]: the whole of Toy_data
+        sel = bed_lines
     bed_text = "\r\n".join(l.rstrip("\r") for l in sel) + "\r\n"      # the toy BED has CRLF line ends
     slots = aseq_io.enumerate_bed_text(bed_text)
     where, pos_id, U = aseq_io.slot_index(slots)
@@ -127,7 +130,7 @@ def toy_slice(n_bed_lines=(0, 22), extra=(150, 160, 330, 345)):
     letters = ["N" if upos[pos_id[i]].sum() == 0 else "ACGT"[int(np.argmax(upos[pos_id[i]]))] for i in range(P)]
     names_n = [f.name[:-len(".PILEUP.ASEQ")] for f in nfiles]
     names_t = [f.name[:-len(".PILEUP.ASEQ")] for f in tfiles]
-    save_case("toy_slice", bed_text, letters, names_n, normals, names_t, tumours, "0.002", "100")
+    save_case(name, bed_text, letters, names_n, normals, names_t, tumours, "0.002", "100")
 
 
 def synth_small():
@@ -152,4 +155,5 @@ if __name__ == "__main__":
         refrun.build_ref()
     function_grids()
     toy_slice()
+    toy_slice("toy_full")
     synth_small()

@@ -58,7 +58,7 @@ def vcf_body(path):
     return "".join(l for l in open(path) if not l.startswith("##fileDate="))
 
 
-@pytest.mark.parametrize("name", gu.CASES)
+@pytest.mark.parametrize("name", gu.CASES + ["toy_full"])
 def test_programs_end_to_end_byte_identical(name, tmp_path):
     """BASELINE.json configs[0]/[1] shape: AmpliSolveErrorEstimation on N/ + BED, then AmpliSolveVariantCalling on T/
     with the table just written; every output file equals the reference's (VCF minus its ##fileDate line)."""

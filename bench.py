@@ -235,6 +235,18 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel, default_workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload."""
+    f = ROOT / "profiles" / "ncu_traffic.json"
+    if not default_workload or not f.exists():
+        return None
+    try:
+        k = json.loads(f.read_text())["kernels"][kernel]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -340,6 +352,7 @@ def run_ours(args):
         ms_per_step = total_ms / args.steps
         tests_per_step = 6.0 * T * P * world
         peak, peak_src = hbm_peak()
+        default_wl = (P, S, T) == (WORKLOAD["slots"], WORKLOAD["normals"], WORKLOAD["tumours"])
         call_bytes = T * P * 32 + P * 33 + found * CALL_DTYPE.itemsize
         noise_bytes = P * (32 * S + 72)
         result = {
@@ -356,11 +369,13 @@ def run_ours(args):
             "kernel_ms": {"noise_model": t_noise_max, "caller": t_call_max},
             "roofline": {"bound": "hbm", "kernel": {0: "call_naive_kernel", 1: "call_queued_kernel"}.get(args.call_kernel, "call_staged_kernel"),
                          "achieved": call_bytes / (t_call * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak,
+                         "traffic": ncu_traffic("call_staged_kernel", default_wl and args.call_kernel == 3), "peak_source": peak_src,
                          "algorithmic_bytes": call_bytes},
             "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel" if args.noise_kernel == 0 else "noise_staged_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": noise_bytes / (t_noise * 1e-3) / 1e9 / peak,
-                               "traffic": None, "algorithmic_bytes": noise_bytes},
+                               "traffic": ncu_traffic("noise_staged_kernel", default_wl and args.noise_kernel == 1),
+                               "algorithmic_bytes": noise_bytes},
             "gpu_launches": int(launches * world), "clocks": clocks,
         }
         if gather_ms is not None:

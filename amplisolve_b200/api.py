@@ -29,7 +29,7 @@ EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host", "as_poisson_test_host",
-    "as_kf_gammaq_host", "as_synth_counts_dev", "as_hash_iteration_order", "as_error_estimation_main",
+    "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
 
@@ -42,7 +42,7 @@ class SynthParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("mean_depth", C.c_float), ("depth_sigma", C.c_float),
                 ("germline_rate", C.c_float), ("somatic_rate", C.c_float), ("somatic_vaf_lo", C.c_float),
                 ("somatic_vaf_hi", C.c_float), ("absent_rate", C.c_float), ("sample_offset", C.c_int32),
-                ("slot_offset", C.c_int64)]
+                ("slot_offset", C.c_int64), ("twin_period", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -86,6 +86,7 @@ def lib():
     L.as_poisson_test_host.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.as_kf_gammaq_host.argtypes = [vp, vp, vp, i64, vp]
     L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
+    L.as_synth_twin_links_dev.argtypes = [vp, i64, C.POINTER(SynthParams), vp, vp, vp]
     L.as_hash_iteration_order.argtypes = [C.POINTER(C.c_char_p), i32, vp]
     for name in ("as_error_estimation_main", "as_variant_calling_main"):
         if hasattr(L, name):
@@ -266,17 +267,27 @@ class Context:
 
     def synth_counts_dev(self, n_samples, P, *, seed, mean_depth, somatic_rate=0.0, sample_offset=0, slot_offset=0,
                          depth_sigma=0.5, germline_rate=1e-3, vaf=(0.01, 0.2), absent_rate=0.0, want_ref=True,
-                         stream=None):
+                         twin_period=0, stream=None):
         """Synthetic panel generated in HBM.  Returns (counts int32 [n][2][P][4], ref uint8 [P])."""
         import torch
         dev = f"cuda:{self.device}"
         counts = torch.empty((n_samples, 2, P, 4), dtype=torch.int32, device=dev)
         ref = torch.empty(P, dtype=torch.uint8, device=dev) if want_ref else None
         prm = SynthParams(seed, mean_depth, depth_sigma, germline_rate, somatic_rate, vaf[0], vaf[1], absent_rate,
-                          sample_offset, slot_offset)
+                          sample_offset, slot_offset, twin_period, 0)
         _check(lib().as_synth_counts_dev(self._h, _dp(counts), n_samples, P, _dp(ref), C.byref(prm),
                                          self._stream(stream)))
         return counts, ref
+
+    def synth_twin_links_dev(self, P, *, seed, slot_offset=0, twin_period=6, stream=None):
+        """twin_next / twin_head (int32 CUDA tensors [P]) of the synthetic panel geometry."""
+        import torch
+        dev = f"cuda:{self.device}"
+        nxt = torch.empty(P, dtype=torch.int32, device=dev)
+        head = torch.empty(P, dtype=torch.int32, device=dev)
+        prm = SynthParams(seed, 0, 0, 0, 0, 0, 0, 0, 0, slot_offset, twin_period, 0)
+        _check(lib().as_synth_twin_links_dev(self._h, P, C.byref(prm), _dp(nxt), _dp(head), self._stream(stream)))
+        return nxt, head
 
 
 def calls_from_device(calls, n_calls) -> np.ndarray:

@@ -158,7 +158,7 @@ int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_
     if (d_twin_next) {
         CU(c->heads.need(sizeof(int32_t) * (size_t)std::max<int64_t>(1, (e - b + 1) / 2 + 1)));
         CU(c->nheads.need(sizeof(uint32_t)));
-        CU(as_launch_noise_twins(d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
+        CU(as_launch_noise_twins(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
                                  (uint32_t*)c->nheads.p, C, (uint32_t)cut, d_thr, d_germ_val, d_germ_state, d_count,
                                  d_nrec, st));
         c->launches += 2;
@@ -256,6 +256,12 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
     std::vector<int32_t> c_next, c_head;
     for (int64_t p = 0; p < P; ++p) {
         if (twin_head[p] == (int32_t)p && twin_next[p] >= 0) {
+            if (AS_INTILE_TWINS && c->noise_cfg != 0) {
+                // a pair inside one 128-slot CTA tile of its host tile was already reduced by the staged kernel
+                // (same predicate as intile_twin_distance in as_kernels.cu)
+                const int64_t t = twin_next[p], tile_start = p / TP * TP;
+                if (t > p && t < P && twin_next[t] < 0 && t / TP == p / TP && (t - tile_start) / 128 == (p - tile_start) / 128) continue;
+            }
             const int32_t head_c = (int32_t)members.size();
             for (int32_t q = (int32_t)p; q >= 0; q = twin_next[q]) {
                 if (q >= P) return fail(AS_EINVAL, "twin_next[%d] out of range", q);
@@ -294,7 +300,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
         CUB(cudaMemcpyAsync(d_next, c_next.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
         CUB(cudaMemcpyAsync(d_head, c_head.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
         char* o = (char*)d_out.p;
-        CUB(as_launch_noise_twins((const uint32_t*)d_cnt.p, S, M, 0, M, d_next, d_head, d_heads, (uint32_t*)c->nheads.p, C,
+        CUB(as_launch_noise_twins(0, (const uint32_t*)d_cnt.p, S, M, 0, M, d_next, d_head, d_heads, (uint32_t*)c->nheads.p, C,
                                   (uint32_t)cut, (float*)(o + ml.thr), (float*)(o + ml.germ_val),
                                   (uint8_t*)(o + ml.germ_state), (uint32_t*)(o + ml.count), (uint32_t*)(o + ml.nrec), st));
         c->launches += 2;
@@ -452,6 +458,16 @@ int as_synth_counts_dev(as_ctx* c, uint32_t* d_counts, int32_t n_samples, int64_
     if (!c || !d_counts || !prm || n_samples < 0 || P < 0) return fail(AS_EINVAL, "bad argument");
     CU(cudaSetDevice(c->device));
     CU(as_launch_synth(d_counts, n_samples, P, d_ref, prm, (cudaStream_t)stream));
+    c->launches += 1;
+    return AS_OK;
+}
+
+int as_synth_twin_links_dev(as_ctx* c, int64_t P, const as_synth_params* prm, int32_t* d_twin_next, int32_t* d_twin_head,
+                            void* stream) {
+    if (!c || !prm || !d_twin_next || !d_twin_head || P < 0) return fail(AS_EINVAL, "bad argument");
+    if (prm->slot_offset % 125 != 0) return fail(AS_EINVAL, "slot_offset must be a multiple of the 125-slot amplicon");
+    CU(cudaSetDevice(c->device));
+    CU(as_launch_synth_twin_links(P, prm, d_twin_next, d_twin_head, (cudaStream_t)stream));
     c->launches += 1;
     return AS_OK;
 }

@@ -83,9 +83,26 @@ noise_main_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t p0
     noise_store(acc, p, thr, germ_val, germ_state, count, nrec);
 }
 
+// A duplicated position whose two slots lie in the same 128-slot CTA tile (the common case: consecutive amplicons
+// overlapping by a few bases put the second enumeration `overlap` slots after the first) is reduced by the thread of
+// its first slot, which reads both records of every sample in file order.  Returns the distance to the twin slot
+// for such a head, 0 otherwise.  idx = index into the twin arrays, gid = panel-global id of that slot, tid = index in
+// the CTA tile, n_slots = valid slots of the tile.  Everything else with twins goes to noise_twin_kernel.
+__device__ __forceinline__ int intile_twin_distance(const int32_t* __restrict__ twin_next,
+                                                    const int32_t* __restrict__ twin_head, int64_t idx, int64_t gid, int tid,
+                                                    int n_slots) {
+    const int32_t nx = twin_next[idx];
+    if (nx < 0 || twin_head[idx] != (int32_t)gid) return 0;
+    const int64_t d = (int64_t)nx - gid;
+    if (d <= 0 || tid + d >= n_slots) return 0;
+    if (twin_next[idx + d] >= 0) return 0;  // three or more enumerations: general kernel
+    return (int)d;
+}
+
 // Finalise one slot: fast-path state, or the general code over global memory when a depth >= 2^24 was seen.
+// twin_d > 0: the slot at distance twin_d belongs to the same position (its rows follow this slot's, per sample).
 __device__ __forceinline__ void noise_finish_slot(FastAcc& f, const uint4* __restrict__ q, int S, int64_t P, float C,
-                                                  uint32_t cut, int64_t p, float* __restrict__ thr,
+                                                  uint32_t cut, int64_t p, int twin_d, float* __restrict__ thr,
                                                   float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
                                                   uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
     NoiseAcc acc;
@@ -95,12 +112,16 @@ __device__ __forceinline__ void noise_finish_slot(FastAcc& f, const uint4* __res
         noise_init(acc);
 #pragma unroll 1
         for (int s = 0; s < S; ++s) {
-            const uint4 fw = ld_stream(q + (int64_t)s * 2 * P);
-            const uint4 bw = ld_stream(q + (int64_t)s * 2 * P + P);
-            noise_accumulate<false>(acc, fw, bw, C, cut);
+#pragma unroll 1
+            for (int r = 0; r <= (twin_d > 0 ? 1 : 0); ++r) {
+                const uint4 fw = ld_stream(q + (int64_t)s * 2 * P + r * twin_d);
+                const uint4 bw = ld_stream(q + (int64_t)s * 2 * P + P + r * twin_d);
+                noise_accumulate<false>(acc, fw, bw, C, cut);
+            }
         }
     }
     noise_store(acc, p, thr, germ_val, germ_state, count, nrec);
+    if (twin_d > 0) noise_store(acc, p + twin_d, thr, germ_val, germ_state, count, nrec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -125,7 +146,13 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
     }
     const int64_t p = tile0 + tid;
     bool active = tid < n_slots;
-    if (active && twin_next != nullptr && (twin_next[p] >= 0 || twin_head[p] != (int32_t)(p + twin_base))) active = false;
+    int twin_d = 0;
+    if (active && twin_next != nullptr) {
+        if (AS_INTILE_TWINS) twin_d = intile_twin_distance(twin_next, twin_head, p, p + twin_base, tid, n_slots);
+        // other members of twin groups are reduced by their head (in this tile) or by noise_twin_kernel
+        if (twin_d == 0 && (twin_next[p] >= 0 || twin_head[p] != (int32_t)(p + twin_base))) active = false;
+    }
+    const int n_rows = (AS_INTILE_TWINS && twin_d > 0) ? 2 : 1;
 
     FastAcc f;
     fast_init(f);
@@ -137,18 +164,21 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (j < k) {
-                    const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid];
-                    const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid];
-                    fast_accumulate(f, fw, bw, C, cut);
+#pragma unroll 1
+                    for (int r = 0; r < n_rows; ++r) {  // the second row only for the head of an in-tile twin pair
+                        const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid + r * twin_d];
+                        const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid + r * twin_d];
+                        fast_accumulate(f, fw, bw, C, cut);
+                    }
                 }
             }
         }
         ring.consumer_release(it);
-        since_fold += K;
+        since_fold += 2 * K;
         if (since_fold >= AS_FOLD_EVERY) { fast_fold(f); since_fold = 0; }
     }
     fast_fold(f);
-    if (active) noise_finish_slot(f, counts + p, S, P, C, cut, p, thr, germ_val, germ_state, count, nrec);
+    if (active) noise_finish_slot(f, counts + p, S, P, C, cut, p, twin_d, thr, germ_val, germ_state, count, nrec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -156,10 +186,17 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
 // slot of a duplicated position feeds ONE estimate (EE:1241-1245), in the order file, then row.
 // ------------------------------------------------------------------------------------------------
 __global__ void twin_heads_kernel(const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head,
-                                  int64_t p0, int64_t p1, int32_t* __restrict__ heads, uint32_t* __restrict__ n_heads) {
+                                  int64_t p0, int64_t p1, int skip_intile, int32_t* __restrict__ heads,
+                                  uint32_t* __restrict__ n_heads) {
     const int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    if (twin_head[p] == (int32_t)p && twin_next[p] >= 0) heads[atomicAdd(n_heads, 1u)] = (int32_t)p;
+    if (twin_head[p] != (int32_t)p || twin_next[p] < 0) return;
+    if (skip_intile) {  // pairs inside one CTA tile of the staged kernel are reduced there
+        const int tid = (int)((p - p0) % AS_TILE_SLOTS);
+        const int n_slots = (int)min((int64_t)AS_TILE_SLOTS, p1 - (p - tid));
+        if (intile_twin_distance(twin_next, twin_head, p, p, tid, n_slots) > 0) return;
+    }
+    heads[atomicAdd(n_heads, 1u)] = (int32_t)p;
 }
 
 __device__ __forceinline__ uint32_t shfl_down_u32(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -588,11 +625,42 @@ __global__ void gammaq_kernel(const double* __restrict__ s, const double* __rest
 // ------------------------------------------------------------------------------------------------
 // synthetic panels generated in HBM; not on the parity path
 // ------------------------------------------------------------------------------------------------
+// Synthetic panel geometry: amplicons of AS_SYNTH_AMPLICON slots; one junction in `twin_period` (0 = none) overlaps
+// the next amplicon by 2..10 positions, which then own two slots each (~1.6 % duplicated slots at
+// period 6).  overlap(a) is the overlap of amplicon a with a+1; it is 0 when a+1 is not completely inside the shard.
+#define AS_SYNTH_AMPLICON 125
+__device__ __forceinline__ int synth_overlap(const as_synth_params& prm, int64_t a, int64_t P) {
+    if (prm.twin_period <= 0 || a < 0) return 0;
+    const int64_t first = prm.slot_offset / AS_SYNTH_AMPLICON;  // shards start on amplicon boundaries
+    if ((a + 2 - first) * AS_SYNTH_AMPLICON > P || a < first) return 0;
+    const uint64_t h = key4(prm.seed, (uint64_t)a, 0x50, 0);
+    return (h % (uint64_t)prm.twin_period) == 0 ? 2 + (int)((h >> 20) % 9) : 0;
+}
+// first slot (global index) of the position that global slot g enumerates
+__device__ __forceinline__ int64_t synth_head(const as_synth_params& prm, int64_t g, int64_t P) {
+    const int64_t a = g / AS_SYNTH_AMPLICON, j = g % AS_SYNTH_AMPLICON;
+    const int ov = synth_overlap(prm, a - 1, P);
+    return j < ov ? (a - 1) * AS_SYNTH_AMPLICON + AS_SYNTH_AMPLICON - ov + j : g;
+}
+
+__global__ void synth_twin_links_kernel(int64_t P, as_synth_params prm, int32_t* __restrict__ twin_next,
+                                        int32_t* __restrict__ twin_head) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const int64_t g = p + prm.slot_offset;
+    const int64_t a = g / AS_SYNTH_AMPLICON, j = g % AS_SYNTH_AMPLICON;
+    twin_head[p] = (int32_t)(synth_head(prm, g, P) - prm.slot_offset);
+    const int ov = synth_overlap(prm, a, P);
+    twin_next[p] = j >= AS_SYNTH_AMPLICON - ov ? (int32_t)((a + 1) * AS_SYNTH_AMPLICON + j - (AS_SYNTH_AMPLICON - ov) - prm.slot_offset)
+                                               : -1;
+}
+
 __global__ void synth_kernel(uint4* __restrict__ counts, int n_samples, int64_t P, uint8_t* __restrict__ ref_out,
                              as_synth_params prm) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
-    const uint64_t gp = (uint64_t)(p + prm.slot_offset);
+    // all randomness is keyed by the POSITION, so the slots of a duplicated position carry identical rows
+    const uint64_t gp = (uint64_t)synth_head(prm, p + prm.slot_offset, P);
     const uint64_t hs = key4(prm.seed, gp, 0x51, 0);
     const uint32_t ref = (uint32_t)(hs & 3);
     if (ref_out != nullptr && blockIdx.y == 0) ref_out[p] = (uint8_t)ref;
@@ -697,15 +765,15 @@ cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64
 }
 
 // 3 launches (memset node + 2 kernels)
-cudaError_t as_launch_noise_twins(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
                                   uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
     if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
     const uint4* c = reinterpret_cast<const uint4*>(d_counts);
     cudaMemsetAsync(d_nheads_scratch, 0, sizeof(uint32_t), st);
-    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, d_heads_scratch,
-                                                           d_nheads_scratch);
+    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, (AS_INTILE_TWINS && cfg != 0) ? 1 : 0,
+                                                           d_heads_scratch, d_nheads_scratch);
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
     noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_heads_scratch, d_nheads_scratch, C, cut, d_thr,
                                             d_germ_val, d_germ_state, d_count, d_nrec);
@@ -782,6 +850,13 @@ cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const fl
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     gammaq_kernel<<<cdiv64(n, 128), 128, 0, st>>>(s, z, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_synth_twin_links(int64_t P, const as_synth_params* prm, int32_t* d_twin_next, int32_t* d_twin_head,
+                                       cudaStream_t st) {
+    if (P <= 0) return cudaSuccess;
+    synth_twin_links_kernel<<<cdiv64(P, 256), 256, 0, st>>>(P, *prm, d_twin_next, d_twin_head);
     return cudaGetLastError();
 }
 

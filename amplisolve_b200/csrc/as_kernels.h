@@ -10,6 +10,9 @@
 #define AS_NOISE_THREADS 128
 #define AS_NOISE_UNROLL 4
 #define AS_CALL_THREADS 128
+/* 1: a duplicated position whose two slots share a CTA tile is reduced inside the staged noise kernel (measured
+ * slower than leaving every twin group to noise_twin_kernel: the extra row loop costs every thread) */
+#define AS_INTILE_TWINS 0
 #define AS_DEFAULT_CALL_KERNEL 3  /* TMA-staged, 4 samples per stage, 2 stages: best of the measured sweep */
 #define AS_DEFAULT_NOISE_KERNEL 1 /* TMA-staged, 4 samples per stage, 3 stages */
 
@@ -17,7 +20,7 @@ cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64
                                  const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base, float C,
                                  uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
                                  uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
-cudaError_t as_launch_noise_twins(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
                                   uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
@@ -29,5 +32,7 @@ cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
                                    double* q, cudaStream_t st);
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);
+cudaError_t as_launch_synth_twin_links(int64_t P, const as_synth_params* prm, int32_t* d_twin_next, int32_t* d_twin_head,
+                                       cudaStream_t st);
 cudaError_t as_launch_synth(uint32_t* d_counts, int n_samples, int64_t P, uint8_t* d_ref, const as_synth_params* prm,
                             cudaStream_t st);

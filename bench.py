@@ -29,7 +29,8 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOAD = {"name": "c3: synthetic 500-gene panel shard per GPU", "slots": 2_000_000, "normals": 100, "tumours": 500,
-            "depth": 2000.0, "C_value": 0.002, "coverage_cutoff": 100, "seed": 20183}
+            "depth": 2000.0, "C_value": 0.002, "coverage_cutoff": 100, "seed": 20183, "somatic_rate": 2e-4, "vaf": (0.01, 0.2),
+            "twin_period": 6}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only when MEASURED_PEAKS.json is absent
 
 
@@ -42,6 +43,10 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=WORKLOAD["slots"], help="slots per GPU (default: the named workload)")
     ap.add_argument("--normals", type=int, default=WORKLOAD["normals"])
     ap.add_argument("--tumours", type=int, default=WORKLOAD["tumours"])
+    ap.add_argument("--depth", type=float, default=WORKLOAD["depth"])
+    ap.add_argument("--somatic-rate", type=float, default=WORKLOAD["somatic_rate"])
+    ap.add_argument("--vaf", type=float, nargs=2, default=list(WORKLOAD["vaf"]))
+    ap.add_argument("--twin-period", type=int, default=WORKLOAD["twin_period"], help="0 = no duplicated positions")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -267,9 +272,16 @@ def run_ours(args):
     C, cut = WORKLOAD["C_value"], WORKLOAD["coverage_cutoff"]
 
     # synthetic inputs generated in HBM, untimed; rank r owns global slots [r*P, (r+1)*P)
-    normals, ref = ctx.synth_counts_dev(S, P, seed=WORKLOAD["seed"], mean_depth=WORKLOAD["depth"], slot_offset=rank * P)
-    tumours, _ = ctx.synth_counts_dev(T, P, seed=WORKLOAD["seed"], mean_depth=WORKLOAD["depth"], somatic_rate=2e-4,
-                                      sample_offset=1 << 20, slot_offset=rank * P, want_ref=False)
+    if P % 125 != 0:
+        raise SystemExit("--slots must be a multiple of the 125-slot synthetic amplicon")
+    gen = dict(seed=WORKLOAD["seed"], mean_depth=args.depth, slot_offset=rank * P, twin_period=args.twin_period)
+    normals, ref = ctx.synth_counts_dev(S, P, **gen)
+    tumours, _ = ctx.synth_counts_dev(T, P, somatic_rate=args.somatic_rate, vaf=tuple(args.vaf), sample_offset=1 << 20,
+                                      want_ref=False, **gen)
+    twin_next = twin_head = None
+    if args.twin_period > 0:   # ~1.6 % of the slots are second enumerations of a position (overlapping amplicons)
+        twin_next, twin_head = ctx.synth_twin_links_dev(P, seed=WORKLOAD["seed"], slot_offset=rank * P,
+                                                        twin_period=args.twin_period)
     out = ctx.alloc_noise_outputs(P)
     view = torch.empty_like(out["thr"])
     cap = max(1 << 16, int(T * P * 0.004))
@@ -283,7 +295,7 @@ def run_ours(args):
     def step(marks=None):
         if marks is not None:
             marks[0].record()
-        ctx.estimate_thresholds_dev(normals, C, cut, out)
+        ctx.estimate_thresholds_dev(normals, C, cut, out, twin_next, twin_head)
         if marks is not None:
             marks[1].record()
         ctx.thresholds_caller_view_dev(out["thr"], view)
@@ -345,14 +357,14 @@ def run_ours(args):
     # ---- end to end through the host-buffer C ABI ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, ctx, normals, tumours, ref, rank, world, barrier)
+        e2e = run_e2e(args, ctx, normals, tumours, ref, twin_next, twin_head, rank, world, barrier)
 
     result = None
     if rank == 0:
         ms_per_step = total_ms / args.steps
         tests_per_step = 6.0 * T * P * world
         peak, peak_src = hbm_peak()
-        default_wl = (P, S, T) == (WORKLOAD["slots"], WORKLOAD["normals"], WORKLOAD["tumours"])
+        default_wl = (P, S, T, args.depth) == (WORKLOAD["slots"], WORKLOAD["normals"], WORKLOAD["tumours"], WORKLOAD["depth"])
         call_bytes = T * P * 32 + P * 33 + found * CALL_DTYPE.itemsize
         noise_bytes = P * (32 * S + 72)
         result = {
@@ -360,8 +372,10 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 scan + f64 incomplete gamma",
             "data": "synthetic (seeded generator in HBM, SURVEY.md 8d)",
-            "config": {"workload": WORKLOAD["name"] if P == WORKLOAD["slots"] else "custom", "slots_per_gpu": P,
-                       "normals": S, "tumours": T, "depth": WORKLOAD["depth"], "C_value": C, "coverage_cutoff": cut,
+            "config": {"workload": WORKLOAD["name"] if default_wl else "custom", "slots_per_gpu": P,
+                       "normals": S, "tumours": T, "depth": args.depth, "C_value": C, "coverage_cutoff": cut,
+                       "duplicated_slots": "none" if twin_next is None else f"one amplicon junction in {args.twin_period} overlaps by 2-10 positions (~1.6 % of slots at 6)",
+                       "somatic_rate": args.somatic_rate, "vaf": list(args.vaf),
                        "sharding": f"positions x{world}, no collective on the data path",
                        "l2": "inputs (6.4 GB normals + 32 GB tumours per step) far larger than the 126 MB L2",
                        "calls_per_step_rank0": found, "call_kernel_variant": args.call_kernel, "noise_kernel_variant": args.noise_kernel},
@@ -392,7 +406,7 @@ def run_ours(args):
     return result
 
 
-def run_e2e(args, ctx, d_normals, d_tumours, d_ref, rank, world, barrier):
+def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, rank, world, barrier):
     """Same step through as_noise_estimate_host / as_call_variants_host: inputs start in pinned HOST memory;
     H2D of all counts and D2H of the noise table and the calls are inside the timed region."""
     import ctypes as C
@@ -427,13 +441,17 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, rank, world, barrier):
     t_n.copy_(d_normals[:, :, :Pe, :])
     t_t.copy_(d_tumours[:, :, :Pe, :])
     h_ref = d_ref[:Pe].cpu().numpy()
+    h_tn = h_th = None
+    if d_twin_next is not None:
+        h_tn, h_th = d_twin_next[:Pe].cpu().numpy().copy(), d_twin_head[:Pe].cpu().numpy().copy()
+        h_tn[h_tn >= Pe] = -1     # a slot prefix of the shard: a pair cut by the prefix end becomes two singletons
     torch.cuda.synchronize()
     cut, Cv = WORKLOAD["coverage_cutoff"], WORKLOAD["C_value"]
     cap = max(1 << 16, int(T * Pe * 0.004))
     stats = {}
 
     def one():
-        noise = ctx.estimate_thresholds(h_norm, Cv, cut)
+        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th)
         view = ctx.thresholds_caller_view_dev(torch.from_numpy(noise["thr"]).cuda()).cpu().numpy()
         calls = ctx.call_variants(h_tum, h_ref, view, cut, cap=cap)
         stats["calls"] = len(calls)

@@ -150,10 +150,15 @@ typedef struct {
     float somatic_vaf_hi; /* e.g. 0.2 */
     float absent_rate;    /* fraction of (sample,slot) records dropped */
     int32_t sample_offset; /* global index of the first sample (decorrelates normals and tumours) */
-    int64_t slot_offset;   /* global index of the first slot (position sharding across GPUs) */
+    int64_t slot_offset;   /* global index of the first slot (position sharding across GPUs); multiple of 125 */
+    int32_t twin_period;   /* 0 = no duplicated positions; n = one amplicon junction in n overlaps by 2..10 positions */
+    int32_t reserved;
 } as_synth_params;
 int as_synth_counts_dev(as_ctx* ctx, uint32_t* d_counts, int32_t n_samples, int64_t P, uint8_t* d_ref,
                         const as_synth_params* prm, void* stream);
+/* twin_next / twin_head [P] of the synthetic panel geometry (125-slot amplicons, see twin_period). */
+int as_synth_twin_links_dev(as_ctx* ctx, int64_t P, const as_synth_params* prm, int32_t* d_twin_next,
+                            int32_t* d_twin_head, void* stream);
 
 /* ---- host side of the two programs (text formats; amplisolve_b200/csrc/as_host.cpp) ---------- */
 /* Iteration order of a libstdc++ std::unordered_map<std::string,std::string> after inserting keys

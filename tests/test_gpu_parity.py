@@ -252,33 +252,43 @@ def test_device_pipeline_matches_host_entry_points(ctx):
 
 
 def test_synthetic_generator_round_trip(ctx):
-    """The HBM generator (bench input) feeds both kernels; a slice is checked against the oracle."""
+    """The HBM generator (bench input, with duplicated positions) feeds both kernels; checked against the oracle."""
     import torch
+    from amplisolve_b200 import calls_from_device
     P, S, T = 3000, 20, 16
-    normals, ref = ctx.synth_counts_dev(S, P, seed=20181, mean_depth=2000.0, absent_rate=0.02)
-    tumours, _ = ctx.synth_counts_dev(T, P, seed=20181, mean_depth=2000.0, somatic_rate=2e-4, sample_offset=1 << 20,
-                                      absent_rate=0.02, want_ref=False)
+    gen = dict(seed=20181, mean_depth=2000.0, absent_rate=0.02, twin_period=3, slot_offset=125 * 40)
+    normals, ref = ctx.synth_counts_dev(S, P, **gen)
+    tumours, _ = ctx.synth_counts_dev(T, P, somatic_rate=2e-4, sample_offset=1 << 20, want_ref=False, **gen)
+    nxt, head = ctx.synth_twin_links_dev(P, seed=20181, slot_offset=125 * 40, twin_period=3)
     out = ctx.alloc_noise_outputs(P)
-    ctx.estimate_thresholds_dev(normals, 0.002, 100, out)
+    ctx.estimate_thresholds_dev(normals, 0.002, 100, out, nxt, head)
     view = ctx.thresholds_caller_view_dev(out["thr"])
     calls = torch.zeros(48 * 200000, dtype=torch.uint8, device="cuda")
     n = torch.zeros(1, dtype=torch.int64, device="cuda")
     ctx.call_variants_dev(tumours, ref, view, 100, calls, n)
-    from amplisolve_b200 import calls_from_device
     got_calls = calls_from_device(calls, n)
     h_norm = normals.cpu().numpy().view(np.uint32)
     h_tum = tumours.cpu().numpy().view(np.uint32)
     h_ref = ref.cpu().numpy()
-    pos_id = np.arange(P, dtype=np.int32)
-    want = oracle_noise(h_norm, pos_id, P, np.float32(0.002), 100)
+    h_head, h_next = head.cpu().numpy(), nxt.cpu().numpy()
+    # geometry: heads point backwards, links are mutual, twins carry identical rows and the same reference base
+    twins = np.nonzero(h_head != np.arange(P))[0]
+    assert 10 < len(twins) < 0.05 * P
+    assert np.array_equal(h_next[h_head[twins]], twins) and (h_head[twins] < twins).all()
+    assert np.array_equal(h_norm[:, :, twins], h_norm[:, :, h_head[twins]]) and np.array_equal(h_ref[twins], h_ref[h_head[twins]])
+    uniq, pos_id = np.unique(h_head, return_inverse=True)
+    pos_id = pos_id.astype(np.int32)
+    U = len(uniq)
+    want = oracle_noise(h_norm, pos_id, U, np.float32(0.002), 100)
     got = {k: v.cpu().numpy() for k, v in out.items()}
     got["count"] = got["count"].view(np.uint32)
     got["nrec"] = got["nrec"].view(np.uint32)
     check_noise(got, want, pos_id)
     thr_u = pyoracle.thr_as_caller_sees(np.where(np.isnan(want["thr"]), np.float32(0.01), want["thr"]))
-    wcalls, _, _ = oracle_calls(h_tum, pos_id, P, h_ref, thr_u, 100)
+    ref_u = np.zeros(U, np.uint8)
+    ref_u[pos_id] = h_ref
+    wcalls, _, _ = oracle_calls(h_tum, pos_id, U, ref_u, thr_u, 100)
     present = h_tum[:, 0, :, 0] != 0xFFFFFFFF
     check_calls(got_calls, wcalls, [np.nonzero(present[s])[0] for s in range(T)])
-    # sanity of the synthetic model itself: depth and sparsity in the intended range
     rd = h_norm.astype(np.int64).sum(axis=(1, 3))[h_norm[:, 0, :, 0] != 0xFFFFFFFF]
     assert 1200 < np.median(rd) < 3000

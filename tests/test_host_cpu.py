@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"{name} is declared in include/amplisolve_b200.h but not exported"
     assert set(api.EXPORTS) == set(declared)
-    assert C.sizeof(api.SynthParams) == 48 and api.CALL_DTYPE.itemsize == 48
+    assert C.sizeof(api.SynthParams) == 56 and api.CALL_DTYPE.itemsize == 48
 
 
 def test_no_cpu_fallback():

@@ -47,7 +47,9 @@ struct as_ctx {
     int call_variant = AS_DEFAULT_CALL_KERNEL;   // 0 straightforward, 1 queued (direct loads), >= 2 TMA-staged (K, stages) variants
     int noise_cfg = AS_DEFAULT_NOISE_KERNEL;      // 0 direct loads, >= 1 TMA-staged (K, stages) variants
     int64_t launches = 0;
-    cudaStream_t copy_stream = nullptr, exec_stream = nullptr;
+    int64_t host_tile_slots = 0;  // 0 = automatic
+    cudaStream_t copy_stream = nullptr, exec_stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
     DevBuf tile[2], out[2], aux[2], misc, calls;  // _host pipelines
@@ -86,6 +88,9 @@ int as_create(int device, as_ctx** out) {
     c->device = device;
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->exec_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -104,6 +109,9 @@ void as_destroy(as_ctx* c) {
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->exec_stream) cudaStreamDestroy(c->exec_stream);
     delete c;
@@ -130,6 +138,11 @@ int as_set_noise_kernel(as_ctx* c, int variant) {
     return AS_OK;
 }
 int64_t as_kernel_launches(const as_ctx* c) { return c ? c->launches : 0; }
+int as_set_host_tile_slots(as_ctx* c, int64_t slots) {
+    if (!c || slots < 0 || (slots % 128) != 0) return fail(AS_EINVAL, "host tile size must be 0 (automatic) or a multiple of 128 slots");
+    c->host_tile_slots = slots;
+    return AS_OK;
+}
 
 static int check_common(as_ctx* c, const void* counts, int32_t n_samples, int64_t P, int64_t b, int64_t e, int32_t cut) {
     if (!c) return fail(AS_EINVAL, "ctx is NULL");
@@ -152,17 +165,23 @@ int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_
     if ((d_twin_next == nullptr) != (d_twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (d_twin_next) {
+        // twin groups (~1-2 % of the slots, scattered reads) write slots the streaming kernel skips: fork them onto a
+        // second stream so they run under the streaming kernel, join before returning control to the caller's stream
+        CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((e - b + 1) / 2 + 1)));
+        CU(c->nheads.need(2 * sizeof(uint32_t)));
+        CU(cudaEventRecord(c->ev_fork, st));
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        CU(as_launch_noise_twins(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
+                                 (uint32_t*)c->nheads.p, C, (uint32_t)cut, d_thr, d_germ_val, d_germ_state, d_count,
+                                 d_nrec, c->aux_stream));
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        c->launches += 3;
+    }
     CU(as_launch_noise_main(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
                             d_germ_state, d_count, d_nrec, st));
     c->launches += 1;
-    if (d_twin_next) {
-        CU(c->heads.need(sizeof(int32_t) * (size_t)std::max<int64_t>(1, (e - b + 1) / 2 + 1)));
-        CU(c->nheads.need(sizeof(uint32_t)));
-        CU(as_launch_noise_twins(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
-                                 (uint32_t*)c->nheads.p, C, (uint32_t)cut, d_thr, d_germ_val, d_germ_state, d_count,
-                                 d_nrec, st));
-        c->launches += 2;
-    }
+    if (d_twin_next) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return AS_OK;
 }
 
@@ -175,7 +194,8 @@ int as_thresholds_caller_view_dev(as_ctx* c, const float* d_thr, float* d_view, 
 }
 
 // Slots per tile of the _host pipelines: ~256 MiB of counts per buffer, multiple of 1024 slots.
-static int64_t tile_slots(int32_t n_samples, int64_t P) {
+static int64_t tile_slots(const as_ctx* c, int32_t n_samples, int64_t P) {
+    if (c->host_tile_slots > 0) return std::min(c->host_tile_slots, std::max<int64_t>(P, 1));
     const int64_t per_slot = 32ll * std::max(1, n_samples);
     int64_t t = (256ll << 20) / per_slot;
     t = std::max<int64_t>(1024, (t / 1024) * 1024);
@@ -210,58 +230,99 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
     if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
     if (P == 0) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(S, P);
+    const int64_t TP = tile_slots(c, S, P);
     const NoiseOutLayout lay(TP);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)std::max(1, S)));
         CU(c->out[i].need(lay.total));
         if (twin_next) CU(c->aux[i].need((size_t)TP * 8));
     }
-    // pass 1: singleton slots, tile by tile (copy of tile i+1 overlaps the kernel of tile i)
+    // pass 1, tile by tile (the copy of tile i+1 overlaps the kernels of tile i): singleton slots by the streaming
+    // kernel, twin groups that lie completely inside the tile by the twin kernels on tile-local links.  A group that
+    // straddles a tile boundary is excluded here (all its members get head = -1) and done in pass 2.
     int64_t ntiles = (P + TP - 1) / TP;
+    int32_t* h_links[2] = {nullptr, nullptr};  // pinned staging of the tile-local links: next[n] | head[n]
+    std::vector<int32_t> crossing;             // heads of the groups that straddle tiles
+    if (twin_next) {
+        for (int i = 0; i < 2; ++i) CU(cudaHostAlloc((void**)&h_links[i], (size_t)TP * 8, cudaHostAllocDefault));
+        CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((TP + 1) / 2 + 1)));
+        CU(c->nheads.need(2 * sizeof(uint32_t)));
+    }
+    int ret1 = AS_OK;
+#define CUT(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret1 = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
     for (int64_t t = 0; t < ntiles; ++t) {
         const int bsel = (int)(t & 1);
         const int64_t p0 = t * TP, n = std::min(TP, P - p0);
-        if (t >= 2) CU(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));  // buffer free again
-        CU(upload_tile(c->tile[bsel].p, counts, S, P, p0, n, c->copy_stream));
+        if (t >= 2) CUT(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));  // buffer free again
+        CUT(upload_tile(c->tile[bsel].p, counts, S, P, p0, n, c->copy_stream));
         int32_t *d_tn = nullptr, *d_th = nullptr;
         if (twin_next) {
+            if (t >= 2) CUT(cudaEventSynchronize(c->ev_up[bsel]));  // the staging block of this buffer has been uploaded
+            int32_t* ln = h_links[bsel];
+            int32_t* lh = ln + n;
+            for (int64_t i = 0; i < n; ++i) {
+                const int64_t g = p0 + i, h = twin_head[g], nx = twin_next[g];
+                if (h == g && nx < 0) { ln[i] = -1; lh[i] = (int32_t)i; continue; }  // singleton
+                bool inside = h >= p0;
+                if (inside && h == g)  // decide once per group, at its head: does the chain stay inside the tile?
+                    for (int64_t q = g; q >= 0; q = twin_next[q])
+                        if (q >= p0 + n) { inside = false; break; }
+                if (inside && h != g) inside = lh[h - p0] >= 0;  // members follow their head's verdict
+                if (inside) {
+                    ln[i] = nx >= 0 ? (int32_t)(nx - p0) : -1;
+                    lh[i] = (int32_t)(h - p0);
+                } else {
+                    ln[i] = -1;
+                    lh[i] = -1;  // neither a singleton nor a head: skipped by every tile kernel
+                    if (h == g) crossing.push_back((int32_t)g);
+                }
+            }
             d_tn = (int32_t*)c->aux[bsel].p;
-            d_th = d_tn + TP;
-            CU(cudaMemcpyAsync(d_tn, twin_next + p0, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
-            CU(cudaMemcpyAsync(d_th, twin_head + p0, (size_t)n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+            d_th = d_tn + n;
+            CUT(cudaMemcpyAsync(d_tn, ln, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
         }
-        CU(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
-        CU(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
+        CUT(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
+        CUT(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
         char* o = (char*)c->out[bsel].p;
-        if (twin_next) CU(cudaMemsetAsync(o, 0, lay.total, c->exec_stream));  // twin members are filled in pass 2
-        CU(as_launch_noise_main(c->noise_cfg, (const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th, p0, C, (uint32_t)cut,
-                                (float*)(o + lay.thr), (float*)(o + lay.germ_val), (uint8_t*)(o + lay.germ_state),
-                                (uint32_t*)(o + lay.count), (uint32_t*)(o + lay.nrec), c->exec_stream));
+        if (twin_next) CUT(cudaMemsetAsync(o, 0, lay.total, c->exec_stream));  // slots of crossing groups are filled in pass 2
+        float* o_thr = (float*)(o + lay.thr);
+        float* o_gv = (float*)(o + lay.germ_val);
+        uint8_t* o_gs = (uint8_t*)(o + lay.germ_state);
+        uint32_t* o_cnt = (uint32_t*)(o + lay.count);
+        uint32_t* o_nrec = (uint32_t*)(o + lay.nrec);
+        CUT(as_launch_noise_main(c->noise_cfg, (const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th, 0, C, (uint32_t)cut,
+                                 o_thr, o_gv, o_gs, o_cnt, o_nrec, c->exec_stream));
         c->launches += 1;
-        CU(cudaMemcpyAsync(thr + p0 * 8, o + lay.thr, (size_t)n * 32, cudaMemcpyDeviceToHost, c->exec_stream));
-        CU(cudaMemcpyAsync(germ_val + p0 * 4, o + lay.germ_val, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
-        CU(cudaMemcpyAsync(count + p0 * 4, o + lay.count, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
-        CU(cudaMemcpyAsync(nrec + p0, o + lay.nrec, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
-        CU(cudaMemcpyAsync(germ_state + p0 * 4, o + lay.germ_state, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
-        CU(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
+        if (twin_next) {
+            CUT(as_launch_noise_twins(c->noise_cfg, (const uint32_t*)c->tile[bsel].p, S, n, 0, n, d_tn, d_th,
+                                      (int32_t*)c->heads.p, (uint32_t*)c->nheads.p, C, (uint32_t)cut, o_thr, o_gv, o_gs, o_cnt,
+                                      o_nrec, c->exec_stream));
+            c->launches += 3;
+        }
+        CUT(cudaMemcpyAsync(thr + p0 * 8, o + lay.thr, (size_t)n * 32, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUT(cudaMemcpyAsync(germ_val + p0 * 4, o + lay.germ_val, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUT(cudaMemcpyAsync(count + p0 * 4, o + lay.count, (size_t)n * 16, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUT(cudaMemcpyAsync(nrec + p0, o + lay.nrec, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUT(cudaMemcpyAsync(germ_state + p0 * 4, o + lay.germ_state, (size_t)n * 4, cudaMemcpyDeviceToHost, c->exec_stream));
+        CUT(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
     }
-    CU(cudaStreamSynchronize(c->exec_stream));
-    CU(cudaStreamSynchronize(c->copy_stream));
-    if (!twin_next) return AS_OK;
+#undef CUT
+    {
+        cudaError_t e1 = cudaStreamSynchronize(c->exec_stream), e2 = cudaStreamSynchronize(c->copy_stream);
+        for (int i = 0; i < 2; ++i)
+            if (h_links[i]) cudaFreeHost(h_links[i]);
+        if (ret1 != AS_OK) return ret1;
+        if (e1 != cudaSuccess || e2 != cudaSuccess)
+            return fail(AS_ECUDA, "noise pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+    }
+    if (!twin_next || crossing.empty()) return AS_OK;
 
-    // pass 2: twin groups.  Their member slots may lie in different tiles, so the records of all members
-    // are gathered (pure data movement) into one compact tensor [S][2][M][4] with compact twin links.
+    // pass 2: the few twin groups whose members lie in different tiles.  Their records are gathered (pure data
+    // movement) into one compact tensor [S][2][M][4] with compact twin links.
     std::vector<int32_t> members;  // compact id -> panel slot
     std::vector<int32_t> c_next, c_head;
-    for (int64_t p = 0; p < P; ++p) {
-        if (twin_head[p] == (int32_t)p && twin_next[p] >= 0) {
-            if (AS_INTILE_TWINS && c->noise_cfg != 0) {
-                // a pair inside one 128-slot CTA tile of its host tile was already reduced by the staged kernel
-                // (same predicate as intile_twin_distance in as_kernels.cu)
-                const int64_t t = twin_next[p], tile_start = p / TP * TP;
-                if (t > p && t < P && twin_next[t] < 0 && t / TP == p / TP && (t - tile_start) / 128 == (p - tile_start) / 128) continue;
-            }
+    for (const int32_t p : crossing) {
+        {
             const int32_t head_c = (int32_t)members.size();
             for (int32_t q = (int32_t)p; q >= 0; q = twin_next[q]) {
                 if (q >= P) return fail(AS_EINVAL, "twin_next[%d] out of range", q);
@@ -285,7 +346,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
     DevBuf d_cnt, d_out, d_links;
     cudaError_t e1 = d_cnt.need((size_t)M * 32 * (size_t)std::max(1, S));
     cudaError_t e2 = d_out.need(ml.total);
-    cudaError_t e3 = d_links.need((size_t)M * 12 + 16);
+    cudaError_t e3 = d_links.need((size_t)M * 16 + 64);
     std::vector<char> h_out(ml.total);
     int ret = AS_OK;
     do {
@@ -295,7 +356,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
         int32_t* d_heads = d_head + M;
         cudaStream_t st = c->exec_stream;
 #define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
-        CUB(c->nheads.need(sizeof(uint32_t)));
+        CUB(c->nheads.need(2 * sizeof(uint32_t)));
         CUB(cudaMemcpyAsync(d_cnt.p, h_gather, (size_t)M * 32 * (size_t)S, cudaMemcpyHostToDevice, st));
         CUB(cudaMemcpyAsync(d_next, c_next.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
         CUB(cudaMemcpyAsync(d_head, c_head.data(), (size_t)M * 4, cudaMemcpyHostToDevice, st));
@@ -303,7 +364,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
         CUB(as_launch_noise_twins(0, (const uint32_t*)d_cnt.p, S, M, 0, M, d_next, d_head, d_heads, (uint32_t*)c->nheads.p, C,
                                   (uint32_t)cut, (float*)(o + ml.thr), (float*)(o + ml.germ_val),
                                   (uint8_t*)(o + ml.germ_state), (uint32_t*)(o + ml.count), (uint32_t*)(o + ml.nrec), st));
-        c->launches += 2;
+        c->launches += 3;
         CUB(cudaMemcpyAsync(h_out.data(), o, ml.total, cudaMemcpyDeviceToHost, st));
         CUB(cudaStreamSynchronize(st));
 #undef CUB
@@ -344,7 +405,7 @@ int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t 
     *n_calls = 0;
     if (P == 0 || T == 0) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(T, P);
+    const int64_t TP = tile_slots(c, T, P);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)T));
         CU(c->aux[i].need((size_t)TP * 36));  // thr_view (32 B/slot) + ref (1 B/slot, padded)

@@ -185,18 +185,126 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
 // noise model, twin groups: the reference keys records by "chrom_pos" text, so every row of every
 // slot of a duplicated position feeds ONE estimate (EE:1241-1245), in the order file, then row.
 // ------------------------------------------------------------------------------------------------
+// Heads of twin groups in [p0, p1): 2-chains (a position enumerated twice, by far the common case) go to the pair
+// list, longer chains to the general list.  counters[0] = pairs, counters[1] = longer groups.
 __global__ void twin_heads_kernel(const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head,
-                                  int64_t p0, int64_t p1, int skip_intile, int32_t* __restrict__ heads,
-                                  uint32_t* __restrict__ n_heads) {
+                                  int64_t p0, int64_t p1, int skip_intile, int32_t* __restrict__ pairs,
+                                  int32_t* __restrict__ groups, uint32_t* __restrict__ counters) {
     const int64_t p = p0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= p1) return;
-    if (twin_head[p] != (int32_t)p || twin_next[p] < 0) return;
+    const int32_t nx = twin_next[p];
+    if (twin_head[p] != (int32_t)p || nx < 0) return;
     if (skip_intile) {  // pairs inside one CTA tile of the staged kernel are reduced there
         const int tid = (int)((p - p0) % AS_TILE_SLOTS);
         const int n_slots = (int)min((int64_t)AS_TILE_SLOTS, p1 - (p - tid));
         if (intile_twin_distance(twin_next, twin_head, p, p, tid, n_slots) > 0) return;
     }
-    heads[atomicAdd(n_heads, 1u)] = (int32_t)p;
+    if (twin_next[nx] < 0)
+        pairs[atomicAdd(&counters[0], 1u)] = (int32_t)p;
+    else
+        groups[atomicAdd(&counters[1], 1u)] = (int32_t)p;
+}
+
+// Twin pairs: a warp takes eight pairs, four lanes per pair (one per base), and walks the samples in file order (slot
+// a's row, then slot b's row) with the fast-path arithmetic -- no partial-state merge.  The 32 lanes first fetch the
+// 4 words (fw/bw of a and b) x 8 pairs of AS_PAIR_BATCH samples into a per-warp shared-memory block, so that
+// AS_PAIR_BATCH scattered 16-byte reads per lane are in flight at once; then every lane reads its pair's four words
+// back (broadcast within the quad).
+#define AS_PAIR_BATCH 8
+__global__ void __launch_bounds__(128)
+noise_pair_kernel(const uint4* __restrict__ counts, int S, int64_t P, const int32_t* __restrict__ twin_next,
+                  const int32_t* __restrict__ pairs, const uint32_t* __restrict__ counters, float C, uint32_t cut,
+                  float* __restrict__ thr, float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
+                  uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
+    __shared__ __align__(16) uint4 stage_all[4][AS_PAIR_BATCH][32];
+    const int lane = threadIdx.x & 31, base = lane & 3, quad0 = lane & ~3;
+    uint4 (*stage)[32] = stage_all[threadIdx.x >> 5];
+    const uint32_t n = counters[0];
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const int64_t sstride = 2 * P;
+    for (uint32_t wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wg * 8 < n; wg += warps) {
+        const uint32_t g = wg * 8 + (lane >> 2);
+        const bool valid = g < n;
+        const int32_t a = valid ? pairs[g] : 0;
+        const int32_t b = valid ? twin_next[a] : 0;
+        // this lane fetches word `base` of its pair: 0 = fw(a), 1 = bw(a), 2 = fw(b), 3 = bw(b)
+        const uint4* src = counts + ((base & 2) ? b : a) + ((base & 1) ? P : 0);
+        FastBase f;
+        f.s_b_fw = f.s_b_bw = 0u;
+        f.s_d_fw = f.s_d_bw = f.s_p_fw = f.s_p_bw = 0.0;
+        f.count = 0u; f.g_x = 1u; f.g_rd = 0u;
+        uint32_t n_records = 0, big = 0;
+        int since_fold = 0;
+        for (int s0 = 0; s0 < S; s0 += AS_PAIR_BATCH) {
+            const int k = min(AS_PAIR_BATCH, S - s0);
+            uint4 w[AS_PAIR_BATCH];
+#pragma unroll
+            for (int j = 0; j < AS_PAIR_BATCH; ++j)
+                if (j < k && valid) w[j] = ld_stream(src + (int64_t)(s0 + j) * sstride);
+            __syncwarp();  // the previous batch has been consumed
+#pragma unroll
+            for (int j = 0; j < AS_PAIR_BATCH; ++j)
+                if (j < k && valid) stage[j][lane] = w[j];
+            __syncwarp();
+            if (valid) {
+#pragma unroll 2
+                for (int j = 0; j < k; ++j) {
+#pragma unroll
+                    for (int row = 0; row < 2; ++row) {
+                        const uint4 fw = stage[j][quad0 + 2 * row], bw = stage[j][quad0 + 2 * row + 1];
+                        if ((int32_t)fw.x >= 0) {
+                            FastRecord r;
+                            n_records += 1;
+                            fast_record(r, fw, bw, C, cut);
+                            big |= r.RD;
+                            fast_base_update(f, r, comp(fw, base), comp(bw, base));
+                        }
+                    }
+                }
+            }
+            since_fold += 2 * AS_PAIR_BATCH;
+            if (since_fold >= AS_FOLD_EVERY) {
+                f.s_p_fw = __dadd_rn(f.s_p_fw, u32_to_double(f.s_b_fw));
+                f.s_p_bw = __dadd_rn(f.s_p_bw, u32_to_double(f.s_b_bw));
+                f.s_b_fw = f.s_b_bw = 0u;
+                since_fold = 0;
+            }
+        }
+        const bool redo = valid && big >= (1u << 24);
+        if (redo && base == 0) {
+            // a depth of 2^24 or more: int -> float is inexact, the lane of base A redoes the pair with the general code
+            NoiseAcc acc;
+            noise_init(acc);
+            const uint4 *qa = counts + a, *qb = counts + b;
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) {
+                noise_accumulate<false>(acc, ld_stream(qa + (int64_t)s * sstride), ld_stream(qa + (int64_t)s * sstride + P), C, cut);
+                noise_accumulate<false>(acc, ld_stream(qb + (int64_t)s * sstride), ld_stream(qb + (int64_t)s * sstride + P), C, cut);
+            }
+            noise_store(acc, a, thr, germ_val, germ_state, count, nrec);
+            noise_store(acc, b, thr, germ_val, germ_state, count, nrec);
+        }
+        NoiseBase nb;
+        fast_base_to_general(f, nb);
+        float q_fw, q_bw, gv;
+        uint32_t st;
+        noise_final_base(nb, n_records, base, q_fw, q_bw, gv, st);
+        // gather the four bases on the quad's first lane
+        float t[8], gg[4];
+        uint32_t c[4], gs = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            t[2 * i] = __shfl_sync(0xffffffffu, q_fw, quad0 + i);
+            t[2 * i + 1] = __shfl_sync(0xffffffffu, q_bw, quad0 + i);
+            gg[i] = __shfl_sync(0xffffffffu, gv, quad0 + i);
+            c[i] = __shfl_sync(0xffffffffu, nb.count, quad0 + i);
+            gs |= __shfl_sync(0xffffffffu, st, quad0 + i) << (8 * i);
+        }
+        if (valid && !redo && base == 0) {
+            noise_store_raw(a, t, gg, gs, c, n_records, thr, germ_val, germ_state, count, nrec);
+            noise_store_raw(b, t, gg, gs, c, n_records, thr, germ_val, germ_state, count, nrec);
+        }
+    }
 }
 
 __device__ __forceinline__ uint32_t shfl_down_u32(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
@@ -224,12 +332,12 @@ __device__ __forceinline__ void noise_shfl_down(NoiseAcc& r, const NoiseAcc& a, 
 // record is dropped" semantics (EE:1258-1262) exact.
 __global__ void __launch_bounds__(128)
 noise_twin_kernel(const uint4* __restrict__ counts, int S, int64_t P, const int32_t* __restrict__ twin_next,
-                  const int32_t* __restrict__ heads, const uint32_t* __restrict__ n_heads, float C, uint32_t cut,
+                  const int32_t* __restrict__ heads, const uint32_t* __restrict__ counters, float C, uint32_t cut,
                   float* __restrict__ thr, float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
                   uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n = *n_heads;
+    const uint32_t n = counters[1];
     const int per = (S + 31) / 32;
     const int64_t sstride = 2 * P;
     for (uint32_t g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n; g += warps) {
@@ -764,19 +872,27 @@ cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64
 #undef AS_NOISE_ARGS
 }
 
-// 3 launches (memset node + 2 kernels)
+// 4 launches (memset node + 3 kernels).  d_heads_scratch holds n slots of int32 (pairs in the first half, longer
+// groups in the second), d_counters two uint32.
 cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
-                                  uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
+                                  uint32_t* d_counters, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
     if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
     const uint4* c = reinterpret_cast<const uint4*>(d_counts);
-    cudaMemsetAsync(d_nheads_scratch, 0, sizeof(uint32_t), st);
+    const int64_t half = (p1 - p0 + 1) / 2 + 1;
+    int32_t* d_pairs = d_heads_scratch;
+    int32_t* d_groups = d_heads_scratch + half;
+    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), st);
     twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, (AS_INTILE_TWINS && cfg != 0) ? 1 : 0,
-                                                           d_heads_scratch, d_nheads_scratch);
-    const unsigned grid = (unsigned)std::min<int64_t>(148 * 8, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
-    noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_heads_scratch, d_nheads_scratch, C, cut, d_thr,
-                                            d_germ_val, d_germ_state, d_count, d_nrec);
+                                                           d_pairs, d_groups, d_counters);
+    // pairs: at most (p1-p0)/2 quads; enough CTAs to cover a typical panel (~1 % of the slots) in one pass
+    const unsigned pair_grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (p1 - p0) / 64 / 32 + 1));  // 32 pairs per CTA
+    noise_pair_kernel<<<pair_grid, 128, 0, st>>>(c, S, P, d_twin_next, d_pairs, d_counters, C, cut, d_thr, d_germ_val,
+                                                 d_germ_state, d_count, d_nrec);
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 2, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
+    noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_groups, d_counters, C, cut, d_thr, d_germ_val,
+                                            d_germ_state, d_count, d_nrec);
     return cudaGetLastError();
 }
 

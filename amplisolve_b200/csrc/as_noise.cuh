@@ -161,57 +161,70 @@ __device__ __forceinline__ void fast_fold(FastAcc& a) {
     }
 }
 
+// what one record contributes to every base of its slot
+struct FastRecord {
+    int32_t lim_fw, lim_bw, lim_rd;  // 5 % limits (af_limit), or -1 when the coverage gate fails: every signed test fails
+    uint32_t RD;
+    double d_fw, d_bw, p_fw, p_bw;   // strand depths and float(depth)*float(C), as exact doubles
+};
+
+__device__ __forceinline__ void fast_record(FastRecord& r, const uint4 fw, const uint4 bw, const float C,
+                                            const uint32_t cut) {
+    const uint32_t FW = fw.x + fw.y + fw.z + fw.w;
+    const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
+    r.RD = FW + BW;
+    const bool cov = min(FW, BW) >= cut;  // counts are < 2^31, so the signed compares below are safe
+    r.lim_fw = cov ? (int32_t)af_limit(FW) : -1;
+    r.lim_bw = cov ? (int32_t)af_limit(BW) : -1;
+    r.lim_rd = cov ? (int32_t)af_limit(r.RD) : -1;
+    r.d_fw = u32_to_double(FW);
+    r.d_bw = u32_to_double(BW);
+    r.p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);
+    r.p_bw = (double)__fmul_rn(__uint2float_rn(BW), C);
+}
+
+__device__ __forceinline__ void fast_base_update(FastBase& s, const FastRecord& r, const uint32_t bf, const uint32_t bb) {
+    if (((int32_t)bf <= r.lim_fw) & ((int32_t)bb <= r.lim_bw)) {
+        s.s_b_fw += bf; s.s_b_bw += bb;
+        s.s_d_fw = __dadd_rn(s.s_d_fw, r.d_fw); s.s_d_bw = __dadd_rn(s.s_d_bw, r.d_bw);
+        s.s_p_fw = __dadd_rn(s.s_p_fw, r.p_fw); s.s_p_bw = __dadd_rn(s.s_p_bw, r.p_bw);
+        s.count += 1;
+    }
+    const uint32_t x = bf + bb;
+    const bool qual = (int32_t)x <= r.lim_rd;
+    // bitwise &: both products are always formed so that the update is predicated, not branched
+    const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * r.RD;  // EE:1263: value <= AF
+    const bool first = qual & (s.g_rd == 0u);
+    const bool upd = qual & ge;
+    s.g_x = first ? 0u : (upd ? x : s.g_x);
+    s.g_rd = first ? 1u : (upd ? r.RD : s.g_rd);
+}
+
 __device__ __forceinline__ void fast_accumulate(FastAcc& a, const uint4 fw, const uint4 bw, const float C,
                                                 const uint32_t cut) {
     if ((int32_t)fw.x < 0) return;  // AS_ABSENT
     a.nrec += 1;
-    const uint32_t FW = fw.x + fw.y + fw.z + fw.w;
-    const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
-    const uint32_t RD = FW + BW;
-    a.big |= RD;
-    // coverage gate folded into the limits: a limit of -1 fails every (signed) comparison; counts are < 2^31
-    const bool cov = min(FW, BW) >= cut;
-    const int32_t lim_fw = cov ? (int32_t)af_limit(FW) : -1;
-    const int32_t lim_bw = cov ? (int32_t)af_limit(BW) : -1;
-    const int32_t lim_rd = cov ? (int32_t)af_limit(RD) : -1;
-    const double d_fw = u32_to_double(FW), d_bw = u32_to_double(BW);
-    const double p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);
-    const double p_bw = (double)__fmul_rn(__uint2float_rn(BW), C);
+    FastRecord r;
+    fast_record(r, fw, bw, C, cut);
+    a.big |= r.RD;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        FastBase& s = a.b[i];
-        const uint32_t bf = comp(fw, i), bb = comp(bw, i);
-        if (((int32_t)bf <= lim_fw) & ((int32_t)bb <= lim_bw)) {
-            s.s_b_fw += bf; s.s_b_bw += bb;
-            s.s_d_fw = __dadd_rn(s.s_d_fw, d_fw); s.s_d_bw = __dadd_rn(s.s_d_bw, d_bw);
-            s.s_p_fw = __dadd_rn(s.s_p_fw, p_fw); s.s_p_bw = __dadd_rn(s.s_p_bw, p_bw);
-            s.count += 1;
-        }
-        const uint32_t x = bf + bb;
-        const bool qual = (int32_t)x <= lim_rd;
-        // bitwise &: both products are always formed so that the update is predicated, not branched
-        const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * RD;  // EE:1263: value <= AF
-        const bool first = qual & (s.g_rd == 0u);
-        const bool upd = qual & ge;
-        s.g_x = first ? 0u : (upd ? x : s.g_x);
-        s.g_rd = first ? 1u : (upd ? RD : s.g_rd);
-    }
+    for (int i = 0; i < 4; ++i) fast_base_update(a.b[i], r, comp(fw, i), comp(bw, i));
+}
+
+__device__ __forceinline__ void fast_base_to_general(const FastBase& s, NoiseBase& d) {
+    d.s_b_fw = s.s_b_fw; d.s_b_bw = s.s_b_bw;
+    d.s_d_fw = (unsigned long long)__double2ll_rn(s.s_d_fw); d.s_d_bw = (unsigned long long)__double2ll_rn(s.s_d_bw);
+    d.s_p_fw = s.s_p_fw; d.s_p_bw = s.s_p_bw;
+    d.count = s.count;
+    d.g_n = s.g_rd == 0u ? 0u : (s.g_rd == 1u ? 1u : 2u);
+    d.g_x = s.g_x; d.g_rd = s.g_rd == 0u ? 1u : s.g_rd;
+    d.g_first_x = 0; d.g_first_rd = 1;
 }
 
 __device__ __forceinline__ void fast_to_general(const FastAcc& f, NoiseAcc& a) {
     a.nrec = f.nrec;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const FastBase& s = f.b[i];
-        NoiseBase& d = a.b[i];
-        d.s_b_fw = s.s_b_fw; d.s_b_bw = s.s_b_bw;
-        d.s_d_fw = (unsigned long long)__double2ll_rn(s.s_d_fw); d.s_d_bw = (unsigned long long)__double2ll_rn(s.s_d_bw);
-        d.s_p_fw = s.s_p_fw; d.s_p_bw = s.s_p_bw;
-        d.count = s.count;
-        d.g_n = s.g_rd == 0u ? 0u : (s.g_rd == 1u ? 1u : 2u);
-        d.g_x = s.g_x; d.g_rd = s.g_rd == 0u ? 1u : s.g_rd;
-        d.g_first_x = 0; d.g_first_rd = 1;
-    }
+    for (int i = 0; i < 4; ++i) fast_base_to_general(f.b[i], a.b[i]);
 }
 
 // Merge the state R of a LATER record segment into L (earlier).  Associative.
@@ -242,41 +255,53 @@ __device__ __forceinline__ void noise_merge(NoiseAcc& L, const NoiseAcc& R) {
     }
 }
 
-// Per-position finalise (EE:1742-1797) and store for one slot.
-__device__ __forceinline__ void noise_store(const NoiseAcc& a, int64_t slot, float* __restrict__ thr,
-                                            float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
-                                            uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
-    float t[8], g[4];
-    uint32_t c[4];
-    uint32_t gs = 0;
-    const double n_rule = __dmul_rn(0.338, (double)a.nrec);  // EE:1742
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const NoiseBase& s = a.b[i];
-        float q_fw, q_bw;
-        if ((double)s.count < n_rule) {
-            q_fw = q_bw = __int_as_float(0x7fc00000);  // "-1_-1"
-        } else {
-            const double nt_fw = __dadd_rn((double)s.s_b_fw, s.s_p_fw);
-            const double nt_bw = __dadd_rn((double)s.s_b_bw, s.s_p_bw);
-            q_fw = __fdiv_rn(__double2float_rn(nt_fw), __double2float_rn((double)s.s_d_fw));  // EE:1762
-            q_bw = __fdiv_rn(__double2float_rn(nt_bw), __double2float_rn((double)s.s_d_bw));  // EE:1763
-            if (isnan(q_fw) || isnan(q_bw)) q_fw = q_bw = __int_as_float(0x7fc00000);         // EE:1765-1770
-        }
-        t[2 * i] = q_fw; t[2 * i + 1] = q_bw;
-        c[i] = s.count;
-        const uint32_t st = s.g_n == 0 ? 0u : (s.g_n == 1 ? 1u : 2u);
-        gs |= st << (8 * i);
-        g[i] = st == 2 ? __fdiv_rn(__uint2float_rn(s.g_x), __uint2float_rn(s.g_rd))  // EE:1229-1232
-                       : (i == 0 ? -888.0f : 0.0f);                                     // EE:1260, EE:1318
+// Per-(position, base) finalise (EE:1742-1797, EE:1258-1270): the two thresholds (NaN = "-1_-1"), the Germ_Max value
+// and its state (0 absent, 1 one record = the floor, 2 value).
+__device__ __forceinline__ void noise_final_base(const NoiseBase& s, const uint32_t n_records, const int i, float& q_fw,
+                                                 float& q_bw, float& g, uint32_t& st) {
+    const double n_rule = __dmul_rn(0.338, (double)n_records);  // EE:1742
+    if ((double)s.count < n_rule) {
+        q_fw = q_bw = __int_as_float(0x7fc00000);  // "-1_-1"
+    } else {
+        const double nt_fw = __dadd_rn((double)s.s_b_fw, s.s_p_fw);
+        const double nt_bw = __dadd_rn((double)s.s_b_bw, s.s_p_bw);
+        q_fw = __fdiv_rn(__double2float_rn(nt_fw), __double2float_rn((double)s.s_d_fw));  // EE:1762
+        q_bw = __fdiv_rn(__double2float_rn(nt_bw), __double2float_rn((double)s.s_d_bw));  // EE:1763
+        if (isnan(q_fw) || isnan(q_bw)) q_fw = q_bw = __int_as_float(0x7fc00000);         // EE:1765-1770
     }
+    st = s.g_n == 0 ? 0u : (s.g_n == 1 ? 1u : 2u);
+    g = st == 2 ? __fdiv_rn(__uint2float_rn(s.g_x), __uint2float_rn(s.g_rd))  // EE:1229-1232
+                : (i == 0 ? -888.0f : 0.0f);                                     // EE:1260, EE:1318
+}
+
+__device__ __forceinline__ void noise_store_raw(int64_t slot, const float (&t)[8], const float (&g)[4], const uint32_t gs,
+                                                const uint32_t (&c)[4], const uint32_t n_records, float* __restrict__ thr,
+                                                float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
+                                                uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
     float4* t4 = reinterpret_cast<float4*>(thr + slot * 8);
     t4[0] = make_float4(t[0], t[1], t[2], t[3]);
     t4[1] = make_float4(t[4], t[5], t[6], t[7]);
     *reinterpret_cast<float4*>(germ_val + slot * 4) = make_float4(g[0], g[1], g[2], g[3]);
     *reinterpret_cast<uint32_t*>(germ_state + slot * 4) = gs;
     *reinterpret_cast<uint4*>(count + slot * 4) = make_uint4(c[0], c[1], c[2], c[3]);
-    nrec[slot] = a.nrec;
+    nrec[slot] = n_records;
+}
+
+// Per-position finalise and store for one slot.
+__device__ __forceinline__ void noise_store(const NoiseAcc& a, int64_t slot, float* __restrict__ thr,
+                                            float* __restrict__ germ_val, uint8_t* __restrict__ germ_state,
+                                            uint32_t* __restrict__ count, uint32_t* __restrict__ nrec) {
+    float t[8], g[4];
+    uint32_t c[4];
+    uint32_t gs = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t st;
+        noise_final_base(a.b[i], a.nrec, i, t[2 * i], t[2 * i + 1], g[i], st);
+        c[i] = a.b[i].count;
+        gs |= st << (8 * i);
+    }
+    noise_store_raw(slot, t, g, gs, c, a.nrec, thr, germ_val, germ_state, count, nrec);
 }
 
 }  // namespace asdev

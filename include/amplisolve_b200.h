@@ -84,6 +84,9 @@ int as_host_free(void* p);
  *   noise : 0 = direct loads, 1..6 = TMA-staged with (4,3) default, (4,4), (2,4), (8,2), (8,3), (4,2) */
 int as_set_call_kernel(as_ctx* ctx, int variant);
 int as_set_noise_kernel(as_ctx* ctx, int variant);
+/* Slots per tile of the _host pipelines: 0 = automatic (~256 MiB of counts per buffer), else a multiple of 128.
+ * Small values are for tests (tile-boundary handling). */
+int as_set_host_tile_slots(as_ctx* ctx, int64_t slots);
 /* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
 int64_t as_kernel_launches(const as_ctx* ctx);
 

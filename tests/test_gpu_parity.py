@@ -219,6 +219,32 @@ def test_calls_match_oracle(ctx, variant, T, n_amp, depth, cut, seed):
     check_calls(got, want, rows_slot)
 
 
+@pytest.mark.parametrize("tile", [128, 512, 1024])
+def test_host_pipelines_across_tile_boundaries(ctx, tile):
+    """The _host entry points tile over slots; twin groups that straddle a tile boundary take the gather path."""
+    _, slots, pos_id, U = synth.make_panel(60, seed=41, overlap_frac=0.7)
+    P = len(slots)
+    normals, ref = synth.make_counts(11, P, depth=1500, seed=41, pos_id=pos_id)
+    tumours, _ = synth.make_counts(9, P, depth=1500, seed=42, ref=ref, pos_id=pos_id, somatic_rate=0.02)
+    nxt, head = ctx_twins(pos_id)
+    crossing = sum(1 for p in range(P) if nxt[p] >= 0 and nxt[p] // tile != p // tile)
+    assert crossing > 0
+    ctx.set_host_tile_slots(tile)
+    try:
+        got = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head)
+        want = oracle_noise(normals, pos_id, U, np.float32(0.002), 100)
+        check_noise(got, want, pos_id)
+        thr_u = pyoracle.thr_as_caller_sees(np.where(np.isnan(want["thr"]), np.float32(0.01), want["thr"]))
+        ref_u = np.zeros(U, np.uint8)
+        ref_u[pos_id] = ref
+        calls = ctx.call_variants(tumours, ref_u[pos_id], thr_u[pos_id], 100)
+    finally:
+        ctx.set_host_tile_slots(0)
+    wcalls, _, _ = oracle_calls(tumours, pos_id, U, ref_u, thr_u, 100)
+    present = tumours[:, 0, :, 0] != 0xFFFFFFFF
+    check_calls(calls, wcalls, [np.nonzero(present[s])[0] for s in range(9)])
+
+
 def test_device_pipeline_matches_host_entry_points(ctx):
     """_dev entry points (inputs resident in HBM, torch tensors) == _host entry points, incl. slot ranges."""
     import torch

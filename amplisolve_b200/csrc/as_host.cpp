@@ -327,6 +327,22 @@ bool load_all(const std::vector<CountFile>& files, const Panel& panel, uint32_t*
     return true;
 }
 
+template <class F>
+void parallel_for(size_t n, F body) {
+    if (n == 0) return;
+    std::atomic<size_t> next(0);
+    const size_t grain = 256;
+    auto work = [&]() {
+        for (size_t b = next.fetch_add(grain); b < n; b = next.fetch_add(grain))
+            for (size_t i = b; i < std::min(n, b + grain); ++i) body(i);
+    };
+    const unsigned hw = (unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), (n + grain - 1) / grain));
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
 bool make_dir(const std::string& path) {  // mkdir -p (EE:3079)
     std::string cur;
     for (size_t i = 0; i <= path.size(); ++i) {
@@ -348,6 +364,28 @@ std::string arg_value(const char* arg, const char* key) {  // sscanf(arg, "key=%
     while (*q && *q != ' ' && *q != '\t' && *q != '\n') ++q;
     return std::string(p, q);
 }
+
+// AS_TIMING=1 in the environment prints one "AS_TIMING <phase> <seconds>" line per phase on stderr
+// (stdout stays what the reference prints)
+struct PhaseTimer {
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    PhaseTimer() : on(getenv("AS_TIMING") != nullptr), t0(now()) {}
+    void lap(const char* phase, double units = 0, const char* unit = "") {
+        const double t1 = now();
+        if (on) {
+            fprintf(stderr, "AS_TIMING %s %.6f", phase, t1 - t0);
+            if (units > 0) fprintf(stderr, " (%.3g %s/s)", units / (t1 - t0), unit);
+            fprintf(stderr, "\n");
+        }
+        t0 = t1;
+    }
+};
 
 struct Pinned {
     void* p = nullptr;
@@ -559,6 +597,7 @@ int as_error_estimation_main(int argc, char** argv) {
     const std::string stem = interm + "/" + std::to_string(seed);
 
     // panel enumeration, reference bases, duplicated positions (replaces generateReferenceBases, EE:578-670)
+    PhaseTimer timer;
     std::cout << "\nRunning function generateReferenceBases: ";
     Panel panel;
     int n_amplicons = 0;
@@ -590,6 +629,7 @@ int as_error_estimation_main(int argc, char** argv) {
     std::cout << "Running function storeReference: panel reference bases stored with success " << GREEN << panel.first_slot.size()
               << RESET << std::endl;
 
+    timer.lap("panel_and_reference_bases", (double)P, "positions");
     const char* header =
         "chrom\tposition\treference\tduplicate\tThres_A\tThres_C\tThres_G\tThres_T\tGerm_Max_A\tGerm_Max_C\tGerm_Max_G\tGerm_Max_T";
     if (!with_germlines) {
@@ -633,6 +673,11 @@ int as_error_estimation_main(int argc, char** argv) {
         return 0;
     }
     report_load(files, stats);
+    {
+        double rows = 0;
+        for (const AseqStats& st : stats) rows += (double)st.rows;
+        timer.lap("parse_normals", rows, "rows");
+    }
 
     std::cout << "Running function estimateThresholds: ";
     std::vector<float> thr((size_t)P * 8), germ_val((size_t)P * 4);
@@ -643,6 +688,7 @@ int as_error_estimation_main(int argc, char** argv) {
                                           germ_val.data(), germ_state.data(), count.data(), nrec.data());
     as_destroy(ctx);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
+    timer.lap("noise_model_gpu", (double)P, "positions");
     std::cout << "thresholds for " << panel.first_slot.size() << " positions estimated on the GPU" << std::endl;
 
     // generateFinalOutput (EE:2546-2944)
@@ -676,6 +722,7 @@ int as_error_estimation_main(int argc, char** argv) {
             output << std::endl;
         }
     }
+    timer.lap("write_noise_table", (double)P, "rows");
     char msg_name[4096];
     snprintf(msg_name, sizeof msg_name, "%s/positionSpecific_%.4f.txt", output_dir.c_str(), C_value_float);  // sic, EE:458
     std::cout << "\nAmpliSolveErrorEstimation execution was successful. Results can be found at: " << YELLOW << msg_name << RESET
@@ -732,6 +779,7 @@ int as_variant_calling_main(int argc, char** argv) {
         return 0;
     }
 
+    PhaseTimer timer;
     // ---- noise table (storeInputFile, VC:430-576): one slot per row; also re-emits the dummy VCF (VC:564)
     Panel panel;
     std::vector<float> thr_view;              // [P][4][2] through std::stof (VC:889-890)
@@ -813,6 +861,7 @@ int as_variant_calling_main(int argc, char** argv) {
         else if (r == "T") ref_code[i] = 3;
     }
 
+    timer.lap("parse_noise_table", (double)P, "rows");
     // ---- tumour files in the reference's order
     srand((unsigned)time(nullptr));
     const int seed = rand() % 1000;  // VC:328-331
@@ -842,6 +891,11 @@ int as_variant_calling_main(int argc, char** argv) {
     report_load(files, stats);
     for (int i = 0; i < T; ++i)
         for (int64_t k = 0; k < stats[i].outside; ++k) std::cout << "mistake..." << std::endl;  // VC:847-852
+    {
+        double rows = 0;
+        for (const AseqStats& st : stats) rows += (double)st.rows;
+        timer.lap("parse_tumours", rows, "rows");
+    }
 
     // ---- the hot path on the GPU
     std::vector<as_call> calls;
@@ -867,6 +921,19 @@ int as_variant_calling_main(int argc, char** argv) {
         });
     }
     as_destroy(ctx);
+    timer.lap("caller_gpu", 6.0 * (double)T * (double)P, "tests");
+
+    // Fisher strand-bias p of every call (VC:902), in parallel: independent per call, deterministic
+    const uint32_t* cnt = (const uint32_t*)counts.p;
+    std::vector<double> fisher_p(calls.size());
+    parallel_for(calls.size(), [&](size_t i) {
+        const as_call& c = calls[i];
+        const uint32_t* fw = cnt + ((size_t)c.sample * 2 * P + c.slot) * 4;
+        const uint32_t* bw = cnt + ((size_t)c.sample * 2 * P + P + c.slot) * 4;
+        fisher_p[i] = fisher_test((int)(fw[0] + fw[1] + fw[2] + fw[3]), (int)(bw[0] + bw[1] + bw[2] + bw[3]), (int)fw[c.alt],
+                                  (int)bw[c.alt]);
+    });
+    timer.lap("fisher_tests", (double)calls.size(), "calls");
 
     // ---- writers (VC:662-688, VC:1040-1066)
     const std::string summary_name = output_dir + "/Summary_Variant_Info.txt";
@@ -877,7 +944,6 @@ int as_variant_calling_main(int argc, char** argv) {
            << std::endl;
     const char* L = "ACGT";
     size_t ci = 0;
-    const uint32_t* cnt = (const uint32_t*)counts.p;
     for (int t = 0; t < T; ++t) {
         const std::string vcf_name = output_dir + "/" + files[t].sample + ".vcf";
         std::ofstream vcf(vcf_name.c_str());
@@ -907,7 +973,7 @@ int as_variant_calling_main(int argc, char** argv) {
             const float AF_fw = FW == 0 ? 0.f : float(k_fw) / float(FW);        // VC:776-795
             const float AF_bw = BW == 0 ? 0.f : float(k_bw) / float(BW);        // VC:797-812
             const long double Q_fw = q_from_p(c.p_fw), Q_bw = q_from_p(c.p_bw);  // VC:895-896
-            const double p = fisher_test(FW, BW, k_fw, k_bw);                   // VC:902
+            const double p = fisher_p[ci];                                      // VC:902
             const char* flag_fisher = (p <= p_value_float) ? "YES" : "NO";      // VC:903-910
             const char* flag_dup = panel.dup[s] ? "YES" : "NO";
             const bool high = !(k_fw < 5 || k_bw < 5);                          // VC:912-919
@@ -953,6 +1019,7 @@ int as_variant_calling_main(int argc, char** argv) {
         }
     }
     output.close();
+    timer.lap("write_outputs", (double)calls.size(), "calls");
     std::cout << "\nAmpliSolveVariantCalling execution was successful. The results can be found at : " << YELLOW << summary_name
               << RESET << std::endl;
     std::cout << "\n" << STARS << std::endl;

@@ -398,7 +398,29 @@ struct Pinned {
 // ---------------------------------------------------------------------------------------------------
 // two-sided Fisher exact test as VC:3797-3814.  Boost.Math 1.61 is not part of the reference tree
 // (.MISSING_LARGE_BLOBS); the pdf is C(r,k) C(N-r,n-k) / C(N,n) through lgamma, like the oracle's stand-in.
-double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+// lgamma(i + 1) for small integers is looked up (same function values, so bit-identical to calling lgamma each time;
+// a germline call at depth 5000 otherwise costs ~45,000 lgamma evaluations).
+struct LgTable {
+    std::vector<double> v;
+    void build(size_t n_max) {
+        if (n_max + 2 <= v.size()) return;
+        const size_t old = v.size();
+        v.resize(n_max + 2);
+        parallel_for(v.size() - old, [&](size_t i) {
+            int sign = 0;
+            v[old + i] = lgamma_r((double)(old + i) + 1.0, &sign);
+        });
+    }
+    double operator()(double x) const {  // lgamma(x + 1) for a non-negative integer-valued x
+        const size_t i = (size_t)x;
+        if (i < v.size()) return v[i];
+        int sign = 0;
+        return lgamma_r(x + 1.0, &sign);
+    }
+};
+LgTable g_lg;
+
+double log_choose(double n, double k) { return g_lg(n) - g_lg(k) - g_lg(n - k); }
 double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {
     return exp(log_choose(r, k) + log_choose((double)N - r, (double)n - k) - log_choose(N, n));
 }
@@ -665,6 +687,7 @@ int as_error_estimation_main(int argc, char** argv) {
     if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
     Pinned counts;
     if (!counts.alloc((size_t)S * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
+    timer.lap("cuda_context_and_pinned_alloc");
     std::cout << "Running function storeGermlineStatistics:" << std::endl;
     std::vector<AseqStats> stats;
     if (!load_all(files, panel, (uint32_t*)counts.p, nullptr, stats)) {
@@ -882,6 +905,7 @@ int as_variant_calling_main(int argc, char** argv) {
     if (!counts.alloc((size_t)T * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
     std::vector<int32_t> row_of((size_t)T * (size_t)P, -1);
     std::vector<AseqStats> stats;
+    timer.lap("cuda_context_and_pinned_alloc");
     std::cout << "\nRunning function callVariants...." << std::endl;
     if (!load_all(files, panel, (uint32_t*)counts.p, row_of.data(), stats)) {
         for (int i = 0; i < T; ++i)
@@ -926,6 +950,15 @@ int as_variant_calling_main(int argc, char** argv) {
     // Fisher strand-bias p of every call (VC:902), in parallel: independent per call, deterministic
     const uint32_t* cnt = (const uint32_t*)counts.p;
     std::vector<double> fisher_p(calls.size());
+    {
+        size_t max_depth = 0;
+        for (const as_call& c : calls) {
+            const uint32_t* fw = cnt + ((size_t)c.sample * 2 * P + c.slot) * 4;
+            const uint32_t* bw = fw + (size_t)P * 4;
+            max_depth = std::max<size_t>(max_depth, (size_t)fw[0] + fw[1] + fw[2] + fw[3] + bw[0] + bw[1] + bw[2] + bw[3]);
+        }
+        g_lg.build(std::min<size_t>(max_depth, (size_t)1 << 26));
+    }
     parallel_for(calls.size(), [&](size_t i) {
         const as_call& c = calls[i];
         const uint32_t* fw = cnt + ((size_t)c.sample * 2 * P + c.slot) * 4;

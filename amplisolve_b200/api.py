@@ -28,7 +28,8 @@ assert CALL_DTYPE.itemsize == 48
 EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
-    "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host", "as_poisson_test_host",
+    "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
+    "as_call_variants_host16", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
@@ -36,6 +37,29 @@ EXPORTS = [
 
 class AmpliSolveError(RuntimeError):
     pass
+
+
+WIDE_DTYPE = np.dtype([("sample", "<i4"), ("slot", "<i4"), ("fw", "<u4", (4,)), ("bw", "<u4", (4,))])
+assert WIDE_DTYPE.itemsize == 40
+WIRE_ABSENT, WIRE_ESCAPE = 0xFFFF, 0xFFFE
+
+
+def to_wire16(counts):
+    """uint32 [S][2][P][4] -> (uint16 wire tensor, wide records) of the _host16 entry points (include/amplisolve_b200.h):
+    absent records are 0xFFFF, records with a count >= 65534 are escaped (0xFFFE) into the side list sorted by slot."""
+    counts = np.asarray(counts, dtype=np.uint32)
+    absent = counts[:, 0, :, 0] == ABSENT                                       # [S][P]
+    big = (~absent) & ((counts[:, 0] >= WIRE_ESCAPE).any(-1) | (counts[:, 1] >= WIRE_ESCAPE).any(-1))
+    out = counts.astype(np.uint16)
+    out[:, 0][absent] = WIRE_ABSENT
+    out[:, 1][absent] = WIRE_ABSENT
+    out[:, 0][big] = WIRE_ESCAPE
+    out[:, 1][big] = WIRE_ESCAPE
+    smp, slot = np.nonzero(big)
+    wide = np.zeros(len(smp), dtype=WIDE_DTYPE)
+    wide["sample"], wide["slot"] = smp, slot
+    wide["fw"], wide["bw"] = counts[smp, 0, slot], counts[smp, 1, slot]
+    return out, np.sort(wide, order=["slot", "sample"])
 
 
 class SynthParams(C.Structure):
@@ -81,9 +105,11 @@ def lib():
     L.as_kernel_launches.restype = i64
     L.as_noise_estimate_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     L.as_noise_estimate_host.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp]
+    L.as_noise_estimate_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp]
     L.as_thresholds_caller_view_dev.argtypes = [vp, vp, vp, i64, vp]
     L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
     L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.as_call_variants_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.as_poisson_test_host.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.as_kf_gammaq_host.argtypes = [vp, vp, vp, i64, vp]
     L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
@@ -180,9 +206,12 @@ class Context:
         _check(lib().as_set_host_tile_slots(self._h, slots))
 
     # ---- host-buffer entry points --------------------------------------------------------------
-    def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None):
-        """counts: uint32 [S][2][P][4] host array, normals in the reference's file order."""
-        counts = _np(counts, np.uint32)
+    def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None, wide_records=None):
+        """counts: uint32 [S][2][P][4] host array, or the uint16 wire format with its wide_records (to_wire16);
+        normals in the reference's file order."""
+        wide = np.asarray(counts).dtype != np.uint16
+        counts = _np(counts, np.uint32 if wide else np.uint16)
+        wr = _np(wide_records if wide_records is not None else np.zeros(0, WIDE_DTYPE), WIDE_DTYPE)
         S, two, P, four = counts.shape
         assert two == 2 and four == 4
         out = {"thr": np.empty((P, 4, 2), np.float32), "germ_val": np.empty((P, 4), np.float32),
@@ -191,15 +220,20 @@ class Context:
         tn = th = None
         if twin_next is not None:
             tn, th = _np(twin_next, np.int32), _np(twin_head, np.int32)
-        _check(lib().as_noise_estimate_host(self._h, _hp(counts), S, P, None if tn is None else _hp(tn),
-                                            None if th is None else _hp(th), np.float32(c_value), int(coverage_cutoff),
-                                            _hp(out["thr"]), _hp(out["germ_val"]), _hp(out["germ_state"]),
-                                            _hp(out["count"]), _hp(out["nrec"])))
+        tail = (None if tn is None else _hp(tn), None if th is None else _hp(th), np.float32(c_value), int(coverage_cutoff),
+                _hp(out["thr"]), _hp(out["germ_val"]), _hp(out["germ_state"]), _hp(out["count"]), _hp(out["nrec"]))
+        if wide:
+            _check(lib().as_noise_estimate_host(self._h, _hp(counts), S, P, *tail))
+        else:
+            _check(lib().as_noise_estimate_host16(self._h, _hp(counts), _hp(wr), len(wr), S, P, *tail))
         return out
 
-    def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None):
-        """counts: uint32 [T][2][P][4] host array.  Returns calls sorted by (sample, slot, alt)."""
-        counts = _np(counts, np.uint32)
+    def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None, wide_records=None):
+        """counts: uint32 [T][2][P][4] host array, or the uint16 wire format with its wide_records (to_wire16).
+        Returns calls sorted by (sample, slot, alt)."""
+        wide = np.asarray(counts).dtype != np.uint16
+        counts = _np(counts, np.uint32 if wide else np.uint16)
+        wr = _np(wide_records if wide_records is not None else np.zeros(0, WIDE_DTYPE), WIDE_DTYPE)
         T, two, P, four = counts.shape
         assert two == 2 and four == 4
         ref = _np(ref, np.uint8)
@@ -209,11 +243,14 @@ class Context:
             cap = max(1024, T * P // 8)
         calls = np.zeros(cap, dtype=CALL_DTYPE)
         n = C.c_int64(0)
-        rc = lib().as_call_variants_host(self._h, _hp(counts), T, P, _hp(ref), _hp(thr_view), int(coverage_cutoff),
-                                         _hp(calls), cap, C.byref(n))
+        tail = (T, P, _hp(ref), _hp(thr_view), int(coverage_cutoff), _hp(calls), cap, C.byref(n))
+        if wide:
+            rc = lib().as_call_variants_host(self._h, _hp(counts), *tail)
+        else:
+            rc = lib().as_call_variants_host16(self._h, _hp(counts), _hp(wr), len(wr), *tail)
         _check(rc, allow_overflow=True)
         if rc == -5:
-            return self.call_variants(counts, ref, thr_view, coverage_cutoff, cap=int(n.value))
+            return self.call_variants(counts, ref, thr_view, coverage_cutoff, cap=int(n.value), wide_records=wide_records)
         return calls[:n.value]
 
     def mutation_rules_poisson_quality_score(self, k, rd, err):

@@ -52,7 +52,7 @@ struct as_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
-    DevBuf tile[2], out[2], aux[2], misc, calls;  // _host pipelines
+    DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls;  // _host pipelines
 };
 
 extern "C" {
@@ -105,7 +105,7 @@ void as_destroy(as_ctx* c) {
     cudaDeviceSynchronize();
     c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release();
     for (int i = 0; i < 2; ++i) {
-        c->tile[i].release(); c->out[i].release(); c->aux[i].release();
+        c->tile[i].release(); c->tile16[i].release(); c->wide[i].release(); c->out[i].release(); c->aux[i].release();
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
@@ -202,11 +202,74 @@ static int64_t tile_slots(const as_ctx* c, int32_t n_samples, int64_t P) {
     return std::min(t, std::max<int64_t>(P, 1));
 }
 
-// upload slots [p0, p0+n) of a host tensor [n_samples][2][P][4] into a packed device tile [n_samples][2][n][4]
-static cudaError_t upload_tile(void* d_tile, const uint32_t* counts, int32_t n_samples, int64_t P, int64_t p0, int64_t n,
+// A host count tensor: uint32 (elem = 4) or the uint16 wire format (elem = 2) with its side list of wide records.
+struct HostSrc {
+    const void* counts;
+    int elem;
+    const as_wide_record* wide;  // sorted by slot
+    int64_t n_wide;
+};
+
+// upload slots [p0, p0+n) of a host tensor [n_samples][2][P][4] into a packed device tile [n_samples][2][n][4] of uint32.
+// elem = 4: the host tensor is uint32.  elem = 2: it is uint16 (lossless wire format for counts < 65535, absent =
+// 0xFFFF); the half-size tile goes through a staging buffer and is widened on the device.
+static cudaError_t upload_tile(as_ctx* c, int bsel, const HostSrc& src, int32_t n_samples, int64_t P, int64_t p0, int64_t n,
                                cudaStream_t st) {
-    return cudaMemcpy2DAsync(d_tile, (size_t)n * 16, counts + p0 * 4, (size_t)P * 16, (size_t)n * 16,
-                             (size_t)n_samples * 2, cudaMemcpyHostToDevice, st);
+    const size_t word = (size_t)src.elem * 4;  // bytes per (sample, strand, slot)
+    void* dst = src.elem == 4 ? c->tile[bsel].p : c->tile16[bsel].p;
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)n * word, (const char*)src.counts + (size_t)p0 * word, (size_t)P * word,
+                                      (size_t)n * word, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess || src.elem == 4) return e;
+    e = as_launch_widen16((const uint16_t*)dst, (uint32_t*)c->tile[bsel].p, (int64_t)n_samples * 2 * n, st);
+    c->launches += 1;
+    if (e != cudaSuccess || src.n_wide == 0) return e;
+    // records with a count beyond 16 bits travel in the side list: patch the ones of this tile into the widened tile
+    const as_wide_record* lo = std::lower_bound(src.wide, src.wide + src.n_wide, p0,
+                                                [](const as_wide_record& r, int64_t v) { return (int64_t)r.slot < v; });
+    const as_wide_record* hi = std::lower_bound(lo, src.wide + src.n_wide, p0 + n,
+                                                [](const as_wide_record& r, int64_t v) { return (int64_t)r.slot < v; });
+    const int64_t m = hi - lo;
+    if (m == 0) return e;
+    e = c->wide[bsel].need((size_t)m * sizeof(as_wide_record));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(c->wide[bsel].p, lo, (size_t)m * sizeof(as_wide_record), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    c->launches += 1;
+    return as_launch_patch_wide((const as_wide_record*)c->wide[bsel].p, m, (uint32_t*)c->tile[bsel].p, n, p0, n_samples, st);
+}
+
+// the eight counts of (sample, slot) out of a host tensor in either format (used for the few gathered twin members)
+static void host_record(const HostSrc& src, int64_t P, int64_t sample, int64_t slot, uint32_t* fw, uint32_t* bw) {
+    const int64_t wf = (sample * 2) * P + slot, wb = wf + P;
+    if (src.elem == 4) {
+        memcpy(fw, (const uint32_t*)src.counts + wf * 4, 16);
+        memcpy(bw, (const uint32_t*)src.counts + wb * 4, 16);
+        return;
+    }
+    const uint16_t* f = (const uint16_t*)src.counts + wf * 4;
+    const uint16_t* b = (const uint16_t*)src.counts + wb * 4;
+    if (f[0] == 0xFFFFu) {
+        for (int i = 0; i < 4; ++i) fw[i] = bw[i] = AS_ABSENT;
+    } else if (f[0] == 0xFFFEu) {  // escaped: the real counts are in the side list
+        const as_wide_record* r = std::lower_bound(src.wide, src.wide + src.n_wide, slot,
+                                                   [](const as_wide_record& x, int64_t v) { return (int64_t)x.slot < v; });
+        for (; r < src.wide + src.n_wide && r->slot == slot; ++r)
+            if (r->sample == sample) { memcpy(fw, r->fw, 16); memcpy(bw, r->bw, 16); return; }
+        for (int i = 0; i < 4; ++i) fw[i] = bw[i] = AS_ABSENT;  // inconsistent input: treated as absent
+    } else {
+        for (int i = 0; i < 4; ++i) { fw[i] = f[i]; bw[i] = b[i]; }
+    }
+}
+
+static int check_wide(const HostSrc& src, int32_t n_samples, int64_t P) {
+    if (src.elem != 2) return AS_OK;
+    if (src.n_wide < 0 || (src.n_wide > 0 && !src.wide)) return fail(AS_EINVAL, "bad wide-record list");
+    for (int64_t i = 0; i < src.n_wide; ++i) {
+        const as_wide_record& r = src.wide[i];
+        if (r.slot < 0 || r.slot >= P || r.sample < 0 || r.sample >= n_samples) return fail(AS_EINVAL, "wide record %lld out of range", (long long)i);
+        if (i > 0 && src.wide[i - 1].slot > r.slot) return fail(AS_EINVAL, "wide records must be sorted by slot");
+    }
+    return AS_OK;
 }
 
 struct NoiseOutLayout {  // one device block per tile: thr | germ_val | count | nrec | germ_state
@@ -221,11 +284,13 @@ struct NoiseOutLayout {  // one device block per tile: thr | germ_val | count | 
     }
 };
 
-int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
-                           const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
-                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec) {
-    int rc = check_common(c, counts, S, P, 0, P, cut);
+static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, int64_t P, const int32_t* twin_next,
+                                    const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
+                                    uint8_t* germ_state, uint32_t* count, uint32_t* nrec) {
+    const int elem = src.elem;
+    int rc = check_common(c, src.counts, S, P, 0, P, cut);
     if (rc) return rc;
+    if ((rc = check_wide(src, S, P)) != AS_OK) return rc;
     if (!thr || !germ_val || !germ_state || !count || !nrec) return fail(AS_EINVAL, "output pointer is NULL");
     if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
     if (P == 0) return AS_OK;
@@ -234,6 +299,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
     const NoiseOutLayout lay(TP);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)std::max(1, S)));
+        if (elem == 2) CU(c->tile16[i].need((size_t)TP * 16 * (size_t)std::max(1, S)));
         CU(c->out[i].need(lay.total));
         if (twin_next) CU(c->aux[i].need((size_t)TP * 8));
     }
@@ -254,7 +320,7 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
         const int bsel = (int)(t & 1);
         const int64_t p0 = t * TP, n = std::min(TP, P - p0);
         if (t >= 2) CUT(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));  // buffer free again
-        CUT(upload_tile(c->tile[bsel].p, counts, S, P, p0, n, c->copy_stream));
+        CUT(upload_tile(c, bsel, src, S, P, p0, n, c->copy_stream));
         int32_t *d_tn = nullptr, *d_th = nullptr;
         if (twin_next) {
             if (t >= 2) CUT(cudaEventSynchronize(c->ev_up[bsel]));  // the staging block of this buffer has been uploaded
@@ -337,11 +403,9 @@ int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t
     if (M == 0) return AS_OK;
     uint32_t* h_gather = nullptr;
     CU(cudaHostAlloc((void**)&h_gather, (size_t)M * 32 * (size_t)std::max(1, S), cudaHostAllocDefault));
-    for (int64_t row = 0; row < (int64_t)S * 2; ++row) {
-        const uint32_t* src = counts + row * P * 4;
-        uint32_t* dst = h_gather + row * M * 4;
-        for (int64_t m = 0; m < M; ++m) memcpy(dst + m * 4, src + (int64_t)members[m] * 4, 16);
-    }
+    for (int64_t smp = 0; smp < S; ++smp)
+        for (int64_t m = 0; m < M; ++m)
+            host_record(src, P, smp, members[m], h_gather + ((smp * 2) * M + m) * 4, h_gather + ((smp * 2 + 1) * M + m) * 4);
     const NoiseOutLayout ml(M);
     DevBuf d_cnt, d_out, d_links;
     cudaError_t e1 = d_cnt.need((size_t)M * 32 * (size_t)std::max(1, S));
@@ -397,10 +461,12 @@ int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t
     return AS_OK;
 }
 
-int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
-                          const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
-    int rc = check_common(c, counts, T, P, 0, P, cut);
+static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int64_t P, const uint8_t* ref,
+                                   const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
+    const int elem = src.elem;
+    int rc = check_common(c, src.counts, T, P, 0, P, cut);
     if (rc) return rc;
+    if ((rc = check_wide(src, T, P)) != AS_OK) return rc;
     if (!ref || !thr_view || !n_calls || (!calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
     *n_calls = 0;
     if (P == 0 || T == 0) return AS_OK;
@@ -408,6 +474,7 @@ int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t 
     const int64_t TP = tile_slots(c, T, P);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)T));
+        if (elem == 2) CU(c->tile16[i].need((size_t)TP * 16 * (size_t)T));
         CU(c->aux[i].need((size_t)TP * 36));  // thr_view (32 B/slot) + ref (1 B/slot, padded)
     }
     CU(c->calls.need(sizeof(as_call) * (size_t)std::max<int64_t>(cap, 1)));
@@ -424,7 +491,7 @@ int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t 
         const int64_t p0 = t * TP, n = std::min(TP, P - p0);
 #define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
         if (t >= 2) CUB(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));
-        CUB(upload_tile(c->tile[bsel].p, counts, T, P, p0, n, c->copy_stream));
+        CUB(upload_tile(c, bsel, src, T, P, p0, n, c->copy_stream));
         float* d_tv = (float*)c->aux[bsel].p;
         uint8_t* d_rf = (uint8_t*)c->aux[bsel].p + (size_t)TP * 32;
         CUB(cudaMemcpyAsync(d_tv, thr_view + p0 * 8, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
@@ -469,6 +536,30 @@ int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t 
     }
     cudaFreeHost(h_n);
     return ret;
+}
+
+int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
+                           const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
+                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec) {
+    const HostSrc src{counts, 4, nullptr, 0};
+    return noise_estimate_host_impl(c, src, S, P, twin_next, twin_head, C, cut, thr, germ_val, germ_state, count, nrec);
+}
+int as_noise_estimate_host16(as_ctx* c, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t S,
+                             int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut, float* thr,
+                             float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec) {
+    const HostSrc src{counts, 2, wide, n_wide};
+    return noise_estimate_host_impl(c, src, S, P, twin_next, twin_head, C, cut, thr, germ_val, germ_state, count, nrec);
+}
+int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
+                          const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
+    const HostSrc src{counts, 4, nullptr, 0};
+    return call_variants_host_impl(c, src, T, P, ref, thr_view, cut, calls, cap, n_calls);
+}
+int as_call_variants_host16(as_ctx* c, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t T,
+                            int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls, int64_t cap,
+                            int64_t* n_calls) {
+    const HostSrc src{counts, 2, wide, n_wide};
+    return call_variants_host_impl(c, src, T, P, ref, thr_view, cut, calls, cap, n_calls);
 }
 
 // ---- element-wise evaluators -----------------------------------------------------------------------

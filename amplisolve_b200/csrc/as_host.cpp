@@ -229,7 +229,11 @@ bool list_count_files(const std::string& dir, std::vector<CountFile>& files, std
 // ---------------------------------------------------------------------------------------------------
 // .PILEUP.ASEQ -> dense counts of one sample (EE:1114-1176, VC:723-770)
 // ---------------------------------------------------------------------------------------------------
-struct AseqStats { int64_t rows = 0, outside = 0, extra = 0, bad_rd = 0; bool ok = true; };
+struct AseqStats {
+    int64_t rows = 0, outside = 0, extra = 0, bad_rd = 0;
+    bool ok = true;
+    std::vector<as_wide_record> wide;  // records of this file with a count beyond the 16-bit wire format
+};
 
 inline bool parse_int(const char*& p, const char* e, long long& v) {
     p = skip_ws(p, e);
@@ -242,8 +246,12 @@ inline bool parse_int(const char*& p, const char* e, long long& v) {
     return true;
 }
 
-// counts: this sample's plane pair, [2][P][4]; row_of (optional) [P] file row index of each filled slot
-AseqStats load_aseq(const std::string& path, const Panel& panel, uint32_t* counts, int32_t* row_of) {
+// counts: this sample's plane pair, [2][P][4]; row_of (optional) [P] file row index of each filled slot.
+// E = uint32_t (the canonical layout) or uint16_t (wire format of include/amplisolve_b200.h: a record with a count
+// of 65534 or more is escaped and goes to stats.wide).
+template <typename E>
+AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int32_t* row_of, int32_t sample) {
+    const E absent = (E)~(E)0;
     AseqStats st;
     std::string text;
     if (!read_file(path, text)) { st.ok = false; return st; }
@@ -279,7 +287,7 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, uint32_t* count
                     const int k = seen[slot]++;
                     for (int j = 0; j < k && slot >= 0; ++j) slot = panel.twin_next[slot];
                     if (slot < 0) ++st.extra;
-                } else if (slot >= 0 && counts[(int64_t)slot * 4] != AS_ABSENT) {
+                } else if (slot >= 0 && counts[(int64_t)slot * 4] != absent) {
                     slot = -1;  // a second row for a position that owns one slot
                     ++st.extra;
                 } else if (slot < 0) {
@@ -288,11 +296,25 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, uint32_t* count
                 if (slot >= 0) {
                     // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
                     if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
-                    uint32_t* fw = counts + (int64_t)slot * 4;
-                    uint32_t* bw = counts + ((int64_t)P + slot) * 4;
+                    E* fw = counts + (int64_t)slot * 4;
+                    E* bw = counts + ((int64_t)P + slot) * 4;
+                    bool escape = false;
                     for (int b = 0; b < 4; ++b) {
-                        fw[b] = (uint32_t)(v[b] - v[5 + b]);
-                        bw[b] = (uint32_t)v[5 + b];
+                        const long long f = v[b] - v[5 + b], r2 = v[5 + b];
+                        if (sizeof(E) == 2 && (f >= AS_WIRE_ESCAPE || r2 >= AS_WIRE_ESCAPE || f < 0 || r2 < 0)) escape = true;
+                        fw[b] = (E)f;
+                        bw[b] = (E)r2;
+                    }
+                    if (escape) {
+                        as_wide_record w;
+                        w.sample = sample;
+                        w.slot = slot;
+                        for (int b = 0; b < 4; ++b) {
+                            w.fw[b] = (uint32_t)(v[b] - v[5 + b]);
+                            w.bw[b] = (uint32_t)v[5 + b];
+                            fw[b] = bw[b] = (E)AS_WIRE_ESCAPE;
+                        }
+                        st.wide.push_back(w);
                     }
                     if (row_of) row_of[slot] = (int32_t)row;
                 }
@@ -304,7 +326,8 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, uint32_t* count
 }
 
 // all samples, in the given order, into one pinned tensor [n][2][P][4]
-bool load_all(const std::vector<CountFile>& files, const Panel& panel, uint32_t* counts, int32_t* row_of,
+template <typename E>
+bool load_all(const std::vector<CountFile>& files, const Panel& panel, E* counts, int32_t* row_of,
               std::vector<AseqStats>& stats) {
     const int n = (int)files.size();
     const int64_t P = panel.size();
@@ -312,9 +335,9 @@ bool load_all(const std::vector<CountFile>& files, const Panel& panel, uint32_t*
     std::atomic<int> next(0);
     auto work = [&]() {
         for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
-            uint32_t* plane = counts + (int64_t)i * 2 * P * 4;
-            memset(plane, 0xFF, (size_t)P * 32);
-            stats[i] = load_aseq(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr);
+            E* plane = counts + (int64_t)i * 2 * P * 4;
+            memset(plane, 0xFF, (size_t)P * 8 * sizeof(E));
+            stats[i] = load_aseq<E>(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr, (int32_t)i);
         }
     };
     const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n)));
@@ -341,6 +364,49 @@ void parallel_for(size_t n, F body) {
     for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
     work();
     for (auto& t : th) t.join();
+}
+
+// The count tensor of a run, in the 16-bit wire format (half the pinned memory and PCIe traffic of uint32): the few
+// records with a count of 65534 or more are escaped into `wide`, sorted by (slot, sample).
+struct HostCounts {
+    uint16_t* p = nullptr;
+    std::vector<as_wide_record> wide;
+    ~HostCounts() { if (p) as_host_free(p); }
+    // the eight counts of (sample, slot); P = slots of the panel
+    void record(int64_t sample, int64_t slot, int64_t P, uint32_t (&fw)[4], uint32_t (&bw)[4]) const {
+        const uint16_t* f = p + ((sample * 2) * P + slot) * 4;
+        const uint16_t* b = f + P * 4;
+        if (f[0] == AS_WIRE_ESCAPE) {
+            as_wide_record key;
+            key.slot = (int32_t)slot;
+            key.sample = (int32_t)sample;
+            auto it = std::lower_bound(wide.begin(), wide.end(), key, [](const as_wide_record& x, const as_wide_record& y) {
+                return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
+            });
+            if (it != wide.end() && it->slot == slot && it->sample == sample) {
+                for (int i = 0; i < 4; ++i) { fw[i] = it->fw[i]; bw[i] = it->bw[i]; }
+                return;
+            }
+        }
+        for (int i = 0; i < 4; ++i) { fw[i] = f[i]; bw[i] = b[i]; }
+    }
+};
+// returns 0 ok, 1 pinned allocation failed, 2 a file could not be opened
+int load_counts(const std::vector<CountFile>& files, const Panel& panel, HostCounts& hc, int32_t* row_of,
+                std::vector<AseqStats>& stats) {
+    const size_t words = (size_t)files.size() * 2 * (size_t)panel.size() * 4;
+    void* mem = nullptr;
+    if (as_host_alloc(&mem, std::max<size_t>(16, words * 2)) != AS_OK) return 1;
+    hc.p = (uint16_t*)mem;
+    if (!load_all<uint16_t>(files, panel, hc.p, row_of, stats)) return 2;
+    for (AseqStats& s : stats) {
+        hc.wide.insert(hc.wide.end(), s.wide.begin(), s.wide.end());
+        s.wide.clear();
+    }
+    std::sort(hc.wide.begin(), hc.wide.end(), [](const as_wide_record& x, const as_wide_record& y) {
+        return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
+    });
+    return 0;
 }
 
 bool make_dir(const std::string& path) {  // mkdir -p (EE:3079)
@@ -685,12 +751,13 @@ int as_error_estimation_main(int argc, char** argv) {
     const int S = (int)files.size();
     as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
     if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
-    Pinned counts;
-    if (!counts.alloc((size_t)S * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
-    timer.lap("cuda_context_and_pinned_alloc");
+    timer.lap("cuda_context");
     std::cout << "Running function storeGermlineStatistics:" << std::endl;
+    HostCounts counts;
     std::vector<AseqStats> stats;
-    if (!load_all(files, panel, (uint32_t*)counts.p, nullptr, stats)) {
+    const int lrc = load_counts(files, panel, counts, nullptr, stats);
+    if (lrc == 1) return report_gpu_error("pinned host allocation");
+    if (lrc == 2) {
         for (int i = 0; i < S; ++i)
             if (!stats[i].ok) printf("Error: Cannot open %s\n", files[i].path.c_str());
         return 0;
@@ -706,9 +773,11 @@ int as_error_estimation_main(int argc, char** argv) {
     std::vector<float> thr((size_t)P * 8), germ_val((size_t)P * 4);
     std::vector<uint8_t> germ_state((size_t)P * 4);
     std::vector<uint32_t> count((size_t)P * 4), nrec((size_t)P);
-    const int rc = as_noise_estimate_host(ctx, (const uint32_t*)counts.p, S, P, panel.has_twins ? panel.twin_next.data() : nullptr,
-                                          panel.has_twins ? panel.twin_head.data() : nullptr, C_value_float, cut, thr.data(),
-                                          germ_val.data(), germ_state.data(), count.data(), nrec.data());
+    const int32_t* tn = panel.has_twins ? panel.twin_next.data() : nullptr;
+    const int32_t* th = panel.has_twins ? panel.twin_head.data() : nullptr;
+    const int rc = as_noise_estimate_host16(ctx, counts.p, counts.wide.data(), (int64_t)counts.wide.size(), S, P, tn, th,
+                                            C_value_float, cut, thr.data(), germ_val.data(), germ_state.data(), count.data(),
+                                            nrec.data());
     as_destroy(ctx);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");
@@ -901,13 +970,14 @@ int as_variant_calling_main(int argc, char** argv) {
     const int T = (int)files.size();
     as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
     if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
-    Pinned counts;
-    if (!counts.alloc((size_t)T * (size_t)P * 32)) return report_gpu_error("pinned host allocation");
     std::vector<int32_t> row_of((size_t)T * (size_t)P, -1);
     std::vector<AseqStats> stats;
-    timer.lap("cuda_context_and_pinned_alloc");
+    timer.lap("cuda_context");
     std::cout << "\nRunning function callVariants...." << std::endl;
-    if (!load_all(files, panel, (uint32_t*)counts.p, row_of.data(), stats)) {
+    HostCounts counts;
+    const int lrc = load_counts(files, panel, counts, row_of.data(), stats);
+    if (lrc == 1) return report_gpu_error("pinned host allocation");
+    if (lrc == 2) {
         for (int i = 0; i < T; ++i)
             if (!stats[i].ok) printf("\tError from callVariants:  Cannot open %s\n", files[i].path.c_str());
         return 0;
@@ -929,8 +999,8 @@ int as_variant_calling_main(int argc, char** argv) {
         int rc;
         for (;;) {
             calls.resize((size_t)cap);
-            rc = as_call_variants_host(ctx, (const uint32_t*)counts.p, T, P, ref_code.data(), thr_view.data(), cut, calls.data(), cap,
-                                       &n_calls);
+            rc = as_call_variants_host16(ctx, counts.p, counts.wide.data(), (int64_t)counts.wide.size(), T, P, ref_code.data(),
+                                         thr_view.data(), cut, calls.data(), cap, &n_calls);
             if (rc != AS_EOVERFLOW) break;
             cap = n_calls;
         }
@@ -948,21 +1018,22 @@ int as_variant_calling_main(int argc, char** argv) {
     timer.lap("caller_gpu", 6.0 * (double)T * (double)P, "tests");
 
     // Fisher strand-bias p of every call (VC:902), in parallel: independent per call, deterministic
-    const uint32_t* cnt = (const uint32_t*)counts.p;
+    // the eight strand counts of a call's record
+    auto record = [&](const as_call& c, uint32_t (&fw)[4], uint32_t (&bw)[4]) { counts.record(c.sample, c.slot, P, fw, bw); };
     std::vector<double> fisher_p(calls.size());
     {
         size_t max_depth = 0;
         for (const as_call& c : calls) {
-            const uint32_t* fw = cnt + ((size_t)c.sample * 2 * P + c.slot) * 4;
-            const uint32_t* bw = fw + (size_t)P * 4;
+            uint32_t fw[4], bw[4];
+            record(c, fw, bw);
             max_depth = std::max<size_t>(max_depth, (size_t)fw[0] + fw[1] + fw[2] + fw[3] + bw[0] + bw[1] + bw[2] + bw[3]);
         }
         g_lg.build(std::min<size_t>(max_depth, (size_t)1 << 26));
     }
     parallel_for(calls.size(), [&](size_t i) {
         const as_call& c = calls[i];
-        const uint32_t* fw = cnt + ((size_t)c.sample * 2 * P + c.slot) * 4;
-        const uint32_t* bw = cnt + ((size_t)c.sample * 2 * P + P + c.slot) * 4;
+        uint32_t fw[4], bw[4];
+        record(c, fw, bw);
         fisher_p[i] = fisher_test((int)(fw[0] + fw[1] + fw[2] + fw[3]), (int)(bw[0] + bw[1] + bw[2] + bw[3]), (int)fw[c.alt],
                                   (int)bw[c.alt]);
     });
@@ -996,8 +1067,8 @@ int as_variant_calling_main(int argc, char** argv) {
         for (; ci < calls.size() && calls[ci].sample == t; ++ci) {
             const as_call& c = calls[ci];
             const int64_t s = c.slot;
-            const uint32_t* fw = cnt + ((size_t)t * 2 * P + s) * 4;
-            const uint32_t* bw = cnt + ((size_t)t * 2 * P + P + s) * 4;
+            uint32_t fw[4], bw[4];
+            record(c, fw, bw);
             const int FW = (int)(fw[0] + fw[1] + fw[2] + fw[3]), BW = (int)(bw[0] + bw[1] + bw[2] + bw[3]);
             const int RD = FW + BW;
             const int a = c.alt;

@@ -364,6 +364,34 @@ noise_twin_kernel(const uint4* __restrict__ counts, int S, int64_t P, const int3
 }
 
 // ------------------------------------------------------------------------------------------------
+// uint16 wire format -> uint32 count words (the _host16 entry points): one thread per (sample, strand, slot) word
+// ------------------------------------------------------------------------------------------------
+__global__ void widen16_kernel(const uint2* __restrict__ in, uint4* __restrict__ out, int64_t n_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint2 v = in[i];
+    uint4 o;
+    if (v.x == 0xFFFFFFFFu && v.y == 0xFFFFFFFFu) {
+        o = make_uint4(AS_ABSENT, AS_ABSENT, AS_ABSENT, AS_ABSENT);
+    } else {
+        o = make_uint4(v.x & 0xFFFFu, v.x >> 16, v.y & 0xFFFFu, v.y >> 16);
+    }
+    out[i] = o;
+}
+
+// records whose counts do not fit 16 bits travel as as_wide_record; overwrite their (escaped) words in the tile
+__global__ void patch_wide_kernel(const as_wide_record* __restrict__ wide, int64_t m, uint4* __restrict__ tile, int64_t n,
+                                  int64_t p0, int n_samples) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const as_wide_record r = wide[i];
+    const int64_t slot = (int64_t)r.slot - p0;
+    if (slot < 0 || slot >= n || r.sample < 0 || r.sample >= n_samples) return;
+    tile[((int64_t)r.sample * 2 + 0) * n + slot] = make_uint4(r.fw[0], r.fw[1], r.fw[2], r.fw[3]);
+    tile[((int64_t)r.sample * 2 + 1) * n + slot] = make_uint4(r.bw[0], r.bw[1], r.bw[2], r.bw[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // thresholds as the caller sees them (EE:1787 "%f" text -> VC:889-890 std::stof)
 // ------------------------------------------------------------------------------------------------
 __global__ void thr_view_kernel(const float* __restrict__ thr, float* __restrict__ view, int64_t n) {
@@ -893,6 +921,20 @@ cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int6
     const unsigned grid = (unsigned)std::min<int64_t>(148 * 2, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
     noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_groups, d_counters, C, cut, d_thr, d_germ_val,
                                             d_germ_state, d_count, d_nrec);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st) {
+    if (n_words <= 0) return cudaSuccess;
+    widen16_kernel<<<cdiv64(n_words, 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(d_in), reinterpret_cast<uint4*>(d_out),
+                                                        n_words);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32_t* d_tile, int64_t n, int64_t p0,
+                                 int n_samples, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+    patch_wide_kernel<<<cdiv64(m, 128), 128, 0, st>>>(d_wide, m, reinterpret_cast<uint4*>(d_tile), n, p0, n_samples);
     return cudaGetLastError();
 }
 

@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-wide", action="store_true", help="keep the e2e host tensors in uint32 even when uint16 is lossless")
     ap.add_argument("--call-kernel", type=int, default=3, help="include/amplisolve_b200.h as_set_call_kernel")
     ap.add_argument("--noise-kernel", type=int, default=1, help="include/amplisolve_b200.h as_set_noise_kernel")
     return ap.parse_args()
@@ -189,42 +190,65 @@ def cpu_reference(steps, warmup, sample_slots=1000, sample_normals=100, sample_t
 # clocks
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 20 ms from before the warm-up; the report uses the samples whose timestamps fall inside
+    the timed region (mark_start / mark_end), or the nearest ones when the region is shorter than the sampling period."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t0, self.t1 = index, [], None, None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
+            deadline = time.time() + 3.0
+            while not self.rows and time.time() < deadline:   # nvidia-smi takes a few hundred ms to produce its first line
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            f = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = time.time()
+            self.rows.append((ts, time.time(), f[1:]))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
+        time.sleep(0.06)
         self.proc.terminate()
         self.th.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        inside = [r for r in self.rows if self.t0 is not None and self.t0 <= r[1] <= self.t1 + 0.03]
+        if len(inside) < 2 and self.rows:   # region shorter than the sampling period: take the samples closest to it
+            mid = 0.5 * ((self.t0 or 0) + (self.t1 or 0))
+            inside = sorted(self.rows, key=lambda r: abs(r[1] - mid))[:3]
+        rows = [r[2] for r in inside]
+        sm = [float(r[0]) for r in rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 8:
                 for nm, v in zip(names, r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -311,21 +335,23 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        step()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
     launches0 = ctx.kernel_launches
     marks = [[ev() for _ in range(4)] for _ in range(args.steps)]
     e0, e1 = ev(), ev()
     barrier()
+    sampler.mark_start()
     e0.record()
     for i in range(args.steps):
         step(marks[i])
     e1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = e0.elapsed_time(e1)
     launches = ctx.kernel_launches - launches0 + args.steps  # + the n_calls.zero_() fill kernel of each step
@@ -417,7 +443,6 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     from amplisolve_b200 import CALL_DTYPE, lib
     P, S, T = args.slots, args.normals, args.tumours
     # keep the pinned footprint of all ranks below a third of the free host memory
-    need = (S + T) * P * 32
     avail = psutil.virtual_memory().available / max(1, world) / 3
     Pe = P
     while (S + T) * Pe * 32 > avail and Pe > 50_000:
@@ -431,15 +456,40 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
             raise RuntimeError(L.as_last_error().decode())
         return p
 
-    bn, bt = S * 2 * Pe * 16, T * 2 * Pe * 16
+    # host tensors: the uint16 wire format of the _host16 entry points (records with a count >= 65534 escaped into a side
+    # list of wide records: lossless), or uint32 with --e2e-wide
+    narrow = not args.e2e_wide
+    esz = 2 if narrow else 4
+    bn, bt = S * 2 * Pe * 4 * esz, T * 2 * Pe * 4 * esz
     hp_n, hp_t = pinned(bn), pinned(bt)
-    h_norm = np.ctypeslib.as_array(C.cast(hp_n, C.POINTER(C.c_uint32)), shape=(S, 2, Pe, 4))
-    h_tum = np.ctypeslib.as_array(C.cast(hp_t, C.POINTER(C.c_uint32)), shape=(T, 2, Pe, 4))
-    # untimed: bring the synthetic inputs to the host (slot prefix of the device tensors)
-    t_n = torch.from_numpy(h_norm.view(np.int32))
-    t_t = torch.from_numpy(h_tum.view(np.int32))
-    t_n.copy_(d_normals[:, :, :Pe, :])
-    t_t.copy_(d_tumours[:, :, :Pe, :])
+    ctype, ndt = (C.c_uint16, np.int16) if narrow else (C.c_uint32, np.int32)
+    h_norm = np.ctypeslib.as_array(C.cast(hp_n, C.POINTER(ctype)), shape=(S, 2, Pe, 4))
+    h_tum = np.ctypeslib.as_array(C.cast(hp_t, C.POINTER(ctype)), shape=(T, 2, Pe, 4))
+    from amplisolve_b200.api import WIDE_DTYPE
+
+    def to_host(dst_np, src):
+        """untimed: bring a slot prefix of a device tensor to the pinned host tensor (and its wide records)"""
+        dst = torch.from_numpy(dst_np.view(ndt))
+        wides = []
+        for s0 in range(0, src.shape[0], 50):      # in sample blocks: bounded temporaries on the device
+            blk = src[s0:s0 + 50, :, :Pe, :]
+            if not narrow:
+                dst[s0:s0 + 50].copy_(blk)
+                continue
+            present = blk[:, 0, :, 0] >= 0                                   # absent words are -1 as int32
+            big = present & ((blk[:, 0] >= 0xFFFE).any(-1) | (blk[:, 1] >= 0xFFFE).any(-1))
+            smp, slot = big.nonzero(as_tuple=True)
+            w = np.zeros(len(smp), dtype=WIDE_DTYPE)
+            w["sample"], w["slot"] = (smp + s0).cpu().numpy(), slot.cpu().numpy()
+            w["fw"], w["bw"] = blk[smp, 0, slot].cpu().numpy(), blk[smp, 1, slot].cpu().numpy()
+            wides.append(w)
+            n16 = blk.to(torch.int16)
+            n16[smp, :, slot, :] = -2                                        # 0xFFFE: escaped
+            dst[s0:s0 + 50].copy_(n16)
+        return np.sort(np.concatenate(wides), order=["slot", "sample"]) if wides else np.zeros(0, WIDE_DTYPE)
+
+    w_norm = to_host(h_norm, d_normals)
+    w_tum = to_host(h_tum, d_tumours)
     h_ref = d_ref[:Pe].cpu().numpy()
     h_tn = h_th = None
     if d_twin_next is not None:
@@ -451,9 +501,9 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     stats = {}
 
     def one():
-        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th)
+        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th, wide_records=w_norm)
         view = ctx.thresholds_caller_view_dev(torch.from_numpy(noise["thr"]).cuda()).cpu().numpy()
-        calls = ctx.call_variants(h_tum, h_ref, view, cut, cap=cap)
+        calls = ctx.call_variants(h_tum, h_ref, view, cut, cap=cap, wide_records=w_tum)
         stats["calls"] = len(calls)
 
     one()  # warm-up (allocates the tile buffers)
@@ -471,8 +521,10 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     L.as_host_free(hp_n)
     L.as_host_free(hp_t)
     return {"value": 6.0 * T * Pe * world / dt, "unit": "Poisson tests/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + Pe * 32), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
-            "slots_per_gpu": Pe, "api": "as_noise_estimate_host + as_thresholds_caller_view_dev + as_call_variants_host, pinned host buffers",
+            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + Pe * 32 + 40 * (len(w_norm) + len(w_tum))), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
+            "slots_per_gpu": Pe, "host_dtype": (f"uint16 wire format + {len(w_norm) + len(w_tum)} escaped wide records (lossless)" if narrow else "uint32"),
+            "api": ("as_noise_estimate_host16 + as_thresholds_caller_view_dev + as_call_variants_host16" if narrow else
+                    "as_noise_estimate_host + as_thresholds_caller_view_dev + as_call_variants_host") + ", pinned host buffers",
             "timer": "host wall clock around the blocking C-ABI calls, max over ranks"}
 
 

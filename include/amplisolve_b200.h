@@ -111,6 +111,23 @@ int as_noise_estimate_host(as_ctx* ctx, const uint32_t* counts, int32_t S, int64
                            const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
                            uint8_t* germ_state, uint32_t* count, uint32_t* nrec);
 
+/* The 16-bit wire format of the _host16 entry points: uint16 counts[sample][strand][slot][base], half the host footprint
+ * and PCIe traffic of the uint32 layout.  A record whose eight counts are all < 65534 is stored as is; an absent record
+ * is 0xFFFF in all eight words; a record with a larger count is ESCAPED -- 0xFFFE in all eight words -- and travels in
+ * a side list of as_wide_record, sorted by slot.  Lossless for every input; the tile is widened to the uint32 layout on
+ * the device, the kernels and results are the same. */
+typedef struct {
+    int32_t sample;
+    int32_t slot;
+    uint32_t fw[4];
+    uint32_t bw[4];
+} as_wide_record; /* 40 bytes */
+#define AS_WIRE_ABSENT 0xFFFFu
+#define AS_WIRE_ESCAPE 0xFFFEu
+int as_noise_estimate_host16(as_ctx* ctx, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t S,
+                             int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut, float* thr,
+                             float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec);
+
 /* The noise table crosses to the caller as "%f" text (EE:1787 -> std::stof at VC:889-890) with
  * "-1_-1" replaced by "0.01_0.01" (EE:2680-2684).  This applies exactly that mapping to thr
  * [n] floats in place of the text round trip: NaN -> 0.01f, v -> strtof(sprintf("%f", v)). */
@@ -130,6 +147,10 @@ int as_call_variants_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t T, int64
                          as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, void* stream);
 int as_call_variants_host(as_ctx* ctx, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
                           const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls);
+
+int as_call_variants_host16(as_ctx* ctx, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t T,
+                            int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls, int64_t cap,
+                            int64_t* n_calls);
 
 /* Element-wise Poisson test on the device: p[i] = the double p-value of VC:3858-3866 and
  * q[i] = the Q score of VC:3868-3882 for (k[i], rd[i], err[i]).  Host pointers.  Used by the

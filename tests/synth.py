@@ -121,3 +121,4 @@ def make_counts(n_samples, P, *, depth=2000, seed=2, ref=None, pos_id=None, soma
 def to_oracle_layout(counts):
     """[S][2][P][4] -> [S][P][8] (fw ACGT, bw ACGT) as oracle.pyoracle.dense_to_rows expects."""
     return np.ascontiguousarray(np.concatenate([counts[:, 0], counts[:, 1]], axis=-1))
+

@@ -79,3 +79,31 @@ def test_programs_end_to_end_byte_identical(name, tmp_path):
         assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == case["vcfs"][nm], nm
     dummy = (tmp_path / "v" / "AmpliSolveVariantCalling_interm_files" / "dummyVCF_1.vcf").read_text().splitlines()
     assert len(dummy) == len(slots) and dummy[0] == f"{slots[0][0]}\t{slots[0][1]}\t.\t.\t.\t.\t.\t."
+
+
+def test_program_escapes_counts_beyond_the_16_bit_wire_format(tmp_path):
+    """The loaders fill the uint16 wire format; a record with a count of 65534 or more is escaped into the side list of
+    wide records.  Checked end to end against the oracle's table on a panel with a few ultra-deep positions (incl.
+    depths beyond 2^24, where int -> float stops being exact)."""
+    from tests import synth
+    bed, slots, pos_id, U = synth.make_panel(14, seed=61, chroms=("chr5",))
+    P = len(slots)
+    normals, ref = synth.make_counts(6, P, depth=3000, seed=61, pos_id=pos_id, big_rate=0.01)
+    normals[2, 0, 7, :] = [70000, 3, 0, 1]          # one count just beyond 16 bits
+    assert normals[normals != 0xFFFFFFFF].max() >= 1 << 24
+    ref_u = np.zeros(U, np.uint8)
+    ref_u[pos_id] = ref
+    case = {"bed": "".join(f"{c}\t{s}\t{e}\tA{i}\t.\tG\n" for i, (c, s, e) in enumerate(bed)),
+            "ref_letters": "".join("ACGT"[r] for r in ref_u[pos_id]), "normal_names": [f"BIG{i}" for i in range(6)],
+            "normals": normals, "tumour_names": [], "tumours": np.zeros((0, 2, P, 4), np.uint32)}
+    slots2 = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots2, list(case["ref_letters"]))
+    run("AmpliSolveErrorEstimation", ["panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N", "C_value=0.002",
+                                      "coverage_cutoff=100", "default_error=0.01", "output_dir=o"], tmp_path)
+    got = (tmp_path / "o" / "positionSpecificNoise_0.0020.txt").read_text().splitlines()
+    order = pyoracle.hash_iteration_order([f"N/{n}.PILEUP.ASEQ" for n in case["normal_names"]])
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(normals[order]), pos_id)
+    nz = pyoracle.noise_estimate(rows, off, U, np.float32(0.002), 100)
+    case.update(slots=slots2)
+    want = gu.noise_table_lines(case, nz["thr"][pos_id], nz["germ_val"][pos_id], nz["germ_present"][pos_id])
+    assert got == want

@@ -245,6 +245,35 @@ def test_host_pipelines_across_tile_boundaries(ctx, tile):
     check_calls(calls, wcalls, [np.nonzero(present[s])[0] for s in range(9)])
 
 
+def test_wire16_host_entry_points_equal_the_32_bit_ones(ctx):
+    """as_noise_estimate_host16 / as_call_variants_host16: same kernels behind a half-size PCIe format; records with a
+    count beyond 16 bits travel in the side list of wide records."""
+    from amplisolve_b200 import to_wire16
+    _, slots, pos_id, U = synth.make_panel(30, seed=51, overlap_frac=0.5)
+    P = len(slots)
+    normals, ref = synth.make_counts(13, P, depth=4000, seed=51, pos_id=pos_id, big_rate=0.01)
+    tumours, _ = synth.make_counts(10, P, depth=4000, seed=52, ref=ref, pos_id=pos_id, somatic_rate=0.02, big_rate=0.01)
+    tumours[3, 1, 17, :] = [65534, 1, 0, 0]     # exactly the escape code: must be escaped, not mistaken for it
+    normals[5, 0, 40, :] = [65533, 2, 0, 0]     # the largest count the narrow form carries
+    nxt, head = ctx_twins(pos_id)
+    n16, nw = to_wire16(normals)
+    t16, tw = to_wire16(tumours)
+    assert len(nw) > 5 and len(tw) > 5 and (n16[5, 0, 40] == [65533, 2, 0, 0]).all() and (t16[3, :, 17] == 0xFFFE).all()
+    for tile in (0, 256):
+        ctx.set_host_tile_slots(tile)
+        try:
+            wide = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head)
+            narrow = ctx.estimate_thresholds(n16, 0.002, 100, nxt, head, wide_records=nw)
+            for k in wide:
+                assert np.array_equal(wide[k].view(np.uint8), narrow[k].view(np.uint8)), k
+            view = pyoracle.thr_as_caller_sees(np.where(np.isnan(wide["thr"]), np.float32(0.01), wide["thr"]))
+            a = ctx.call_variants(tumours, ref, view, 100)
+            b = ctx.call_variants(t16, ref, view, 100, wide_records=tw)
+            assert len(a) > 0 and a.tobytes() == b.tobytes()
+        finally:
+            ctx.set_host_tile_slots(0)
+
+
 def test_device_pipeline_matches_host_entry_points(ctx):
     """_dev entry points (inputs resident in HBM, torch tensors) == _host entry points, incl. slot ranges."""
     import torch

@@ -146,13 +146,25 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
     }
     const int64_t p = tile0 + tid;
     bool active = tid < n_slots;
-    int twin_d = 0;
+    // role of this slot: 0 singleton, 1 first slot of a twin pair whose second slot is in this CTA tile, 2 that second
+    // slot, 3 any other member of a twin group (left to noise_pair_kernel / noise_twin_kernel)
+    int role = 0, twin_d = 0;
+    constexpr bool kPairsInTile = AS_INTILE_TWINS && (StageRing<K, STAGES>::kStageBytes * STAGES >= AS_TILE_SLOTS * (int)sizeof(PairXfer));
     if (active && twin_next != nullptr) {
-        if (AS_INTILE_TWINS) twin_d = intile_twin_distance(twin_next, twin_head, p, p + twin_base, tid, n_slots);
-        // other members of twin groups are reduced by their head (in this tile) or by noise_twin_kernel
-        if (twin_d == 0 && (twin_next[p] >= 0 || twin_head[p] != (int32_t)(p + twin_base))) active = false;
+        const int64_t gid = p + twin_base;
+        if (twin_next[p] >= 0 || twin_head[p] != (int32_t)gid) role = 3;
+        if (kPairsInTile) {
+            twin_d = intile_twin_distance(twin_next, twin_head, p, gid, tid, n_slots);
+            if (twin_d > 0) {
+                role = 1;
+            } else if (role == 3) {
+                const int64_t back = gid - (int64_t)twin_head[p];  // distance to the head of this slot's group
+                if (back > 0 && back <= tid && intile_twin_distance(twin_next, twin_head, p - back, gid - back, tid - (int)back, n_slots) == (int)back)
+                    role = 2;
+            }
+        }
+        if (role == 3) active = false;
     }
-    const int n_rows = (AS_INTILE_TWINS && twin_d > 0) ? 2 : 1;
 
     FastAcc f;
     fast_init(f);
@@ -164,21 +176,33 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
 #pragma unroll
             for (int j = 0; j < K; ++j) {
                 if (j < k) {
-#pragma unroll 1
-                    for (int r = 0; r < n_rows; ++r) {  // the second row only for the head of an in-tile twin pair
-                        const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid + r * twin_d];
-                        const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid + r * twin_d];
-                        fast_accumulate(f, fw, bw, C, cut);
-                    }
+                    const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid];
+                    const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid];
+                    fast_accumulate(f, fw, bw, C, cut);
                 }
             }
         }
         ring.consumer_release(it);
-        since_fold += 2 * K;
+        since_fold += K;
         if (since_fold >= AS_FOLD_EVERY) { fast_fold(f); since_fold = 0; }
     }
     fast_fold(f);
-    if (active) noise_finish_slot(f, counts + p, S, P, C, cut, p, twin_d, thr, germ_val, germ_state, count, nrec);
+
+    if (kPairsInTile && twin_next != nullptr) {
+        // Twin pairs inside the tile: both threads reduced their own rows like singletons (no cost in the loop above);
+        // the second slot's thread hands its state over through the (now idle) ring memory and the first slot's thread
+        // merges EXACTLY: sums add; for Germ_Max the file order is (sample, first slot) < (sample, second slot), the
+        // overall first qualifying record is dropped and the other thread's first one joins the maximum (pair_merge).
+        PairXfer* xfer = reinterpret_cast<PairXfer*>(smem_raw);
+        PairFirst mine;
+        if (role == 1 || role == 2) pair_find_first(mine, f, counts + p, S, P, C, cut);
+        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");  // every consumer warp is done with the ring
+        if (role == 2) { xfer[tid].f = f; xfer[tid].first = mine; }
+        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");
+        if (role == 1) pair_merge(f, mine, xfer[tid + twin_d].f, xfer[tid + twin_d].first);
+        if (role == 2) active = false;  // stored by the first slot's thread
+    }
+    if (active) noise_finish_slot(f, counts + p, S, P, C, cut, p, role == 1 ? twin_d : 0, thr, germ_val, germ_state, count, nrec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -912,7 +936,12 @@ cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int6
     int32_t* d_pairs = d_heads_scratch;
     int32_t* d_groups = d_heads_scratch + half;
     cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), st);
-    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, (AS_INTILE_TWINS && cfg != 0) ? 1 : 0,
+    // in-tile pairs are reduced by the staged kernel when its ring can hold the hand-over block (see kPairsInTile)
+    int ring_kb = 0;
+    switch (cfg) { case 0: ring_kb = 0; break; case 2: ring_kb = 64; break; case 3: ring_kb = 32; break; case 4: ring_kb = 64; break;
+                   case 5: ring_kb = 96; break; case 6: ring_kb = 32; break; default: ring_kb = 48; }
+    const int skip_intile = (AS_INTILE_TWINS && ring_kb * 1024 >= AS_TILE_SLOTS * (int)sizeof(PairXfer)) ? 1 : 0;
+    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, skip_intile,
                                                            d_pairs, d_groups, d_counters);
     // pairs: at most (p1-p0)/2 quads; enough CTAs to cover a typical panel (~1 % of the slots) in one pass
     const unsigned pair_grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (p1 - p0) / 64 / 32 + 1));  // 32 pairs per CTA

@@ -10,9 +10,10 @@
 #define AS_NOISE_THREADS 128
 #define AS_NOISE_UNROLL 4
 #define AS_CALL_THREADS 128
-/* 1: a duplicated position whose two slots share a CTA tile is reduced inside the staged noise kernel (measured
- * slower than leaving every twin group to noise_twin_kernel: the extra row loop costs every thread) */
-#define AS_INTILE_TWINS 0
+/* 1: a duplicated position whose two slots share a CTA tile is reduced inside the staged noise kernel: each slot's
+ * thread scans its own rows, the two states are merged exactly after the sample loop (as_noise.cuh pair_merge).
+ * 0: every twin group goes to noise_pair_kernel / noise_twin_kernel. */
+#define AS_INTILE_TWINS 1
 #define AS_DEFAULT_CALL_KERNEL 3  /* TMA-staged, 4 samples per stage, 2 stages: best of the measured sweep */
 #define AS_DEFAULT_NOISE_KERNEL 1 /* TMA-staged, 4 samples per stage, 3 stages */
 

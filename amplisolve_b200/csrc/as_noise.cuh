@@ -227,6 +227,80 @@ __device__ __forceinline__ void fast_to_general(const FastAcc& f, NoiseAcc& a) {
     for (int i = 0; i < 4; ++i) fast_base_to_general(f.b[i], a.b[i]);
 }
 
+// ---- exact merge of the two slots of a twin pair (fast-path states) ----------------------------------------
+// Each thread reduced the rows of its own slot as if it were a singleton, so each dropped ITS first qualifying
+// Germ_Max record.  In file order the rows interleave -- (sample 0, slot a), (sample 0, slot b), (sample 1, slot a) ...
+// -- and the reference drops only the overall first qualifying record (EE:1258-1262).  PairFirst recovers, per base,
+// the sample index and the rational of a thread's own first qualifying record (a short re-scan from sample 0 that
+// stops as soon as every base that has one is found).
+struct PairFirst {
+    uint32_t s[4], x[4], rd[4];
+};
+struct PairXfer {
+    FastAcc f;
+    PairFirst first;
+};
+
+__device__ __forceinline__ void pair_find_first(PairFirst& o, const FastAcc& f, const uint4* __restrict__ q, int S, int64_t P,
+                                                float C, uint32_t cut) {
+    uint32_t need = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        o.s[i] = 0xFFFFFFFFu; o.x[i] = 0; o.rd[i] = 1;
+        if (f.b[i].g_rd != 0u) need |= 1u << i;
+    }
+#pragma unroll 1
+    for (int s = 0; s < S && need; ++s) {
+        uint4 fw, bw;
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(fw.x), "=r"(fw.y), "=r"(fw.z), "=r"(fw.w) : "l"(q + (int64_t)s * 2 * P));
+        asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(bw.x), "=r"(bw.y), "=r"(bw.z), "=r"(bw.w) : "l"(q + (int64_t)s * 2 * P + P));
+        if ((int32_t)fw.x < 0) continue;
+        FastRecord r;
+        fast_record(r, fw, bw, C, cut);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t x = comp(fw, i) + comp(bw, i);
+            if ((need >> i & 1u) && (int32_t)x <= r.lim_rd) {
+                o.s[i] = (uint32_t)s; o.x[i] = x; o.rd[i] = r.RD;
+                need &= ~(1u << i);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void rational_max(uint32_t& bx, uint32_t& brd, bool& have, uint32_t x, uint32_t rd) {
+    if (!have || (unsigned long long)x * brd >= (unsigned long long)bx * rd) { bx = x; brd = rd; }
+    have = true;
+}
+
+// A: state of the first slot's thread (rows precede B's within a sample), B: the second slot's.  Result in A.
+__device__ __forceinline__ void pair_merge(FastAcc& A, const PairFirst& fa, const FastAcc& B, const PairFirst& fb) {
+    A.nrec += B.nrec;
+    A.big |= B.big;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        FastBase& a = A.b[i];
+        const FastBase& b = B.b[i];
+        a.s_b_fw += b.s_b_fw; a.s_b_bw += b.s_b_bw;
+        a.s_d_fw = __dadd_rn(a.s_d_fw, b.s_d_fw); a.s_d_bw = __dadd_rn(a.s_d_bw, b.s_d_bw);
+        a.s_p_fw = __dadd_rn(a.s_p_fw, b.s_p_fw); a.s_p_bw = __dadd_rn(a.s_p_bw, b.s_p_bw);
+        a.count += b.count;
+        const int ca = a.g_rd == 0u ? 0 : (a.g_rd == 1u ? 1 : 2), cb = b.g_rd == 0u ? 0 : (b.g_rd == 1u ? 1 : 2);
+        if (ca == 0 && cb == 0) continue;  // still absent: (g_x, g_rd) = (1, 0)
+        const bool a_is_first = ca > 0 && (cb == 0 || fa.s[i] <= fb.s[i]);
+        uint32_t bx = 0, brd = 1;
+        bool have = false;
+        if (ca == 2) rational_max(bx, brd, have, a.g_x, a.g_rd);
+        if (cb == 2) rational_max(bx, brd, have, b.g_x, b.g_rd);
+        if (ca > 0 && cb > 0) {
+            if (a_is_first) rational_max(bx, brd, have, fb.x[i], fb.rd[i]);
+            else rational_max(bx, brd, have, fa.x[i], fa.rd[i]);
+        }
+        a.g_x = have ? bx : 0u;    // (0, 1): exactly one qualifying record in the pair
+        a.g_rd = have ? brd : 1u;
+    }
+}
+
 // Merge the state R of a LATER record segment into L (earlier).  Associative.
 __device__ __forceinline__ void noise_merge(NoiseAcc& L, const NoiseAcc& R) {
     L.nrec += R.nrec;

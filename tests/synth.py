@@ -38,7 +38,7 @@ def make_panel(n_amplicons=40, amp_len=(60, 130), overlap_frac=0.3, seed=1, chro
 
 
 def make_counts(n_samples, P, *, depth=2000, seed=2, ref=None, pos_id=None, somatic_rate=0.0, absent_rate=0.03,
-                low_cov_rate=0.05, edge_rate=0.02, big_rate=0.0):
+                low_cov_rate=0.05, edge_rate=0.02, big_rate=0.0, ragged_twins=False):
     """Dense counts with: log-normal depth, per-slot strand-specific error rates, germline SNPs, optional
     spiked SNVs, absent rows, low-coverage rows (around the cutoff of 100), rows whose alt fraction sits
     exactly on / next to the 5 % boundary (5/100, 50/1000, 51/1000 ...), zero-depth strands, and
@@ -113,6 +113,15 @@ def make_counts(n_samples, P, *, depth=2000, seed=2, ref=None, pos_id=None, soma
                 counts[:, :, p, :] = counts[:, :, first[u], :]
                 drop = rng.random(n_samples) < 0.1
                 counts[drop, :, p, :] = ABSENT
+                if ragged_twins:
+                    # API-level stress (an ASEQ file cannot express it): rows that differ between the twins, and samples
+                    # where only the SECOND twin has a row, so that the first qualifying Germ_Max record of the pair can
+                    # come from either slot
+                    jitter = rng.random(n_samples) < 0.3
+                    sel = jitter & (counts[:, 0, p, 0] != ABSENT)
+                    counts[sel, 0, p, (ref[p] + 1) % 4] += rng.integers(0, 4, size=int(sel.sum())).astype(np.uint32)
+                    gone = rng.random(n_samples) < 0.15
+                    counts[gone, :, first[u], :] = ABSENT
             else:
                 first[u] = p
     return counts, ref

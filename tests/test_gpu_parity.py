@@ -69,6 +69,28 @@ def ctx_twins(pos_id):
     return twin_links(pos_id)
 
 
+@pytest.mark.parametrize("variant", [1, 4, 6, 0])
+@pytest.mark.parametrize("seed", [71, 72, 73])
+def test_noise_twin_pairs_with_different_rows(ctx, variant, seed):
+    """Twin pairs reduced inside the streaming kernel (exact merge of two per-slot states), by the pair kernel (pairs
+    cut by a CTA tile, variants without the in-tile path) and by the general kernel (three enumerations): the rows of
+    the two slots differ and either slot can hold the pair's first qualifying Germ_Max record."""
+    _, slots, pos_id, U = synth.make_panel(50, seed=seed, overlap_frac=0.8, amp_len=(20, 60))
+    pos_id = pos_id.copy()
+    pos_id[-3] = pos_id[5]          # a position enumerated three times
+    P = len(slots)
+    counts, _ = synth.make_counts(37, P, depth=1200, seed=seed, pos_id=pos_id, ragged_twins=True)
+    nxt, head = ctx_twins(pos_id)
+    ctx.set_noise_kernel(variant)
+    try:
+        got = ctx.estimate_thresholds(counts, 0.002, 100, nxt, head)
+    finally:
+        ctx.set_noise_kernel(-1)
+    _, dense_id = np.unique(pos_id, return_inverse=True)
+    check_noise(got, oracle_noise(counts, dense_id.astype(np.int32), dense_id.max() + 1, np.float32(0.002), 100),
+                dense_id.astype(np.int32))
+
+
 def test_noise_no_twins_ragged_and_empty(ctx):
     for P in (1, 31, 127, 129, 1000):
         pos_id = np.arange(P, dtype=np.int32)

@@ -544,11 +544,11 @@ def main():
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "Poisson tests/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
     res = run_ours(args)
     if res is not None:
-        print(json.dumps(res))
+        print(json.dumps(res), flush=True)
 
 
 if __name__ == "__main__":

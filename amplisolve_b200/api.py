@@ -338,4 +338,9 @@ def calls_from_device(calls, n_calls) -> np.ndarray:
     if n > cap:
         raise AmpliSolveError(f"call list overflow: {n} calls, capacity {cap}")
     raw = calls.view(-1)[: n * CALL_DTYPE.itemsize].cpu().numpy().view(CALL_DTYPE)
-    return np.sort(raw, order=["sample", "slot", "alt"])
+    return sort_calls(raw)
+
+
+def sort_calls(calls: np.ndarray) -> np.ndarray:
+    """Reference row order: sample (file), slot (row), alt (AmpliSolveVariantCalling.cpp:672, :869-3288)."""
+    return calls[np.lexsort((calls["alt"], calls["slot"], calls["sample"]))]

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .api import CALL_DTYPE
+from .api import CALL_DTYPE, sort_calls
 
 
 def shard_ranges(n_slots: int, world: int, twin_head=None, twin_next=None, align: int = 128):
@@ -46,7 +46,7 @@ def gather_calls(calls: np.ndarray, slot_offset: int, group=None, device=None) -
     calls = np.ascontiguousarray(calls, dtype=CALL_DTYPE).copy()
     calls["slot"] += np.int32(slot_offset)
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return np.sort(calls, order=["sample", "slot", "alt"])
+        return sort_calls(calls)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = torch.device(device) if device is not None else torch.device("cpu")
     n = torch.tensor([len(calls)], dtype=torch.int64, device=dev)
@@ -62,4 +62,4 @@ def gather_calls(calls: np.ndarray, slot_offset: int, group=None, device=None) -
     if rank != 0:
         return None
     parts = [o.cpu().numpy()[: s * CALL_DTYPE.itemsize].view(CALL_DTYPE) for o, s in zip(out, sizes)]
-    return np.sort(np.concatenate(parts), order=["sample", "slot", "alt"])
+    return sort_calls(np.concatenate(parts))

@@ -104,8 +104,8 @@ def lib():
     L.as_kernel_launches.argtypes = [vp]
     L.as_kernel_launches.restype = i64
     L.as_noise_estimate_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
-    L.as_noise_estimate_host.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp]
-    L.as_noise_estimate_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp]
+    L.as_noise_estimate_host.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
+    L.as_noise_estimate_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     L.as_thresholds_caller_view_dev.argtypes = [vp, vp, vp, i64, vp]
     L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
     L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
@@ -206,7 +206,8 @@ class Context:
         _check(lib().as_set_host_tile_slots(self._h, slots))
 
     # ---- host-buffer entry points --------------------------------------------------------------
-    def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None, wide_records=None):
+    def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None, wide_records=None,
+                            with_view=False):
         """counts: uint32 [S][2][P][4] host array, or the uint16 wire format with its wide_records (to_wire16);
         normals in the reference's file order."""
         wide = np.asarray(counts).dtype != np.uint16
@@ -217,15 +218,19 @@ class Context:
         out = {"thr": np.empty((P, 4, 2), np.float32), "germ_val": np.empty((P, 4), np.float32),
                "germ_state": np.empty((P, 4), np.uint8), "count": np.empty((P, 4), np.uint32),
                "nrec": np.empty(P, np.uint32)}
+        view = np.empty((P, 4, 2), np.float32) if with_view else None
         tn = th = None
         if twin_next is not None:
             tn, th = _np(twin_next, np.int32), _np(twin_head, np.int32)
         tail = (None if tn is None else _hp(tn), None if th is None else _hp(th), np.float32(c_value), int(coverage_cutoff),
-                _hp(out["thr"]), _hp(out["germ_val"]), _hp(out["germ_state"]), _hp(out["count"]), _hp(out["nrec"]))
+                _hp(out["thr"]), _hp(out["germ_val"]), _hp(out["germ_state"]), _hp(out["count"]), _hp(out["nrec"]),
+                None if view is None else _hp(view))
         if wide:
             _check(lib().as_noise_estimate_host(self._h, _hp(counts), S, P, *tail))
         else:
             _check(lib().as_noise_estimate_host16(self._h, _hp(counts), _hp(wr), len(wr), S, P, *tail))
+        if view is not None:
+            out["thr_view"] = view   # thresholds as the caller parses them ("%f" text round trip, -1_-1 -> 0.01)
         return out
 
     def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None, wide_records=None):

@@ -777,7 +777,7 @@ int as_error_estimation_main(int argc, char** argv) {
     const int32_t* th = panel.has_twins ? panel.twin_head.data() : nullptr;
     const int rc = as_noise_estimate_host16(ctx, counts.p, counts.wide.data(), (int64_t)counts.wide.size(), S, P, tn, th,
                                             C_value_float, cut, thr.data(), germ_val.data(), germ_state.data(), count.data(),
-                                            nrec.data());
+                                            nrec.data(), nullptr);
     as_destroy(ctx);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");

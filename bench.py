@@ -536,9 +536,8 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     stats = {}
 
     def one():
-        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th, wide_records=w_norm)
-        view = ctx.thresholds_caller_view_dev(torch.from_numpy(noise["thr"]).cuda()).cpu().numpy()
-        calls = ctx.call_variants(h_tum, h_ref, view, cut, cap=cap, wide_records=w_tum)
+        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th, wide_records=w_norm, with_view=True)
+        calls = ctx.call_variants(h_tum, h_ref, noise["thr_view"], cut, cap=cap, wide_records=w_tum)
         stats["calls"] = len(calls)
 
     one()  # warm-up (allocates the tile buffers)
@@ -556,10 +555,10 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     L.as_host_free(hp_n)
     L.as_host_free(hp_t)
     return {"value": 6.0 * T * Pe * world / dt, "unit": "Poisson tests/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + Pe * 32 + 40 * (len(w_norm) + len(w_tum))), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
+            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + 40 * (len(w_norm) + len(w_tum))), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
             "slots_per_gpu": Pe, "host_dtype": (f"uint16 wire format + {len(w_norm) + len(w_tum)} escaped wide records (lossless)" if narrow else "uint32"),
-            "api": ("as_noise_estimate_host16 + as_thresholds_caller_view_dev + as_call_variants_host16" if narrow else
-                    "as_noise_estimate_host + as_thresholds_caller_view_dev + as_call_variants_host") + ", pinned host buffers",
+            "api": ("as_noise_estimate_host16 + as_call_variants_host16" if narrow else
+                    "as_noise_estimate_host + as_call_variants_host") + ", pinned host count tensors",
             "timer": "host wall clock around the blocking C-ABI calls, max over ranks"}
 
 

@@ -107,9 +107,11 @@ int as_noise_estimate_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int6
                           int64_t slot_end, const int32_t* d_twin_next, const int32_t* d_twin_head, float C,
                           int32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count,
                           uint32_t* d_nrec, void* stream);
+/* The _host forms also fill thr_view [P][4][2] when it is not NULL: the thresholds as the caller will parse them
+ * (as_thresholds_caller_view_dev applied while the tile is still on the device). */
 int as_noise_estimate_host(as_ctx* ctx, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
                            const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
-                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec);
+                           uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view);
 
 /* The 16-bit wire format of the _host16 entry points: uint16 counts[sample][strand][slot][base], half the host footprint
  * and PCIe traffic of the uint32 layout.  A record whose eight counts are all < 65534 is stored as is; an absent record
@@ -126,7 +128,7 @@ typedef struct {
 #define AS_WIRE_ESCAPE 0xFFFEu
 int as_noise_estimate_host16(as_ctx* ctx, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t S,
                              int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut, float* thr,
-                             float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec);
+                             float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view);
 
 /* The noise table crosses to the caller as "%f" text (EE:1787 -> std::stof at VC:889-890) with
  * "-1_-1" replaced by "0.01_0.01" (EE:2680-2684).  This applies exactly that mapping to thr

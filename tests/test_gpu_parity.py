@@ -284,11 +284,12 @@ def test_wire16_host_entry_points_equal_the_32_bit_ones(ctx):
     for tile in (0, 256):
         ctx.set_host_tile_slots(tile)
         try:
-            wide = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head)
-            narrow = ctx.estimate_thresholds(n16, 0.002, 100, nxt, head, wide_records=nw)
+            wide = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head, with_view=True)
+            narrow = ctx.estimate_thresholds(n16, 0.002, 100, nxt, head, wide_records=nw, with_view=True)
             for k in wide:
                 assert np.array_equal(wide[k].view(np.uint8), narrow[k].view(np.uint8)), k
             view = pyoracle.thr_as_caller_sees(np.where(np.isnan(wide["thr"]), np.float32(0.01), wide["thr"]))
+            assert np.array_equal(bits(wide["thr_view"]), bits(view))      # the view filled by the host pipeline itself
             a = ctx.call_variants(tumours, ref, view, 100)
             b = ctx.call_variants(t16, ref, view, 100, wide_records=tw)
             assert len(a) > 0 and a.tobytes() == b.tobytes()

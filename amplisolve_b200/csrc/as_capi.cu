@@ -90,7 +90,12 @@ int as_create(int device, as_ctx** out) {
     c->device = device;
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->exec_stream, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    {
+        // highest priority: its few CTAs must be dispatched between the waves of the streaming kernel, not after them
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi));
+    }
     CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
@@ -168,22 +173,25 @@ int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_
     CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (d_twin_next) {
-        // twin groups (~1-2 % of the slots, scattered reads) write slots the streaming kernel skips: fork them onto a
-        // second stream so they run under the streaming kernel, join before returning control to the caller's stream
         CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((e - b + 1) / 2 + 1)));
         CU(c->nheads.need(2 * sizeof(uint32_t)));
         CU(cudaEventRecord(c->ev_fork, st));
+    }
+    // the streaming kernel goes out first so that it starts at once ...
+    CU(as_launch_noise_main(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
+                            d_germ_state, d_count, d_nrec, st));
+    c->launches += 1;
+    if (d_twin_next) {
+        // ... and the twin groups it leaves out (pairs cut by a CTA tile, longer chains: scattered reads, a few CTAs)
+        // run beside it on a second stream; they write other slots.  Joined before control returns to the caller's stream.
         CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
         CU(as_launch_noise_twins(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
                                  (uint32_t*)c->nheads.p, C, (uint32_t)cut, d_thr, d_germ_val, d_germ_state, d_count,
                                  d_nrec, c->aux_stream));
         CU(cudaEventRecord(c->ev_join, c->aux_stream));
         c->launches += 3;
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
-    CU(as_launch_noise_main(c->noise_cfg, d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, C, (uint32_t)cut, d_thr, d_germ_val,
-                            d_germ_state, d_count, d_nrec, st));
-    c->launches += 1;
-    if (d_twin_next) CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     return AS_OK;
 }
 

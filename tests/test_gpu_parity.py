@@ -370,3 +370,29 @@ def test_synthetic_generator_round_trip(ctx):
     check_calls(got_calls, wcalls, [np.nonzero(present[s])[0] for s in range(T)])
     rd = h_norm.astype(np.int64).sum(axis=(1, 3))[h_norm[:, 0, :, 0] != 0xFFFFFFFF]
     assert 1200 < np.median(rd) < 3000
+
+
+def test_call_list_capacity_and_empty_inputs(ctx):
+    """AS_EOVERFLOW reports the true count (the wrapper retries with it); no tumours / no slots give no calls."""
+    import ctypes as C
+    from amplisolve_b200 import api
+    _, slots, pos_id, U = synth.make_panel(10, seed=91)
+    P = len(slots)
+    normals, ref = synth.make_counts(8, P, depth=3000, seed=91, pos_id=pos_id)
+    tumours, _ = synth.make_counts(6, P, depth=3000, seed=92, ref=ref, pos_id=pos_id, somatic_rate=0.05)
+    nz = oracle_noise(normals, pos_id, U, np.float32(0.002), 100)
+    thr = pyoracle.thr_as_caller_sees(np.where(np.isnan(nz["thr"]), np.float32(0.01), nz["thr"]))[pos_id]
+    full = ctx.call_variants(tumours, ref, thr, 100)
+    assert len(full) > 20
+    small = ctx.call_variants(tumours, ref, thr, 100, cap=7)          # retried internally after AS_EOVERFLOW
+    assert small.tobytes() == full.tobytes()
+    calls = np.zeros(7, dtype=api.CALL_DTYPE)
+    n = C.c_int64(0)
+    rc = api.lib().as_call_variants_host(ctx._h, tumours.ctypes.data_as(C.c_void_p), 6, P, ref.ctypes.data_as(C.c_void_p),
+                                         np.ascontiguousarray(thr).ctypes.data_as(C.c_void_p), 100,
+                                         calls.ctypes.data_as(C.c_void_p), 7, C.byref(n))
+    assert rc == -5 and n.value == len(full) and b"calls found" in api.lib().as_last_error()
+    assert len(ctx.call_variants(np.zeros((0, 2, P, 4), np.uint32), ref, thr, 100)) == 0
+    assert len(ctx.call_variants(np.zeros((3, 2, 0, 4), np.uint32), ref[:0], thr[:0], 100)) == 0
+    with pytest.raises(api.AmpliSolveError, match="cutoff"):
+        ctx.call_variants(tumours, ref, thr, 0)

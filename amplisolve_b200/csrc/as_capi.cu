@@ -44,6 +44,12 @@ struct DevBuf {  // grow-only device scratch
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+struct PinnedBuf {  // pinned host scratch, released on every exit path
+    void* p = nullptr;
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t alloc(size_t n) { return cudaHostAlloc(&p, n ? n : 16, cudaHostAllocDefault); }
+};
+
 struct as_ctx {
     int device = 0;
     int call_variant = AS_DEFAULT_CALL_KERNEL;   // 0 straightforward, 1 queued (direct loads), >= 2 TMA-staged (K, stages) variants
@@ -318,10 +324,14 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     // kernel, twin groups that lie completely inside the tile by the twin kernels on tile-local links.  A group that
     // straddles a tile boundary is excluded here (all its members get head = -1) and done in pass 2.
     int64_t ntiles = (P + TP - 1) / TP;
+    PinnedBuf links_buf[2];
     int32_t* h_links[2] = {nullptr, nullptr};  // pinned staging of the tile-local links: next[n] | head[n]
     std::vector<int32_t> crossing;             // heads of the groups that straddle tiles
     if (twin_next) {
-        for (int i = 0; i < 2; ++i) CU(cudaHostAlloc((void**)&h_links[i], (size_t)TP * 8, cudaHostAllocDefault));
+        for (int i = 0; i < 2; ++i) {
+            CU(links_buf[i].alloc((size_t)TP * 8));
+            h_links[i] = (int32_t*)links_buf[i].p;
+        }
         CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((TP + 1) / 2 + 1)));
         CU(c->nheads.need(2 * sizeof(uint32_t)));
     }
@@ -391,8 +401,6 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
 #undef CUT
     {
         cudaError_t e1 = cudaStreamSynchronize(c->exec_stream), e2 = cudaStreamSynchronize(c->copy_stream);
-        for (int i = 0; i < 2; ++i)
-            if (h_links[i]) cudaFreeHost(h_links[i]);
         if (ret1 != AS_OK) return ret1;
         if (e1 != cudaSuccess || e2 != cudaSuccess)
             return fail(AS_ECUDA, "noise pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -417,8 +425,9 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     }
     const int64_t M = (int64_t)members.size();
     if (M == 0) return AS_OK;
-    uint32_t* h_gather = nullptr;
-    CU(cudaHostAlloc((void**)&h_gather, (size_t)M * 32 * (size_t)std::max(1, S), cudaHostAllocDefault));
+    PinnedBuf gather_buf;
+    CU(gather_buf.alloc((size_t)M * 32 * (size_t)std::max(1, S)));
+    uint32_t* h_gather = (uint32_t*)gather_buf.p;
     for (int64_t smp = 0; smp < S; ++smp)
         for (int64_t m = 0; m < M; ++m)
             host_record(src, P, smp, members[m], h_gather + ((smp * 2) * M + m) * 4, h_gather + ((smp * 2 + 1) * M + m) * 4);
@@ -461,7 +470,6 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
         }
     } while (0);
     d_cnt.release(); d_out.release(); d_links.release();
-    cudaFreeHost(h_gather);
     return ret;
 }
 
@@ -530,8 +538,9 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
     CU(cudaMemsetAsync(d_n, 0, 8, c->exec_stream));
     const int64_t ntiles = (P + TP - 1) / TP;
     // the tile kernels emit tile-local slot ids; the offsets are fixed up after the download
-    unsigned long long* h_n = nullptr;
-    CU(cudaHostAlloc((void**)&h_n, sizeof(unsigned long long) * (size_t)ntiles, cudaHostAllocDefault));
+    PinnedBuf hn_buf;
+    CU(hn_buf.alloc(sizeof(unsigned long long) * (size_t)ntiles));
+    unsigned long long* h_n = (unsigned long long*)hn_buf.p;
     int ret = AS_OK;
     for (int64_t t = 0; t < ntiles && ret == AS_OK; ++t) {
         const int bsel = (int)(t & 1);
@@ -577,7 +586,6 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
             if ((int64_t)total > cap) ret = fail(AS_EOVERFLOW, "%llu calls found, capacity %lld", total, (long long)cap);
         }
     }
-    cudaFreeHost(h_n);
     return ret;
 }
 

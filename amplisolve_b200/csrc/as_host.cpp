@@ -453,11 +453,6 @@ struct PhaseTimer {
     }
 };
 
-struct Pinned {
-    void* p = nullptr;
-    ~Pinned() { if (p) as_host_free(p); }
-    bool alloc(size_t bytes) { return as_host_alloc(&p, bytes ? bytes : 16) == AS_OK; }
-};
 
 // ---------------------------------------------------------------------------------------------------
 // per-call annotations (host only: these run for called variants, a vanishing fraction of the records)

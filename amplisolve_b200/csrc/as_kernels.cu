@@ -891,12 +891,14 @@ template <int K, int STAGES>
 static cudaError_t launch_noise_staged(const uint4* c, int S, int64_t P, int64_t p0, int64_t p1, const int32_t* tn,
                                        const int32_t* th, int64_t twin_base, float C, uint32_t cut, float* thr,
                                        float* gv, uint8_t* gs, uint32_t* cnt, uint32_t* nrec, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[AS_MAX_DEVICES] = {};  // the attribute is per device
     const int smem = StageRing<K, STAGES>::kStageBytes * STAGES;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(noise_staged_kernel<K, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
     }
     noise_staged_kernel<K, STAGES><<<cdiv64(p1 - p0, AS_TILE_SLOTS), AS_CTA_THREADS, smem, st>>>(
         c, S, P, p0, p1, tn, th, twin_base, C, cut, thr, gv, gs, cnt, nrec);
@@ -990,12 +992,14 @@ template <int K, int STAGES>
 static cudaError_t launch_call_staged(dim3 grid, const uint4* c, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
                                       const uint8_t* ref, const float* tv, uint32_t cut, as_call* calls, int64_t cap,
                                       unsigned long long* n, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured[AS_MAX_DEVICES] = {};  // the attribute is per device
     const int smem = StageRing<K, STAGES>::kStageBytes * STAGES;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(call_staged_kernel<K, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
     }
     call_staged_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(c, T, P, p0, p1, chunk, ref, tv, cut, calls, cap, n);
     return cudaGetLastError();

@@ -10,6 +10,7 @@
 #define AS_NOISE_THREADS 128
 #define AS_NOISE_UNROLL 4
 #define AS_CALL_THREADS 128
+#define AS_MAX_DEVICES 64
 /* 1: a duplicated position whose two slots share a CTA tile is reduced inside the staged noise kernel: each slot's
  * thread scans its own rows, the two states are merged exactly after the sample loop (as_noise.cuh pair_merge).
  * 0: every twin group goes to noise_pair_kernel / noise_twin_kernel. */

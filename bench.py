@@ -167,7 +167,7 @@ def cpu_reference(steps, warmup, sample_slots=1000, sample_normals=100, sample_t
     """Times the reference CPU path on all host cores over a bounded sample; returns the JSON fragments."""
     cores = os.cpu_count() or 1
     have_ref = (ROOT / "oracle" / "_ref" / "ee_ref").exists() and (ROOT / "oracle" / "_ref" / "AmpliSolveVariantCalling").exists()
-    kind = "reference" if have_ref else "port"
+    kind = "reference" if have_ref and not os.environ.get("AS_BENCH_FORCE_PORT") else "port"
     with tempfile.TemporaryDirectory(prefix="asb_", dir="/tmp") as td:
         sample = make_reference_sample(td, sample_slots, sample_normals, sample_tumours, WORKLOAD["depth"], WORKLOAD["seed"])
         walls, noises = [], []

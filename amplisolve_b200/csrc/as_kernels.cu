@@ -976,15 +976,15 @@ cudaError_t as_launch_thr_view(const float* d_thr, float* d_view, int64_t n, cud
 }
 
 int as_call_chunk(int T, int64_t n_slots) {
-    // enough threads to fill the chip a few times over; at least 4 samples per thread
-    const int64_t target = 148ll * 2048 * 4;
-    int64_t chunks = (target + n_slots - 1) / (n_slots > 0 ? n_slots : 1);
-    if (chunks < 1) chunks = 1;
+    // tumour samples per CTA.  Enough CTAs for about ten waves of the 148 x 5 resident ones (a short tail even when
+    // CTAs run for milliseconds), but at least 16 samples = 4 stages per CTA (its pipeline fill is a fixed cost).
+    // Measured: 41 k slots x 96 tumours 64 -> 50 us; 100 k x 10,000 unchanged; 2 M x 500 is one chunk either way.
+    const int64_t tiles = (n_slots + AS_TILE_SLOTS - 1) / AS_TILE_SLOTS;
+    const int64_t chunks = std::max<int64_t>(1, (148ll * 5 * 10 + tiles - 1) / std::max<int64_t>(tiles, 1));
     int64_t chunk = (T + chunks - 1) / chunks;
-    if (chunk < 4) chunk = 4;
+    if (chunk < 16) chunk = 16;
     if (chunk > T) chunk = T;
-    // gridDim.y limit
-    while ((T + chunk - 1) / chunk > 65535) chunk *= 2;
+    while ((T + chunk - 1) / chunk > 65535) chunk *= 2;  // gridDim.y limit
     return (int)(chunk < 1 ? 1 : chunk);
 }
 

@@ -396,3 +396,46 @@ def test_call_list_capacity_and_empty_inputs(ctx):
     assert len(ctx.call_variants(np.zeros((3, 2, 0, 4), np.uint32), ref[:0], thr[:0], 100)) == 0
     with pytest.raises(api.AmpliSolveError, match="cutoff"):
         ctx.call_variants(tumours, ref, thr, 0)
+
+
+def test_device_step_can_be_captured_in_a_cuda_graph(ctx):
+    """The _dev entry points only enqueue work (kernels, memset nodes, a fork/join onto the side stream), so a whole
+    step -- noise model, threshold hand-over, caller -- can be captured once and replayed: the way to run small panels,
+    where seven launches cost more than the kernels.  Replays on fresh inputs must equal the eager path."""
+    import torch
+    from amplisolve_b200 import calls_from_device
+    P, S, T = 1000, 12, 9
+    gen = dict(mean_depth=1500.0, twin_period=2)
+    normals, ref = ctx.synth_counts_dev(S, P, seed=1, **gen)
+    tumours, _ = ctx.synth_counts_dev(T, P, seed=1, somatic_rate=0.01, sample_offset=1 << 20, want_ref=False, **gen)
+    nxt, head = ctx.synth_twin_links_dev(P, seed=1, twin_period=2)
+    out = ctx.alloc_noise_outputs(P)
+    view = torch.empty_like(out["thr"])
+    calls = torch.zeros(48 * 50000, dtype=torch.uint8, device="cuda")
+    n = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def step():
+        ctx.estimate_thresholds_dev(normals, 0.002, 100, out, nxt, head)
+        ctx.thresholds_caller_view_dev(out["thr"], view)
+        n.zero_()
+        ctx.call_variants_dev(tumours, ref, view, 100, calls, n)
+
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        step()                                   # warm-up outside capture: scratch allocations, kernel attributes
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            step()
+    for seed in (2, 3):
+        fresh_n, fresh_ref = ctx.synth_counts_dev(S, P, seed=seed, **gen)
+        fresh_t, _ = ctx.synth_counts_dev(T, P, seed=seed, somatic_rate=0.01, sample_offset=1 << 20, want_ref=False, **gen)
+        normals.copy_(fresh_n); tumours.copy_(fresh_t); ref.copy_(fresh_ref)
+        graph.replay()
+        torch.cuda.synchronize()
+        got_thr, got_calls = out["thr"].clone(), calls_from_device(calls, n)
+        step()
+        torch.cuda.synchronize()
+        assert torch.equal(got_thr.view(torch.int32), out["thr"].view(torch.int32))
+        want_calls = calls_from_device(calls, n)
+        assert len(want_calls) > 0 and got_calls.tobytes() == want_calls.tobytes()

@@ -102,3 +102,26 @@ def test_two_ranks_equal_one():
     assert shards[0][2] == shards[1][1] and 0 < shards[0][2] < len(pos_id)
     assert np.array_equal(np.isnan(thr), np.isnan(thr_all))
     assert np.array_equal(thr[~np.isnan(thr)].view(np.uint32), thr_all[~np.isnan(thr_all)].view(np.uint32))
+
+
+def test_shard_ranges_properties_random():
+    """Random panels: the ranges tile [0, P), are near-equal, and never separate the slots of one position."""
+    rng = np.random.default_rng(123)
+    for _ in range(200):
+        P = int(rng.integers(1, 5000))
+        U = max(1, int(P * rng.uniform(0.5, 1.0)))
+        pos_id = np.sort(rng.integers(0, U, P)).astype(np.int32)
+        # overlapping amplicons put a position's second slot a short distance after the first
+        swap = rng.integers(0, P, P // 10)
+        for i in swap:
+            j = min(P - 1, i + int(rng.integers(1, 12)))
+            pos_id[i], pos_id[j] = pos_id[j], pos_id[i]
+        nxt, head = twin_links(pos_id)
+        world = int(rng.integers(1, 9))
+        rs = shard_ranges(P, world, head, nxt, align=int(rng.choice([1, 32, 128])))
+        assert len(rs) == world and rs[0][0] == 0 and rs[-1][1] == P
+        assert all(a[1] == b[0] and a[0] <= a[1] for a, b in zip(rs, rs[1:]))
+        owner = np.empty(P, dtype=np.int64)
+        for r, (b, e) in enumerate(rs):
+            owner[b:e] = r
+        assert np.array_equal(owner, owner[head])        # every slot sits in the shard of its group's first slot

@@ -647,6 +647,52 @@ call_queued_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     if (n2 > 0) stage2_batch(q2, n2, ref, calls, cap, n_calls);
 }
 
+// Survivor entry of the staged kernel: 24 bytes (the thresholds are read again from thr_view when the series is
+// evaluated -- survivors are a few per ten thousand records -- so that five CTAs fit one SM).
+struct StagedCand {
+    uint32_t k_fw, d_fw, k_bw, d_bw;
+    uint32_t sample_alt;  // sample | alt << 30
+    int32_t slot;
+};
+static_assert(sizeof(StagedCand) == 24, "StagedCand is three 8-byte words");
+
+__device__ __forceinline__ void stage2_batch_staged(const StagedCand* __restrict__ q2, int n_pairs,
+                                                    const uint8_t* __restrict__ ref, const float* __restrict__ thr_view,
+                                                    as_call* __restrict__ calls, int64_t cap,
+                                                    unsigned long long* __restrict__ n_calls) {
+    const int lane = threadIdx.x & 31;
+    const int pair = lane >> 1, strand = lane & 1;
+    double p = 1.0;
+    StagedCand c;
+    const bool have = pair < n_pairs;
+    if (have) {
+        c = q2[pair];
+        const float e = thr_view[(int64_t)c.slot * 8 + 2 * (c.sample_alt >> 30) + strand];
+        p = strand == 0 ? poisson_p((int)c.k_fw, (int)c.d_fw, e) : poisson_p((int)c.k_bw, (int)c.d_bw, e);
+    }
+    const double p_other = __shfl_xor_sync(0xffffffffu, p, 1);
+    const bool is_call = have && strand == 0 && q_at_least_5(p) && q_at_least_5(p_other);
+    const unsigned votes = __ballot_sync(0xffffffffu, is_call);
+    if (votes == 0) return;
+    const int leader = __ffs(votes) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(n_calls, (unsigned long long)__popc(votes));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (is_call) {
+        const unsigned long long idx = base + __popc(votes & ((1u << lane) - 1u));
+        if ((int64_t)idx < cap) {
+            as_call o;
+            o.sample = (int32_t)(c.sample_alt & 0x3fffffffu);
+            o.slot = c.slot;
+            o.alt = (int32_t)(c.sample_alt >> 30);
+            o.ref = ref[c.slot];
+            o.p_fw = p; o.p_bw = p_other;
+            o.q_fw = q_from_p(p); o.q_bw = q_from_p(p_other);
+            calls[idx] = o;
+        }
+    }
+}
+
 // TMA-staged caller.  Per stage every consumer thread scans its K records out of shared memory with integer
 // tests only and keeps a 4-bit candidate mask per record; ONE warp prefix sum per stage compacts the
 // candidates into 16-bit (record, lane, base) entries.  Full warps then revisit the candidates in the still
@@ -662,7 +708,7 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES];
     __shared__ uint16_t cand_all[AS_CONSUMER_WARPS][CAND_CAP];
-    __shared__ __align__(16) CallCand q2_all[AS_CONSUMER_WARPS][AS_Q2_CAP];
+    __shared__ __align__(8) StagedCand q2_all[AS_CONSUMER_WARPS][AS_Q2_CAP];
     StageRing<K, STAGES> ring;
     ring.init(smem_raw, bars);
     const int64_t tile0 = p0 + (int64_t)blockIdx.x * AS_TILE_SLOTS;
@@ -681,7 +727,7 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
         if (r <= 3) notref = 0xfu & ~(1u << r);
     }
     uint16_t* cand = cand_all[warp];
-    CallCand* q2 = q2_all[warp];
+    StagedCand* q2 = q2_all[warp];
     int n2 = 0;
     uint32_t notref_rep = notref;  // the 4-bit mask replicated for every record of a stage
 #pragma unroll
@@ -727,7 +773,8 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
             // ---- revisit the candidates with full warps: exact m >= k screen, survivors to the series queue
             for (int base = 0; base < total; base += 32) {
                 const int i = base + lane;
-                uint4 w0 = make_uint4(0, 0, 0, 0), w1 = make_uint4(0, 0, 0, 0);  // the CallCand as two 16-byte words
+                uint4 w0 = make_uint4(0, 0, 0, 0);  // the StagedCand as a 16-byte and an 8-byte word
+                uint2 w1 = make_uint2(0, 0);
                 bool surv = false;
                 if (i < total) {
                     const uint32_t e = cand[i];
@@ -738,20 +785,20 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                     // thresholds of the candidate's slot: a rare read, served by L2
                     const float2 ee = *reinterpret_cast<const float2*>(thr_view + (tile0 + col) * 8 + 2 * b);
                     w0 = make_uint4(comp(fw, b), fw.x + fw.y + fw.z + fw.w, comp(bw, b), bw.x + bw.y + bw.z + bw.w);
-                    w1 = make_uint4(__float_as_uint(ee.x), __float_as_uint(ee.y), (uint32_t)(t + j) | ((uint32_t)b << 30),
-                                    (uint32_t)(tile0 + col));
+                    w1 = make_uint2((uint32_t)(t + j) | ((uint32_t)b << 30), (uint32_t)(tile0 + col));
                     surv = strand_can_pass(w0.x, w0.y, ee.x) && strand_can_pass(w0.z, w0.w, ee.y);
                 }
                 const unsigned votes = __ballot_sync(0xffffffffu, surv);
                 if (surv) {
-                    uint4* dst = reinterpret_cast<uint4*>(q2 + n2 + __popc(votes & ((1u << lane) - 1u)));
-                    dst[0] = w0;
-                    dst[1] = w1;
+                    uint2* dst = reinterpret_cast<uint2*>(q2 + n2 + __popc(votes & ((1u << lane) - 1u)));
+                    dst[0] = make_uint2(w0.x, w0.y);
+                    dst[1] = make_uint2(w0.z, w0.w);
+                    dst[2] = w1;
                 }
                 n2 += __popc(votes);
                 __syncwarp();
                 while (n2 >= 16) {
-                    stage2_batch(q2 + (n2 - 16), 16, ref, calls, cap, n_calls);
+                    stage2_batch_staged(q2 + (n2 - 16), 16, ref, thr_view, calls, cap, n_calls);
                     n2 -= 16;
                     __syncwarp();
                 }
@@ -759,7 +806,7 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
         }
         ring.consumer_release(it);
     }
-    if (n2 > 0) stage2_batch(q2, n2, ref, calls, cap, n_calls);
+    if (n2 > 0) stage2_batch_staged(q2, n2, ref, thr_view, calls, cap, n_calls);
 }
 
 // ------------------------------------------------------------------------------------------------

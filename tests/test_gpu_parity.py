@@ -206,7 +206,7 @@ def check_calls(got, want, rows_slot):
         assert np.allclose(got["q_" + side], want["q_" + side], rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("variant", [3, 2, 1, 0, 5, 7])
+@pytest.mark.parametrize("variant", [11, 3, 2, 1, 0, 5, 7])
 @pytest.mark.parametrize("T,n_amp,depth,cut,seed", [
     (3, 30, 1800, 100, 21),
     (24, 16, 5000, 100, 22),

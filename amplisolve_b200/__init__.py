@@ -4,5 +4,5 @@ The product is libamplisolve_b200.so (CUDA kernels behind a C ABI, include/ampli
 two drop-in programs under amplisolve_b200/bin; this package is the thin Python mirror used by the
 tests and the benchmark.
 """
-from .api import (ABSENT, CALL_DTYPE, AmpliSolveError, Context, calls_from_device, hash_iteration_order, lib,  # noqa: F401
+from .api import (ABSENT, CALL_DTYPE, AmpliSolveError, Context, calls_from_device, fisher_test, hash_iteration_order, lib,  # noqa: F401
                   to_wire16, twin_links)

@@ -30,7 +30,7 @@ EXPORTS = [
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
     "as_call_variants_host16", "as_poisson_test_host",
-    "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_error_estimation_main",
+    "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
 
@@ -115,6 +115,8 @@ def lib():
     L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
     L.as_synth_twin_links_dev.argtypes = [vp, i64, C.POINTER(SynthParams), vp, vp, vp]
     L.as_hash_iteration_order.argtypes = [C.POINTER(C.c_char_p), i32, vp]
+    L.as_fisher_test.restype = C.c_double
+    L.as_fisher_test.argtypes = [i32, i32, i32, i32]
     for name in ("as_error_estimation_main", "as_variant_calling_main"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [C.c_int, C.POINTER(C.c_char_p)]
@@ -149,6 +151,11 @@ def hash_iteration_order(keys) -> list:
     if n < 0:
         raise AmpliSolveError("as_hash_iteration_order failed")
     return [int(i) for i in out[:n]]
+
+
+def fisher_test(fw: int, bw: int, alt_fw: int, alt_bw: int) -> float:
+    """fisherTest(FW, BW, alt_fw, alt_bw) of VC:3797-3814 (host arithmetic of the variant-calling program)."""
+    return float(lib().as_fisher_test(int(fw), int(bw), int(alt_fw), int(alt_bw)))
 
 
 def twin_links(pos_id) -> tuple[np.ndarray, np.ndarray]:

@@ -594,6 +594,13 @@ void report_load(const std::vector<CountFile>& files, const std::vector<AseqStat
 
 extern "C" {
 
+// fisherTest(FW, BW, alt_fw, alt_bw) of VC:3797-3814 as the variant-calling program evaluates it for every call
+// (VC:902).  Host arithmetic only; pinned against Boost.Math's hypergeometric pdf in tests/test_oracle_golden.py.
+double as_fisher_test(int32_t fw, int32_t bw, int32_t alt_fw, int32_t alt_bw) {
+    if (fw < 0 || bw < 0 || alt_fw < 0 || alt_bw < 0) return -1.0;
+    return fisher_test(fw, bw, alt_fw, alt_bw);
+}
+
 // The reference walks std::unordered_map<std::string,std::string> containers (EE:1081 normals, VC:672
 // tumours, VC:1046 FILTER flags) and that order is visible in its outputs.  The only faithful model of
 // libstdc++'s order is libstdc++: insert the same keys in the same sequence, read the order back.

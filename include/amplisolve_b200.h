@@ -192,6 +192,13 @@ int as_synth_twin_links_dev(as_ctx* ctx, int64_t P, const as_synth_params* prm, 
  * order_out[i] = index into keys of the i-th visited entry.  Returns the number of entries. */
 int as_hash_iteration_order(const char* const* keys, int32_t n, int32_t* order_out);
 
+/* Two-sided Fisher exact test of strand bias, fisherTest(a = RD_fw, b = RD_bw, c = alt reads fw, d = alt reads bw) of
+ * VC:3797-3814, as as_variant_calling_main evaluates it for every call (VC:902): cutoff = pdf(c) of the hypergeometric
+ * distribution (r = a + c, n = c + d, N = a + b + c + d), p = sum of the pdf(k) <= cutoff over k ascending.  The reference
+ * takes pdf from Boost.Math 1.61 (not in its tree); here pdf is C(r,k) C(N-r,n-k) / C(N,n) through lgamma.  Host code, no
+ * GPU needed.  Returns -1 for a negative argument. */
+double as_fisher_test(int32_t fw, int32_t bw, int32_t alt_fw, int32_t alt_bw);
+
 /* Whole programs, argv-compatible with the reference (EE:241-520, VC:199-360).  Exit status is
  * the return value; like the reference, usage errors print the usage text and return 0. */
 int as_error_estimation_main(int argc, char** argv);

@@ -6,7 +6,8 @@
  * PARITY PINNED: validated in tests/ against the real reference compiled from /root/reference
  * into oracle/_ref (Toy_data end-to-end, function-level grids for kf_gammaq / Q score) and
  * against the golden fixtures under tests/golden/ generated from that reference.
- * Exception: aso_fisher follows the Boost stand-in (Boost 1.61 is a missing blob) -> unpinned.
+ * aso_fisher follows the Boost stand-in header (Boost 1.61 is a missing blob of the reference); it is pinned to
+ * printed precision against SciPy's compiled-in Boost.Math pdf (tests/golden/fisher_boost.npz).
  *
  * Deliberately written the way the REFERENCE works -- one text-keyed record at a time, float
  * divides, no early-outs -- and on a different data representation (file rows keyed by a

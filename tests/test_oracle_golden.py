@@ -50,6 +50,39 @@ def test_fisher_standin(grid):
     assert np.allclose(got, grid["f_p"], rtol=1e-12, atol=0)
 
 
+def test_fisher_pinned_against_boost_math():
+    """The Fisher column against a REAL Boost.Math hypergeometric pdf (scipy's compiled-in Boost, evaluated by
+    tests/golden/make_fisher_boost.py over the reference's loop, VC:3797-3814) on all 1,202 call rows of the golden
+    cases and 1,500 seeded tables up to depth ~250,000: the oracle's and the product's p agree with Boost's to 2e-9
+    relative, give the same YES/NO strand-bias flag at the float p_value (VC:903), and print the same FisherPvalue text
+    at both precisions the reference uses (6 digits on the first row, 4 after) wherever p is a normal double."""
+    from amplisolve_b200 import fisher_test
+    g = np.load(gu.GOLDEN / "fisher_boost.npz")
+    tables = list(zip(g["fw"].tolist(), g["bw"].tolist(), g["alt_fw"].tolist(), g["alt_bw"].tolist()))
+    want = g["p_boost"]
+    assert len(tables) == 2702 and int(g["n_from_fixtures"]) == 1202
+    for name, fn in (("oracle", pyoracle.fisher), ("product", fisher_test)):
+        got = np.array([fn(*t) for t in tables])
+        normal = want > 1e-300
+        assert np.all(np.abs(got - want)[normal] <= 2e-9 * want[normal]), name
+        assert np.all(got[~normal] < 1e-300), name
+        for p_value in (np.float32(0.05), np.float32(0.01), np.float32(0.001)):
+            assert np.array_equal(got <= p_value, want <= p_value), name
+        for digits in (6, 4):
+            assert [gu.fmt_g(x, digits) for x in got[normal]] == [gu.fmt_g(x, digits) for x in want[normal]], name
+    # the strings the compiled reference (with the stand-in header) printed for the fixture calls are Boost's strings
+    nf = int(g["n_from_fixtures"])
+    for txt, p in zip(g["printed_by_standin"][:nf], want[:nf]):
+        assert str(txt) in (gu.fmt_g(p, 6), gu.fmt_g(p, 4))
+
+
+def test_product_fisher_equals_oracle_bitwise(grid):
+    from amplisolve_b200 import fisher_test
+    for a, b, c, d in zip(grid["f_a"], grid["f_b"], grid["f_c"], grid["f_d"]):
+        assert fisher_test(a, b, c, d) == pyoracle.fisher(a, b, c, d)
+    assert fisher_test(-1, 5, 1, 1) == -1.0
+
+
 def oracle_on_case(case):
     from tests import synth
     normals = case["normals"][case["normal_order"]]

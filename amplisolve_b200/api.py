@@ -29,7 +29,7 @@ EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
-    "as_call_variants_host16", "as_poisson_test_host",
+    "as_call_variants_host16", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
@@ -60,6 +60,49 @@ def to_wire16(counts):
     wide["sample"], wide["slot"] = smp, slot
     wide["fw"], wide["bw"] = counts[smp, 0, slot], counts[smp, 1, slot]
     return out, np.sort(wide, order=["slot", "sample"])
+
+
+PACKED_ABSENT, PACKED_ESCAPE = 0xFFFFFFFF, 0xFFFFFFFE
+
+
+def to_wire_packed(counts):
+    """uint32 [S][2][P][4] -> (packed uint32 [S][2][P], wide records): numpy statement of the packed wire format of the
+    _host_packed entry points (include/amplisolve_b200.h); as_pack_counts is the library's own (threaded) encoder."""
+    counts = np.asarray(counts, dtype=np.uint32)
+    absent = counts[:, 0, :, 0] == ABSENT                                       # [S][P]
+    j = counts.argmax(-1)                                                       # first maximum = lowest base index on ties
+    major = np.take_along_axis(counts, j[..., None], -1)[..., 0]
+    others = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])[j]          # [S][2][P][3]
+    minor = np.take_along_axis(counts, others, -1)
+    fits = (major <= 0xFFFF) & (minor <= 15).all(-1)
+    word = (major | (j.astype(np.uint32) << 16) | (minor[..., 0] << 18) | (minor[..., 1] << 22) | (minor[..., 2] << 26)).astype(np.uint32)
+    escaped = (~absent) & ~(fits[:, 0] & fits[:, 1])
+    for st in (0, 1):
+        word[:, st][escaped] = PACKED_ESCAPE
+        word[:, st][absent] = PACKED_ABSENT
+    smp, slot = np.nonzero(escaped)
+    wide = np.zeros(len(smp), dtype=WIDE_DTYPE)
+    wide["sample"], wide["slot"] = smp, slot
+    wide["fw"], wide["bw"] = counts[smp, 0, slot], counts[smp, 1, slot]
+    return word, np.sort(wide, order=["slot", "sample"])
+
+
+def pack_counts(counts):
+    """as_pack_counts: uint32 [S][2][P][4] -> (packed uint32 [S][2][P], wide records sorted by (slot, sample))."""
+    counts = _np(counts, np.uint32)
+    S, two, P, four = counts.shape
+    assert two == 2 and four == 4
+    packed = np.empty((S, 2, P), np.uint32)
+    cap = max(1024, S * P // 64)
+    while True:
+        wide = np.zeros(cap, dtype=WIDE_DTYPE)
+        n = C.c_int64(0)
+        rc = lib().as_pack_counts(_hp(counts), S, P, _hp(packed), _hp(wide), cap, C.byref(n))
+        if rc == -5:
+            cap = int(n.value)
+            continue
+        _check(rc)
+        return packed, wide[:n.value]
 
 
 class SynthParams(C.Structure):
@@ -110,6 +153,9 @@ def lib():
     L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
     L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.as_call_variants_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.as_noise_estimate_host_packed.argtypes = L.as_noise_estimate_host16.argtypes
+    L.as_call_variants_host_packed.argtypes = L.as_call_variants_host16.argtypes
+    L.as_pack_counts.argtypes = [vp, i32, i64, vp, vp, i64, C.POINTER(i64)]
     L.as_poisson_test_host.argtypes = [vp, vp, vp, vp, i64, vp, vp]
     L.as_kf_gammaq_host.argtypes = [vp, vp, vp, i64, vp]
     L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
@@ -174,6 +220,13 @@ def twin_links(pos_id) -> tuple[np.ndarray, np.ndarray]:
     return nxt, head
 
 
+def _host_format(counts) -> str:
+    a = np.asarray(counts)
+    if a.dtype == np.uint16:
+        return "u16"
+    return "packed" if a.ndim == 3 else "u32"
+
+
 class Context:
     """One per device (as_ctx)."""
 
@@ -184,6 +237,8 @@ class Context:
 
     def close(self):
         if self._h:
+            for p, _ in self.__dict__.pop("_pool", {}).values():
+                lib().as_host_free(p)
             lib().as_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -213,19 +268,38 @@ class Context:
         _check(lib().as_set_host_tile_slots(self._h, slots))
 
     # ---- host-buffer entry points --------------------------------------------------------------
+    def _pinned_array(self, name, shape, dtype):
+        """a numpy view of pinned host memory owned by this context, reused by the next call that asks for `name`"""
+        nbytes = max(16, int(np.prod(shape)) * np.dtype(dtype).itemsize)
+        pool = self.__dict__.setdefault("_pool", {})
+        have = pool.get(name)
+        if have is None or have[1] < nbytes:
+            if have is not None:
+                lib().as_host_free(have[0])
+            p = C.c_void_p()
+            _check(lib().as_host_alloc(C.byref(p), nbytes))
+            pool[name] = have = (p, nbytes)
+        buf = (C.c_char * nbytes).from_address(have[0].value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
     def estimate_thresholds(self, counts, c_value, coverage_cutoff, twin_next=None, twin_head=None, wide_records=None,
-                            with_view=False):
-        """counts: uint32 [S][2][P][4] host array, or the uint16 wire format with its wide_records (to_wire16);
-        normals in the reference's file order."""
-        wide = np.asarray(counts).dtype != np.uint16
-        counts = _np(counts, np.uint32 if wide else np.uint16)
+                            with_view=False, pinned_outputs=False):
+        """counts: uint32 [S][2][P][4] host array, the uint16 wire format [S][2][P][4] with its wide_records (to_wire16)
+        or the packed wire format uint32 [S][2][P] with its wide_records (pack_counts); normals in the reference's file
+        order."""
+        fmt = _host_format(counts)
+        wide = fmt == "u32"
+        counts = _np(counts, np.uint16 if fmt == "u16" else np.uint32)
         wr = _np(wide_records if wide_records is not None else np.zeros(0, WIDE_DTYPE), WIDE_DTYPE)
-        S, two, P, four = counts.shape
-        assert two == 2 and four == 4
-        out = {"thr": np.empty((P, 4, 2), np.float32), "germ_val": np.empty((P, 4), np.float32),
-               "germ_state": np.empty((P, 4), np.uint8), "count": np.empty((P, 4), np.uint32),
-               "nrec": np.empty(P, np.uint32)}
-        view = np.empty((P, 4, 2), np.float32) if with_view else None
+        S, two, P = counts.shape[:3]
+        assert two == 2 and (fmt == "packed" or counts.shape[3] == 4)
+        # pinned_outputs: the arrays live in pinned memory owned by the context (the D2H copies of the tile pipeline are
+        # then truly asynchronous) and are OVERWRITTEN by the next call with pinned_outputs
+        new = (lambda name, shape, dt: self._pinned_array(name, shape, dt)) if pinned_outputs else (lambda name, shape, dt: np.empty(shape, dt))
+        out = {"thr": new("thr", (P, 4, 2), np.float32), "germ_val": new("germ_val", (P, 4), np.float32),
+               "germ_state": new("germ_state", (P, 4), np.uint8), "count": new("count", (P, 4), np.uint32),
+               "nrec": new("nrec", (P,), np.uint32)}
+        view = new("thr_view", (P, 4, 2), np.float32) if with_view else None
         tn = th = None
         if twin_next is not None:
             tn, th = _np(twin_next, np.int32), _np(twin_head, np.int32)
@@ -235,34 +309,39 @@ class Context:
         if wide:
             _check(lib().as_noise_estimate_host(self._h, _hp(counts), S, P, *tail))
         else:
-            _check(lib().as_noise_estimate_host16(self._h, _hp(counts), _hp(wr), len(wr), S, P, *tail))
+            fn = lib().as_noise_estimate_host16 if fmt == "u16" else lib().as_noise_estimate_host_packed
+            _check(fn(self._h, _hp(counts), _hp(wr), len(wr), S, P, *tail))
         if view is not None:
             out["thr_view"] = view   # thresholds as the caller parses them ("%f" text round trip, -1_-1 -> 0.01)
         return out
 
-    def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None, wide_records=None):
-        """counts: uint32 [T][2][P][4] host array, or the uint16 wire format with its wide_records (to_wire16).
-        Returns calls sorted by (sample, slot, alt)."""
-        wide = np.asarray(counts).dtype != np.uint16
-        counts = _np(counts, np.uint32 if wide else np.uint16)
+    def call_variants(self, counts, ref, thr_view, coverage_cutoff, cap=None, wide_records=None, pinned_outputs=False):
+        """counts: uint32 [T][2][P][4] host array, or one of the two wire formats with its wide_records (see
+        estimate_thresholds).  Returns calls sorted by (sample, slot, alt)."""
+        fmt = _host_format(counts)
+        wide = fmt == "u32"
+        counts = _np(counts, np.uint16 if fmt == "u16" else np.uint32)
         wr = _np(wide_records if wide_records is not None else np.zeros(0, WIDE_DTYPE), WIDE_DTYPE)
-        T, two, P, four = counts.shape
-        assert two == 2 and four == 4
+        T, two, P = counts.shape[:3]
+        assert two == 2 and (fmt == "packed" or counts.shape[3] == 4)
         ref = _np(ref, np.uint8)
         thr_view = _np(thr_view, np.float32)
         assert ref.shape == (P,) and thr_view.shape == (P, 4, 2)
         if cap is None:
             cap = max(1024, T * P // 8)
-        calls = np.zeros(cap, dtype=CALL_DTYPE)
+        # only the first n entries are written and returned; pinned_outputs: see estimate_thresholds
+        calls = self._pinned_array("calls", (cap,), CALL_DTYPE) if pinned_outputs else np.empty(cap, dtype=CALL_DTYPE)
         n = C.c_int64(0)
         tail = (T, P, _hp(ref), _hp(thr_view), int(coverage_cutoff), _hp(calls), cap, C.byref(n))
         if wide:
             rc = lib().as_call_variants_host(self._h, _hp(counts), *tail)
         else:
-            rc = lib().as_call_variants_host16(self._h, _hp(counts), _hp(wr), len(wr), *tail)
+            fn = lib().as_call_variants_host16 if fmt == "u16" else lib().as_call_variants_host_packed
+            rc = fn(self._h, _hp(counts), _hp(wr), len(wr), *tail)
         _check(rc, allow_overflow=True)
         if rc == -5:
-            return self.call_variants(counts, ref, thr_view, coverage_cutoff, cap=int(n.value), wide_records=wide_records)
+            return self.call_variants(counts, ref, thr_view, coverage_cutoff, cap=int(n.value), wide_records=wide_records,
+                                      pinned_outputs=pinned_outputs)
         return calls[:n.value]
 
     def mutation_rules_poisson_quality_score(self, k, rd, err):

@@ -8,12 +8,32 @@
 #include <cstdio>
 #include <atomic>
 #include <cstring>
+#include <ctime>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
 #include "as_kernels.h"
+#include "as_wire.h"
 
 static thread_local char g_err[512] = "";
+
+// AS_TIMING=1 in the environment: one "AS_TIMING <phase> <seconds>" line per phase of the _host pipelines on stderr
+struct PhaseClock {
+    bool on;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    PhaseClock() : on(getenv("AS_TIMING") != nullptr), t0(now()) {}
+    void lap(const char* phase) {
+        const double t1 = now();
+        if (on) fprintf(stderr, "AS_TIMING capi.%s %.6f\n", phase, t1 - t0);
+        t0 = t1;
+    }
+};
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -50,6 +70,20 @@ struct PinnedBuf {  // pinned host scratch, released on every exit path
     cudaError_t alloc(size_t n) { return cudaHostAlloc(&p, n ? n : 16, cudaHostAllocDefault); }
 };
 
+struct PinnedGrow {  // grow-only pinned host scratch owned by the context (cudaHostAlloc costs ~1 ms: not per call)
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t need(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; bytes = 0; }
+};
+
 struct as_ctx {
     int device = 0;
     int call_variant = AS_DEFAULT_CALL_KERNEL;   // 0 straightforward, 1 queued (direct loads), >= 2 TMA-staged (K, stages) variants
@@ -60,7 +94,8 @@ struct as_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
-    DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls;  // _host pipelines
+    DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls, sortbuf;  // _host pipelines
+    PinnedGrow h_links, h_small;                                              // _host pipelines, host side
 };
 
 extern "C" {
@@ -116,7 +151,8 @@ void as_destroy(as_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release();
+    c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release(); c->sortbuf.release();
+    c->h_links.release(); c->h_small.release();
     for (int i = 0; i < 2; ++i) {
         c->tile[i].release(); c->tile16[i].release(); c->wide[i].release(); c->out[i].release(); c->aux[i].release();
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
@@ -209,16 +245,19 @@ int as_thresholds_caller_view_dev(as_ctx* c, const float* d_thr, float* d_view, 
     return AS_OK;
 }
 
-// Slots per tile of the _host pipelines: ~256 MiB of counts per buffer, multiple of 1024 slots.
-static int64_t tile_slots(const as_ctx* c, int32_t n_samples, int64_t P) {
+// Slots per tile of the _host pipelines: ~256 MiB of host data per buffer (elem * 8 bytes per record: the denser the
+// host format, the more slots per tile and the fewer tiles), multiple of 1024 slots.
+static int64_t tile_slots(const as_ctx* c, int32_t n_samples, int64_t P, int elem) {
     if (c->host_tile_slots > 0) return std::min(c->host_tile_slots, std::max<int64_t>(P, 1));
-    const int64_t per_slot = 32ll * std::max(1, n_samples);
+    const int64_t per_slot = 8ll * elem * std::max(1, n_samples);
     int64_t t = (256ll << 20) / per_slot;
     t = std::max<int64_t>(1024, (t / 1024) * 1024);
     return std::min(t, std::max<int64_t>(P, 1));
 }
 
-// A host count tensor: uint32 (elem = 4) or the uint16 wire format (elem = 2) with its side list of wide records.
+// A host count tensor: uint32 (elem = 4), the uint16 wire format (elem = 2) or the packed wire format (elem = 1: one
+// uint32 per (sample, strand, slot)); the two wire formats come with a side list of wide records.  elem * 4 = bytes per
+// (sample, strand, slot).
 struct HostSrc {
     const void* counts;
     int elem;
@@ -227,31 +266,44 @@ struct HostSrc {
 };
 
 // upload slots [p0, p0+n) of a host tensor [n_samples][2][P][4] into a packed device tile [n_samples][2][n][4] of uint32.
-// elem = 4: the host tensor is uint32.  elem = 2: it is uint16 (lossless wire format for counts < 65535, absent =
-// 0xFFFF); the half-size tile goes through a staging buffer and is widened on the device.
+// elem = 4: the host tensor is uint32.  elem = 2 / 1: it is in a wire format; the smaller tile goes through a staging
+// buffer and is widened / unpacked on the device, then the escaped records of the tile are patched in.
 static cudaError_t upload_tile(as_ctx* c, int bsel, const HostSrc& src, int32_t n_samples, int64_t P, int64_t p0, int64_t n,
                                cudaStream_t st) {
     const size_t word = (size_t)src.elem * 4;  // bytes per (sample, strand, slot)
     void* dst = src.elem == 4 ? c->tile[bsel].p : c->tile16[bsel].p;
-    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)n * word, (const char*)src.counts + (size_t)p0 * word, (size_t)P * word,
-                                      (size_t)n * word, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess || src.elem == 4) return e;
-    e = as_launch_widen16((const uint16_t*)dst, (uint32_t*)c->tile[bsel].p, (int64_t)n_samples * 2 * n, st);
+    return cudaMemcpy2DAsync(dst, (size_t)n * word, (const char*)src.counts + (size_t)p0 * word, (size_t)P * word,
+                             (size_t)n * word, (size_t)n_samples * 2, cudaMemcpyHostToDevice, st);
+}
+
+// wire formats: the uploaded tile is widened / unpacked into the uint32 tile and the escaped records of the tile are
+// patched in from the device copy of the side list.  Runs on the EXEC stream (after the upload event), so that the copy
+// stream goes straight on to the next tile.
+static cudaError_t expand_tile(as_ctx* c, int bsel, const HostSrc& src, int32_t n_samples, int64_t p0, int64_t n, cudaStream_t st) {
+    if (src.elem == 4) return cudaSuccess;
+    const void* stg = c->tile16[bsel].p;
+    cudaError_t e = src.elem == 2 ? as_launch_widen16((const uint16_t*)stg, (uint32_t*)c->tile[bsel].p, (int64_t)n_samples * 2 * n, st)
+                                  : as_launch_unpack((const uint32_t*)stg, (uint32_t*)c->tile[bsel].p, (int64_t)n_samples * 2 * n, st);
     c->launches += 1;
     if (e != cudaSuccess || src.n_wide == 0) return e;
-    // records with a count beyond 16 bits travel in the side list: patch the ones of this tile into the widened tile
     const as_wide_record* lo = std::lower_bound(src.wide, src.wide + src.n_wide, p0,
                                                 [](const as_wide_record& r, int64_t v) { return (int64_t)r.slot < v; });
     const as_wide_record* hi = std::lower_bound(lo, src.wide + src.n_wide, p0 + n,
                                                 [](const as_wide_record& r, int64_t v) { return (int64_t)r.slot < v; });
     const int64_t m = hi - lo;
     if (m == 0) return e;
-    e = c->wide[bsel].need((size_t)m * sizeof(as_wide_record));
+    c->launches += 1;  // the whole list is on the device already (stage_wide)
+    return as_launch_patch_wide((const as_wide_record*)c->wide[0].p + (lo - src.wide), m, (uint32_t*)c->tile[bsel].p, n, p0,
+                                n_samples, st);
+}
+
+// the side list of a wire-format tensor goes to the device once, ahead of the first tile, on the stream the tiles are
+// uploaded on (one copy instead of one small pageable copy per tile, which would stall the upload queue every tile)
+static cudaError_t stage_wide(as_ctx* c, const HostSrc& src, cudaStream_t st) {
+    if (src.elem == 4 || src.n_wide == 0) return cudaSuccess;
+    cudaError_t e = c->wide[0].need((size_t)src.n_wide * sizeof(as_wide_record));
     if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync(c->wide[bsel].p, lo, (size_t)m * sizeof(as_wide_record), cudaMemcpyHostToDevice, st);
-    if (e != cudaSuccess) return e;
-    c->launches += 1;
-    return as_launch_patch_wide((const as_wide_record*)c->wide[bsel].p, m, (uint32_t*)c->tile[bsel].p, n, p0, n_samples, st);
+    return cudaMemcpyAsync(c->wide[0].p, src.wide, (size_t)src.n_wide * sizeof(as_wide_record), cudaMemcpyHostToDevice, st);
 }
 
 // the eight counts of (sample, slot) out of a host tensor in either format (used for the few gathered twin members)
@@ -262,29 +314,57 @@ static void host_record(const HostSrc& src, int64_t P, int64_t sample, int64_t s
         memcpy(bw, (const uint32_t*)src.counts + wb * 4, 16);
         return;
     }
-    const uint16_t* f = (const uint16_t*)src.counts + wf * 4;
-    const uint16_t* b = (const uint16_t*)src.counts + wb * 4;
-    if (f[0] == 0xFFFFu) {
+    bool absent, escaped;
+    if (src.elem == 2) {
+        const uint16_t* f = (const uint16_t*)src.counts + wf * 4;
+        absent = f[0] == AS_WIRE_ABSENT;
+        escaped = f[0] == AS_WIRE_ESCAPE;
+    } else {
+        const uint32_t w = ((const uint32_t*)src.counts)[wf];
+        absent = w == AS_PACKED_ABSENT;
+        escaped = w == AS_PACKED_ESCAPE;
+    }
+    if (absent) {
         for (int i = 0; i < 4; ++i) fw[i] = bw[i] = AS_ABSENT;
-    } else if (f[0] == 0xFFFEu) {  // escaped: the real counts are in the side list
+    } else if (escaped) {  // the real counts are in the side list
         const as_wide_record* r = std::lower_bound(src.wide, src.wide + src.n_wide, slot,
                                                    [](const as_wide_record& x, int64_t v) { return (int64_t)x.slot < v; });
         for (; r < src.wide + src.n_wide && r->slot == slot; ++r)
             if (r->sample == sample) { memcpy(fw, r->fw, 16); memcpy(bw, r->bw, 16); return; }
         for (int i = 0; i < 4; ++i) fw[i] = bw[i] = AS_ABSENT;  // inconsistent input: treated as absent
-    } else {
+    } else if (src.elem == 2) {
+        const uint16_t* f = (const uint16_t*)src.counts + wf * 4;
+        const uint16_t* b = (const uint16_t*)src.counts + wb * 4;
         for (int i = 0; i < 4; ++i) { fw[i] = f[i]; bw[i] = b[i]; }
+    } else {
+        as_unpack_word(((const uint32_t*)src.counts)[wf], fw);
+        as_unpack_word(((const uint32_t*)src.counts)[wb], bw);
     }
 }
 
 static int check_wide(const HostSrc& src, int32_t n_samples, int64_t P) {
-    if (src.elem != 2) return AS_OK;
+    if (src.elem == 4) return AS_OK;
     if (src.n_wide < 0 || (src.n_wide > 0 && !src.wide)) return fail(AS_EINVAL, "bad wide-record list");
-    for (int64_t i = 0; i < src.n_wide; ++i) {
-        const as_wide_record& r = src.wide[i];
-        if (r.slot < 0 || r.slot >= P || r.sample < 0 || r.sample >= n_samples) return fail(AS_EINVAL, "wide record %lld out of range", (long long)i);
-        if (i > 0 && src.wide[i - 1].slot > r.slot) return fail(AS_EINVAL, "wide records must be sorted by slot");
-    }
+    // range and order of every record (the tiles find their records by binary search); a few threads for long lists
+    const int64_t n = src.n_wide;
+    const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 16u), n / 100000));
+    std::vector<int64_t> bad((size_t)nth, -1);
+    auto work = [&](int k) {
+        const int64_t lo = n * k / nth, hi = n * (k + 1) / nth;
+        for (int64_t i = lo; i < hi; ++i) {
+            const as_wide_record& r = src.wide[i];
+            if (r.slot < 0 || r.slot >= P || r.sample < 0 || r.sample >= n_samples || (i > 0 && src.wide[i - 1].slot > r.slot)) {
+                bad[(size_t)k] = i;
+                return;
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < nth; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto& x : th) x.join();
+    for (int k = 0; k < nth; ++k)
+        if (bad[(size_t)k] >= 0) return fail(AS_EINVAL, "wide record %lld out of range or out of order (sort by slot)", (long long)bad[(size_t)k]);
     return AS_OK;
 }
 
@@ -305,6 +385,7 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
                                     const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
                                     uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view) {
     const int elem = src.elem;
+    PhaseClock clk;
     int rc = check_common(c, src.counts, S, P, 0, P, cut);
     if (rc) return rc;
     if ((rc = check_wide(src, S, P)) != AS_OK) return rc;
@@ -312,11 +393,11 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
     if (P == 0) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(c, S, P);
+    const int64_t TP = tile_slots(c, S, P, elem);
     const NoiseOutLayout lay(TP);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)std::max(1, S)));
-        if (elem == 2) CU(c->tile16[i].need((size_t)TP * 16 * (size_t)std::max(1, S)));
+        if (elem != 4) CU(c->tile16[i].need((size_t)TP * 8 * (size_t)elem * (size_t)std::max(1, S)));
         CU(c->out[i].need(lay.total));
         if (twin_next) CU(c->aux[i].need((size_t)TP * 8));
     }
@@ -324,17 +405,49 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     // kernel, twin groups that lie completely inside the tile by the twin kernels on tile-local links.  A group that
     // straddles a tile boundary is excluded here (all its members get head = -1) and done in pass 2.
     int64_t ntiles = (P + TP - 1) / TP;
-    PinnedBuf links_buf[2];
-    int32_t* h_links[2] = {nullptr, nullptr};  // pinned staging of the tile-local links: next[n] | head[n]
-    std::vector<int32_t> crossing;             // heads of the groups that straddle tiles
+    int32_t* h_links = nullptr;     // pinned: the tile-local links of every tile, tile t at [2 * p0, 2 * (p0 + n)): next[n] | head[n]
+    std::vector<int32_t> crossing;  // heads of the groups that straddle tiles
     if (twin_next) {
-        for (int i = 0; i < 2; ++i) {
-            CU(links_buf[i].alloc((size_t)TP * 8));
-            h_links[i] = (int32_t*)links_buf[i].p;
-        }
+        CU(c->h_links.need((size_t)P * 8));
+        h_links = (int32_t*)c->h_links.p;
         CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((TP + 1) / 2 + 1)));
         CU(c->nheads.need(2 * sizeof(uint32_t)));
+        // every slot's verdict depends on its own chain only (does the whole group lie inside the slot's tile?), so
+        // the links of all tiles are written by a few threads before the first upload
+        const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 16u), P / 65536));
+        std::vector<std::vector<int32_t>> cross_t((size_t)nth);
+        auto work = [&](int k) {
+            for (int64_t g = P * k / nth, ge = P * (k + 1) / nth; g < ge; ++g) {
+                const int64_t p0 = (g / TP) * TP, n = std::min(TP, P - p0), i = g - p0;
+                int32_t* ln = h_links + p0 * 2;
+                int32_t* lh = ln + n;
+                const int64_t h = twin_head[g], nx = twin_next[g];
+                if (h == g && nx < 0) { ln[i] = -1; lh[i] = (int32_t)i; continue; }  // singleton
+                bool inside = h >= p0 && h <= g;
+                if (inside) {
+                    int64_t steps = 0;
+                    for (int64_t q = h; q >= 0; q = twin_next[q])
+                        if (q < p0 || q >= p0 + n || ++steps > n) { inside = false; break; }  // leaves the tile (or malformed: pass 2 reports it)
+                }
+                if (inside) {
+                    ln[i] = nx >= 0 ? (int32_t)(nx - p0) : -1;
+                    lh[i] = (int32_t)(h - p0);
+                } else {
+                    ln[i] = -1;
+                    lh[i] = -1;  // neither a singleton nor a head: skipped by every tile kernel
+                    if (h == g) cross_t[(size_t)k].push_back((int32_t)g);
+                }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int k = 1; k < nth; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto& x : th) x.join();
+        for (const auto& v : cross_t) crossing.insert(crossing.end(), v.begin(), v.end());  // ascending: the chunks are
     }
+    clk.lap("noise.checks_alloc");
+    CU(stage_wide(c, src, c->copy_stream));
+    clk.lap("noise.stage_wide");
     int ret1 = AS_OK;
 #define CUT(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret1 = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
     for (int64_t t = 0; t < ntiles; ++t) {
@@ -344,32 +457,13 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
         CUT(upload_tile(c, bsel, src, S, P, p0, n, c->copy_stream));
         int32_t *d_tn = nullptr, *d_th = nullptr;
         if (twin_next) {
-            if (t >= 2) CUT(cudaEventSynchronize(c->ev_up[bsel]));  // the staging block of this buffer has been uploaded
-            int32_t* ln = h_links[bsel];
-            int32_t* lh = ln + n;
-            for (int64_t i = 0; i < n; ++i) {
-                const int64_t g = p0 + i, h = twin_head[g], nx = twin_next[g];
-                if (h == g && nx < 0) { ln[i] = -1; lh[i] = (int32_t)i; continue; }  // singleton
-                bool inside = h >= p0;
-                if (inside && h == g)  // decide once per group, at its head: does the chain stay inside the tile?
-                    for (int64_t q = g; q >= 0; q = twin_next[q])
-                        if (q >= p0 + n) { inside = false; break; }
-                if (inside && h != g) inside = lh[h - p0] >= 0;  // members follow their head's verdict
-                if (inside) {
-                    ln[i] = nx >= 0 ? (int32_t)(nx - p0) : -1;
-                    lh[i] = (int32_t)(h - p0);
-                } else {
-                    ln[i] = -1;
-                    lh[i] = -1;  // neither a singleton nor a head: skipped by every tile kernel
-                    if (h == g) crossing.push_back((int32_t)g);
-                }
-            }
             d_tn = (int32_t*)c->aux[bsel].p;
             d_th = d_tn + n;
-            CUT(cudaMemcpyAsync(d_tn, ln, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            CUT(cudaMemcpyAsync(d_tn, h_links + p0 * 2, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
         }
         CUT(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
         CUT(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
+        CUT(expand_tile(c, bsel, src, S, p0, n, c->exec_stream));
         char* o = (char*)c->out[bsel].p;
         if (twin_next) CUT(cudaMemsetAsync(o, 0, lay.total, c->exec_stream));  // slots of crossing groups are filled in pass 2
         float* o_thr = (float*)(o + lay.thr);
@@ -399,8 +493,10 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
         CUT(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
     }
 #undef CUT
+    clk.lap("noise.enqueue");
     {
         cudaError_t e1 = cudaStreamSynchronize(c->exec_stream), e2 = cudaStreamSynchronize(c->copy_stream);
+        clk.lap("noise.drain");
         if (ret1 != AS_OK) return ret1;
         if (e1 != cudaSuccess || e2 != cudaSuccess)
             return fail(AS_ECUDA, "noise pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
@@ -473,34 +569,6 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     return ret;
 }
 
-// (sample, slot, alt) order = the reference's row order.  Counting sort by sample, then the (short) per-sample runs
-// are sorted by (slot, alt) on a few threads: ~10x faster than one std::sort over 48-byte records.
-static void sort_calls_reference_order(as_call* calls, int64_t n, int32_t T) {
-    if (n <= 1) return;
-    std::vector<int64_t> start((size_t)T + 1, 0);
-    for (int64_t i = 0; i < n; ++i) start[(size_t)calls[i].sample + 1]++;
-    for (int32_t t = 0; t < T; ++t) start[(size_t)t + 1] += start[(size_t)t];
-    std::vector<as_call> tmp((size_t)n);
-    {
-        std::vector<int64_t> fill(start.begin(), start.end() - 1);
-        for (int64_t i = 0; i < n; ++i) tmp[(size_t)fill[(size_t)calls[i].sample]++] = calls[i];
-    }
-    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), 16u));
-    std::atomic<int32_t> next(0);
-    auto work = [&]() {
-        for (int32_t t = next.fetch_add(1); t < T; t = next.fetch_add(1)) {
-            std::sort(tmp.begin() + start[(size_t)t], tmp.begin() + start[(size_t)t + 1], [](const as_call& a, const as_call& b) {
-                return a.slot != b.slot ? a.slot < b.slot : a.alt < b.alt;
-            });
-            std::copy(tmp.begin() + start[(size_t)t], tmp.begin() + start[(size_t)t + 1], calls + start[(size_t)t]);
-        }
-    };
-    std::vector<std::thread> th;
-    for (unsigned i = 1; i < hw && n > 50000; ++i) th.emplace_back(work);
-    work();
-    for (auto& x : th) x.join();
-}
-
 // ---- caller ----------------------------------------------------------------------------------------
 int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t P, int64_t b, int64_t e,
                          const uint8_t* d_ref, const float* d_thr_view, int32_t cut, as_call* d_calls, int64_t cap,
@@ -519,6 +587,7 @@ int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t
 static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int64_t P, const uint8_t* ref,
                                    const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
     const int elem = src.elem;
+    PhaseClock clk;
     int rc = check_common(c, src.counts, T, P, 0, P, cut);
     if (rc) return rc;
     if ((rc = check_wide(src, T, P)) != AS_OK) return rc;
@@ -526,21 +595,28 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
     *n_calls = 0;
     if (P == 0 || T == 0) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(c, T, P);
+    const int64_t TP = tile_slots(c, T, P, elem);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)T));
-        if (elem == 2) CU(c->tile16[i].need((size_t)TP * 16 * (size_t)T));
-        CU(c->aux[i].need((size_t)TP * 36));  // thr_view (32 B/slot) + ref (1 B/slot, padded)
+        if (elem != 4) CU(c->tile16[i].need((size_t)TP * 8 * (size_t)elem * (size_t)T));
     }
+    // thresholds (32 B/slot) and reference bases (1 B/slot) of the whole panel go up once, ahead of the first tile: a
+    // per-tile copy from pageable memory would stall the upload queue at every tile
+    CU(c->aux[0].need((size_t)P * 33 + 64));
+    float* d_tv_all = (float*)c->aux[0].p;
+    uint8_t* d_rf_all = (uint8_t*)c->aux[0].p + (size_t)P * 32;
+    CU(cudaMemcpyAsync(d_tv_all, thr_view, (size_t)P * 32, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d_rf_all, ref, (size_t)P, cudaMemcpyHostToDevice, c->copy_stream));
     CU(c->calls.need(sizeof(as_call) * (size_t)std::max<int64_t>(cap, 1)));
-    CU(c->misc.need(16));
-    unsigned long long* d_n = (unsigned long long*)c->misc.p;
-    CU(cudaMemsetAsync(d_n, 0, 8, c->exec_stream));
+    CU(c->misc.need(32));
+    CU(c->h_small.need(64));
+    unsigned long long* d_n = (unsigned long long*)c->misc.p;  // calls found so far; d_n[1] = the count before the current tile
+    unsigned long long* h_total = (unsigned long long*)c->h_small.p;
+    CU(cudaMemsetAsync(d_n, 0, 16, c->exec_stream));
     const int64_t ntiles = (P + TP - 1) / TP;
-    // the tile kernels emit tile-local slot ids; the offsets are fixed up after the download
-    PinnedBuf hn_buf;
-    CU(hn_buf.alloc(sizeof(unsigned long long) * (size_t)ntiles));
-    unsigned long long* h_n = (unsigned long long*)hn_buf.p;
+    clk.lap("call.checks_alloc");
+    CU(stage_wide(c, src, c->copy_stream));
+    clk.lap("call.stage_wide");
     int ret = AS_OK;
     for (int64_t t = 0; t < ntiles && ret == AS_OK; ++t) {
         const int bsel = (int)(t & 1);
@@ -548,43 +624,45 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
 #define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
         if (t >= 2) CUB(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));
         CUB(upload_tile(c, bsel, src, T, P, p0, n, c->copy_stream));
-        float* d_tv = (float*)c->aux[bsel].p;
-        uint8_t* d_rf = (uint8_t*)c->aux[bsel].p + (size_t)TP * 32;
-        CUB(cudaMemcpyAsync(d_tv, thr_view + p0 * 8, (size_t)n * 32, cudaMemcpyHostToDevice, c->copy_stream));
-        CUB(cudaMemcpyAsync(d_rf, ref + p0, (size_t)n, cudaMemcpyHostToDevice, c->copy_stream));
         CUB(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
         CUB(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
-        CUB(as_launch_call(c->call_variant, (const uint32_t*)c->tile[bsel].p, T, n, 0, n, d_rf, d_tv, (uint32_t)cut,
-                           (as_call*)c->calls.p, cap, d_n, c->exec_stream));
+        CUB(expand_tile(c, bsel, src, T, p0, n, c->exec_stream));
+        // the tile kernel emits tile-local slot ids; the entries it appended, [d_n[1], d_n[0]), get the tile offset
+        if (p0 > 0) CUB(cudaMemcpyAsync(d_n + 1, d_n, 8, cudaMemcpyDeviceToDevice, c->exec_stream));
+        CUB(as_launch_call(c->call_variant, (const uint32_t*)c->tile[bsel].p, T, n, 0, n, d_rf_all + p0, d_tv_all + p0 * 8,
+                           (uint32_t)cut, (as_call*)c->calls.p, cap, d_n, c->exec_stream));
         c->launches += 1;
-        CUB(cudaMemcpyAsync(h_n + t, d_n, 8, cudaMemcpyDeviceToHost, c->exec_stream));
+        if (p0 > 0) {
+            CUB(as_launch_call_slot_offset((as_call*)c->calls.p, d_n + 1, d_n, cap, (int32_t)p0, c->exec_stream));
+            c->launches += 1;
+        }
         CUB(cudaEventRecord(c->ev_done[bsel], c->exec_stream));
 #undef CUB
     }
+    clk.lap("call.enqueue");
     if (ret == AS_OK) {
+        cudaError_t e0 = cudaMemcpyAsync(h_total, d_n, 8, cudaMemcpyDeviceToHost, c->exec_stream);
         cudaError_t e1 = cudaStreamSynchronize(c->exec_stream), e2 = cudaStreamSynchronize(c->copy_stream);
-        if (e1 != cudaSuccess || e2 != cudaSuccess)
-            ret = fail(AS_ECUDA, "caller pipeline failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        clk.lap("call.drain");
+        if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
+            ret = fail(AS_ECUDA, "caller pipeline failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
     }
     if (ret == AS_OK) {
-        const unsigned long long total = h_n[ntiles - 1];
+        const unsigned long long total = *h_total;
         *n_calls = (int64_t)total;
         const int64_t have = std::min<int64_t>((int64_t)total, cap);
         if (have > 0) {
-            cudaError_t e = cudaMemcpy(calls, c->calls.p, sizeof(as_call) * (size_t)have, cudaMemcpyDeviceToHost);
-            if (e != cudaSuccess) ret = fail(AS_ECUDA, "download of calls failed: %s", cudaGetErrorString(e));
+            // the reference's row order (sample, slot, alt), sorted on the device; one copy into the caller's list
+            const size_t scratch = as_sort_calls_scratch_bytes(have), list = ((size_t)have * sizeof(as_call) + 255) & ~(size_t)255;
+            CU(c->sortbuf.need(list + scratch));
+            CU(as_launch_sort_calls((const as_call*)c->calls.p, have, (as_call*)c->sortbuf.p, (char*)c->sortbuf.p + list, scratch,
+                                    c->exec_stream));
+            c->launches += 3;
+            CU(cudaMemcpyAsync(calls, c->sortbuf.p, sizeof(as_call) * (size_t)have, cudaMemcpyDeviceToHost, c->exec_stream));
+            CU(cudaStreamSynchronize(c->exec_stream));
+            clk.lap("call.sort_download");
         }
-        if (ret == AS_OK) {
-            // calls of tile t occupy list positions [h_n[t-1], h_n[t]) because tiles run in stream order
-            int64_t lo = 0;
-            for (int64_t t = 0; t < ntiles; ++t) {
-                const int64_t hi = std::min<int64_t>((int64_t)h_n[t], have);
-                for (int64_t i = lo; i < hi; ++i) calls[i].slot += (int32_t)(t * TP);
-                lo = std::max(lo, hi);
-            }
-            sort_calls_reference_order(calls, have, T);
-            if ((int64_t)total > cap) ret = fail(AS_EOVERFLOW, "%llu calls found, capacity %lld", total, (long long)cap);
-        }
+        if ((int64_t)total > cap) ret = fail(AS_EOVERFLOW, "%llu calls found, capacity %lld", total, (long long)cap);
     }
     return ret;
 }
@@ -606,6 +684,66 @@ int as_call_variants_host(as_ctx* c, const uint32_t* counts, int32_t T, int64_t 
     const HostSrc src{counts, 4, nullptr, 0};
     return call_variants_host_impl(c, src, T, P, ref, thr_view, cut, calls, cap, n_calls);
 }
+int as_noise_estimate_host_packed(as_ctx* c, const uint32_t* packed, const as_wide_record* wide, int64_t n_wide, int32_t S,
+                                  int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut,
+                                  float* thr, float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec,
+                                  float* thr_view) {
+    const HostSrc src{packed, 1, wide, n_wide};
+    return noise_estimate_host_impl(c, src, S, P, twin_next, twin_head, C, cut, thr, germ_val, germ_state, count, nrec, thr_view);
+}
+int as_call_variants_host_packed(as_ctx* c, const uint32_t* packed, const as_wide_record* wide, int64_t n_wide, int32_t T,
+                                 int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls,
+                                 int64_t cap, int64_t* n_calls) {
+    const HostSrc src{packed, 1, wide, n_wide};
+    return call_variants_host_impl(c, src, T, P, ref, thr_view, cut, calls, cap, n_calls);
+}
+
+// uint32 counts -> packed wire format + escaped records.  Threads over samples; the per-sample lists are concatenated
+// and sorted by (slot, sample).
+int as_pack_counts(const uint32_t* counts, int32_t n_samples, int64_t P, uint32_t* packed, as_wide_record* wide,
+                   int64_t wide_cap, int64_t* n_wide) {
+    if (!counts || !packed || !n_wide || n_samples < 0 || P < 0 || wide_cap < 0 || (wide_cap > 0 && !wide))
+        return fail(AS_EINVAL, "bad argument");
+    *n_wide = 0;
+    std::vector<std::vector<as_wide_record>> per((size_t)n_samples);
+    std::atomic<int32_t> next(0);
+    auto work = [&]() {
+        for (int32_t s = next.fetch_add(1); s < n_samples; s = next.fetch_add(1)) {
+            const uint32_t* f = counts + ((int64_t)s * 2) * P * 4;
+            const uint32_t* b = f + P * 4;
+            uint32_t* pf = packed + ((int64_t)s * 2) * P;
+            uint32_t* pb = pf + P;
+            for (int64_t p = 0; p < P; ++p) {
+                if (f[p * 4] == AS_ABSENT) { pf[p] = pb[p] = AS_PACKED_ABSENT; continue; }
+                uint32_t wf, wb;
+                if (as_pack_word(f + p * 4, &wf) && as_pack_word(b + p * 4, &wb)) { pf[p] = wf; pb[p] = wb; continue; }
+                pf[p] = pb[p] = AS_PACKED_ESCAPE;
+                as_wide_record r;
+                r.sample = s;
+                r.slot = (int32_t)p;
+                memcpy(r.fw, f + p * 4, 16);
+                memcpy(r.bw, b + p * 4, 16);
+                per[(size_t)s].push_back(r);
+            }
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n_samples)));
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    int64_t total = 0;
+    for (const auto& v : per) total += (int64_t)v.size();
+    *n_wide = total;
+    if (total > wide_cap) return fail(AS_EOVERFLOW, "%lld records escape the packed format, capacity %lld", (long long)total, (long long)wide_cap);
+    int64_t k = 0;
+    for (const auto& v : per) { if (!v.empty()) memcpy(wide + k, v.data(), v.size() * sizeof(as_wide_record)); k += (int64_t)v.size(); }
+    std::sort(wide, wide + total, [](const as_wide_record& x, const as_wide_record& y) {
+        return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
+    });
+    return AS_OK;
+}
+
 int as_call_variants_host16(as_ctx* c, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t T,
                             int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls, int64_t cap,
                             int64_t* n_calls) {

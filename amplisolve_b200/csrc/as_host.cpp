@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "../../include/amplisolve_b200.h"
+#include "as_wire.h"
 
 namespace {
 
@@ -232,8 +233,15 @@ bool list_count_files(const std::string& dir, std::vector<CountFile>& files, std
 struct AseqStats {
     int64_t rows = 0, outside = 0, extra = 0, bad_rd = 0;
     bool ok = true;
-    std::vector<as_wide_record> wide;  // records of this file with a count beyond the 16-bit wire format
+    std::vector<as_wide_record> wide;  // records of this file that do not fit the wire format
 };
+
+// Host layouts of a count tensor (include/amplisolve_b200.h).  FMT = bytes per count in the two plain layouts (4: the
+// canonical uint32, 2: the 16-bit wire format), 1 = the packed wire format (one uint32 per (sample, strand, slot)).
+template <int FMT> struct Wire;
+template <> struct Wire<4> { typedef uint32_t E; enum { PER = 4 }; };
+template <> struct Wire<2> { typedef uint16_t E; enum { PER = 4 }; };
+template <> struct Wire<1> { typedef uint32_t E; enum { PER = 1 }; };
 
 inline bool parse_int(const char*& p, const char* e, long long& v) {
     p = skip_ws(p, e);
@@ -246,11 +254,13 @@ inline bool parse_int(const char*& p, const char* e, long long& v) {
     return true;
 }
 
-// counts: this sample's plane pair, [2][P][4]; row_of (optional) [P] file row index of each filled slot.
-// E = uint32_t (the canonical layout) or uint16_t (wire format of include/amplisolve_b200.h: a record with a count
-// of 65534 or more is escaped and goes to stats.wide).
-template <typename E>
-AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int32_t* row_of, int32_t sample) {
+// counts: this sample's plane pair, [2][P][PER]; row_of (optional) [P] file row index of each filled slot.
+// In the wire formats a record that does not fit (a count of 65534 or more in the 16-bit one; a major count beyond 16
+// bits or another count beyond 4 bits in the packed one) is escaped and goes to stats.wide.
+template <int FMT>
+AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<FMT>::E* counts, int32_t* row_of, int32_t sample) {
+    typedef typename Wire<FMT>::E E;
+    const int PER = Wire<FMT>::PER;
     const E absent = (E)~(E)0;
     AseqStats st;
     std::string text;
@@ -287,7 +297,7 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int3
                     const int k = seen[slot]++;
                     for (int j = 0; j < k && slot >= 0; ++j) slot = panel.twin_next[slot];
                     if (slot < 0) ++st.extra;
-                } else if (slot >= 0 && counts[(int64_t)slot * 4] != absent) {
+                } else if (slot >= 0 && counts[(int64_t)slot * PER] != absent) {
                     slot = -1;  // a second row for a position that owns one slot
                     ++st.extra;
                 } else if (slot < 0) {
@@ -296,14 +306,27 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int3
                 if (slot >= 0) {
                     // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
                     if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
-                    E* fw = counts + (int64_t)slot * 4;
-                    E* bw = counts + ((int64_t)P + slot) * 4;
+                    E* fw = counts + (int64_t)slot * PER;
+                    E* bw = counts + ((int64_t)P + slot) * PER;
                     bool escape = false;
-                    for (int b = 0; b < 4; ++b) {
-                        const long long f = v[b] - v[5 + b], r2 = v[5 + b];
-                        if (sizeof(E) == 2 && (f >= AS_WIRE_ESCAPE || r2 >= AS_WIRE_ESCAPE || f < 0 || r2 < 0)) escape = true;
-                        fw[b] = (E)f;
-                        bw[b] = (E)r2;
+                    if (FMT == 1) {
+                        uint32_t f4[4], r4[4], wf = 0, wb = 0;
+                        for (int b = 0; b < 4; ++b) {
+                            const long long f = v[b] - v[5 + b], r2 = v[5 + b];
+                            if (f < 0 || r2 < 0 || f > 0xFFFF || r2 > 0xFFFF) escape = true;
+                            f4[b] = (uint32_t)f;
+                            r4[b] = (uint32_t)r2;
+                        }
+                        if (!escape) escape = !(as_pack_word(f4, &wf) && as_pack_word(r4, &wb));
+                        fw[0] = (E)wf;
+                        bw[0] = (E)wb;
+                    } else {
+                        for (int b = 0; b < 4; ++b) {
+                            const long long f = v[b] - v[5 + b], r2 = v[5 + b];
+                            if (FMT == 2 && (f >= AS_WIRE_ESCAPE || r2 >= AS_WIRE_ESCAPE || f < 0 || r2 < 0)) escape = true;
+                            fw[b] = (E)f;
+                            bw[b] = (E)r2;
+                        }
                     }
                     if (escape) {
                         as_wide_record w;
@@ -312,7 +335,7 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int3
                         for (int b = 0; b < 4; ++b) {
                             w.fw[b] = (uint32_t)(v[b] - v[5 + b]);
                             w.bw[b] = (uint32_t)v[5 + b];
-                            fw[b] = bw[b] = (E)AS_WIRE_ESCAPE;
+                            if (b < PER) fw[b] = bw[b] = (E)(absent - 1);  // AS_WIRE_ESCAPE / AS_PACKED_ESCAPE
                         }
                         st.wide.push_back(w);
                     }
@@ -325,19 +348,21 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, E* counts, int3
     return st;
 }
 
-// all samples, in the given order, into one pinned tensor [n][2][P][4]
-template <typename E>
-bool load_all(const std::vector<CountFile>& files, const Panel& panel, E* counts, int32_t* row_of,
+// all samples, in the given order, into one pinned tensor [n][2][P][PER]
+template <int FMT>
+bool load_all(const std::vector<CountFile>& files, const Panel& panel, typename Wire<FMT>::E* counts, int32_t* row_of,
               std::vector<AseqStats>& stats) {
+    typedef typename Wire<FMT>::E E;
+    const int PER = Wire<FMT>::PER;
     const int n = (int)files.size();
     const int64_t P = panel.size();
     stats.assign(n, AseqStats());
     std::atomic<int> next(0);
     auto work = [&]() {
         for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
-            E* plane = counts + (int64_t)i * 2 * P * 4;
-            memset(plane, 0xFF, (size_t)P * 8 * sizeof(E));
-            stats[i] = load_aseq<E>(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr, (int32_t)i);
+            E* plane = counts + (int64_t)i * 2 * P * PER;
+            memset(plane, 0xFF, (size_t)P * 2 * PER * sizeof(E));
+            stats[i] = load_aseq<FMT>(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr, (int32_t)i);
         }
     };
     const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n)));
@@ -366,17 +391,31 @@ void parallel_for(size_t n, F body) {
     for (auto& t : th) t.join();
 }
 
-// The count tensor of a run, in the 16-bit wire format (half the pinned memory and PCIe traffic of uint32): the few
-// records with a count of 65534 or more are escaped into `wide`, sorted by (slot, sample).
+// The count tensor of a run in a wire format (a quarter / half of the pinned memory and PCIe traffic of uint32).  The
+// loader writes the packed format (8 bytes per record); when more than 1 record in 16 would have to be escaped
+// (ultra-deep or very noisy data) the files are parsed again into the 16-bit format.  Escaped records are in `wide`,
+// sorted by (slot, sample).  AS_WIRE=16 / AS_WIRE=packed in the environment forces one of the two.
 struct HostCounts {
-    uint16_t* p = nullptr;
+    void* p = nullptr;
+    int fmt = 1;  // 1 packed, 2 uint16
     std::vector<as_wide_record> wide;
     ~HostCounts() { if (p) as_host_free(p); }
     // the eight counts of (sample, slot); P = slots of the panel
     void record(int64_t sample, int64_t slot, int64_t P, uint32_t (&fw)[4], uint32_t (&bw)[4]) const {
-        const uint16_t* f = p + ((sample * 2) * P + slot) * 4;
-        const uint16_t* b = f + P * 4;
-        if (f[0] == AS_WIRE_ESCAPE) {
+        const int64_t wf = (sample * 2) * P + slot, wb = wf + P;
+        bool escaped;
+        if (fmt == 2) {
+            const uint16_t* f = (const uint16_t*)p + wf * 4;
+            const uint16_t* b = (const uint16_t*)p + wb * 4;
+            escaped = f[0] == AS_WIRE_ESCAPE;
+            for (int i = 0; i < 4; ++i) { fw[i] = f[i]; bw[i] = b[i]; }
+        } else {
+            const uint32_t* w = (const uint32_t*)p;
+            escaped = w[wf] == AS_PACKED_ESCAPE;
+            as_unpack_word(w[wf], fw);
+            as_unpack_word(w[wb], bw);
+        }
+        if (escaped) {
             as_wide_record key;
             key.slot = (int32_t)slot;
             key.sample = (int32_t)sample;
@@ -385,20 +424,32 @@ struct HostCounts {
             });
             if (it != wide.end() && it->slot == slot && it->sample == sample) {
                 for (int i = 0; i < 4; ++i) { fw[i] = it->fw[i]; bw[i] = it->bw[i]; }
-                return;
             }
         }
-        for (int i = 0; i < 4; ++i) { fw[i] = f[i]; bw[i] = b[i]; }
     }
 };
 // returns 0 ok, 1 pinned allocation failed, 2 a file could not be opened
 int load_counts(const std::vector<CountFile>& files, const Panel& panel, HostCounts& hc, int32_t* row_of,
                 std::vector<AseqStats>& stats) {
-    const size_t words = (size_t)files.size() * 2 * (size_t)panel.size() * 4;
-    void* mem = nullptr;
-    if (as_host_alloc(&mem, std::max<size_t>(16, words * 2)) != AS_OK) return 1;
-    hc.p = (uint16_t*)mem;
-    if (!load_all<uint16_t>(files, panel, hc.p, row_of, stats)) return 2;
+    const size_t strand_words = (size_t)files.size() * 2 * (size_t)panel.size();
+    const char* force = getenv("AS_WIRE");
+    for (int fmt = (force && !strcmp(force, "16")) ? 2 : 1; fmt <= 2; ++fmt) {
+        void* mem = nullptr;
+        if (as_host_alloc(&mem, std::max<size_t>(16, strand_words * 4 * (size_t)fmt)) != AS_OK) return 1;
+        hc.p = mem;
+        hc.fmt = fmt;
+        const bool ok = fmt == 1 ? load_all<1>(files, panel, (uint32_t*)mem, row_of, stats)
+                                 : load_all<2>(files, panel, (uint16_t*)mem, row_of, stats);
+        if (!ok) return 2;
+        int64_t rows = 0, escaped = 0;
+        for (const AseqStats& s : stats) { rows += s.rows; escaped += (int64_t)s.wide.size(); }
+        if (fmt == 1 && escaped * 16 > rows && !(force && !strcmp(force, "packed"))) {  // too many: the 16-bit format is denser
+            as_host_free(mem);
+            hc.p = nullptr;
+            continue;
+        }
+        break;
+    }
     for (AseqStats& s : stats) {
         hc.wide.insert(hc.wide.end(), s.wide.begin(), s.wide.end());
         s.wide.clear();
@@ -777,9 +828,13 @@ int as_error_estimation_main(int argc, char** argv) {
     std::vector<uint32_t> count((size_t)P * 4), nrec((size_t)P);
     const int32_t* tn = panel.has_twins ? panel.twin_next.data() : nullptr;
     const int32_t* th = panel.has_twins ? panel.twin_head.data() : nullptr;
-    const int rc = as_noise_estimate_host16(ctx, counts.p, counts.wide.data(), (int64_t)counts.wide.size(), S, P, tn, th,
-                                            C_value_float, cut, thr.data(), germ_val.data(), germ_state.data(), count.data(),
-                                            nrec.data(), nullptr);
+    const int rc = counts.fmt == 2
+                       ? as_noise_estimate_host16(ctx, (const uint16_t*)counts.p, counts.wide.data(), (int64_t)counts.wide.size(),
+                                                  S, P, tn, th, C_value_float, cut, thr.data(), germ_val.data(),
+                                                  germ_state.data(), count.data(), nrec.data(), nullptr)
+                       : as_noise_estimate_host_packed(ctx, (const uint32_t*)counts.p, counts.wide.data(),
+                                                       (int64_t)counts.wide.size(), S, P, tn, th, C_value_float, cut, thr.data(),
+                                                       germ_val.data(), germ_state.data(), count.data(), nrec.data(), nullptr);
     as_destroy(ctx);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");
@@ -1001,8 +1056,12 @@ int as_variant_calling_main(int argc, char** argv) {
         int rc;
         for (;;) {
             calls.resize((size_t)cap);
-            rc = as_call_variants_host16(ctx, counts.p, counts.wide.data(), (int64_t)counts.wide.size(), T, P, ref_code.data(),
-                                         thr_view.data(), cut, calls.data(), cap, &n_calls);
+            rc = counts.fmt == 2
+                     ? as_call_variants_host16(ctx, (const uint16_t*)counts.p, counts.wide.data(), (int64_t)counts.wide.size(), T,
+                                               P, ref_code.data(), thr_view.data(), cut, calls.data(), cap, &n_calls)
+                     : as_call_variants_host_packed(ctx, (const uint32_t*)counts.p, counts.wide.data(),
+                                                    (int64_t)counts.wide.size(), T, P, ref_code.data(), thr_view.data(), cut,
+                                                    calls.data(), cap, &n_calls);
             if (rc != AS_EOVERFLOW) break;
             cap = n_calls;
         }

@@ -403,6 +403,27 @@ __global__ void widen16_kernel(const uint2* __restrict__ in, uint4* __restrict__
     out[i] = o;
 }
 
+// packed wire format (include/amplisolve_b200.h): one word per (sample, strand, slot) = 16-bit major count, its base
+// index, three 4-bit minor counts in ascending base order.  Escaped words become absent until patch_wide_kernel
+// overwrites them with the record from the side list.
+__global__ void unpack_kernel(const uint32_t* __restrict__ in, uint4* __restrict__ out, int64_t n_words) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint32_t w = in[i];
+    uint4 o;
+    if (w >= AS_PACKED_ESCAPE) {
+        o = make_uint4(AS_ABSENT, AS_ABSENT, AS_ABSENT, AS_ABSENT);
+    } else {
+        const uint32_t m = w & 0xFFFFu, j = (w >> 16) & 3u;
+        const uint32_t a = (w >> 18) & 15u, b = (w >> 22) & 15u, c = (w >> 26) & 15u;
+        o.x = j == 0 ? m : a;
+        o.y = j == 1 ? m : (j == 0 ? a : b);
+        o.z = j == 2 ? m : (j == 3 ? c : b);
+        o.w = j == 3 ? m : c;
+    }
+    out[i] = o;
+}
+
 // records whose counts do not fit 16 bits travel as as_wide_record; overwrite their (escaped) words in the tile
 __global__ void patch_wide_kernel(const as_wide_record* __restrict__ wide, int64_t m, uint4* __restrict__ tile, int64_t n,
                                   int64_t p0, int n_samples) {
@@ -1006,6 +1027,12 @@ cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_w
     if (n_words <= 0) return cudaSuccess;
     widen16_kernel<<<cdiv64(n_words, 256), 256, 0, st>>>(reinterpret_cast<const uint2*>(d_in), reinterpret_cast<uint4*>(d_out),
                                                         n_words);
+    return cudaGetLastError();
+}
+
+cudaError_t as_launch_unpack(const uint32_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st) {
+    if (n_words <= 0) return cudaSuccess;
+    unpack_kernel<<<cdiv64(n_words, 256), 256, 0, st>>>(d_in, reinterpret_cast<uint4*>(d_out), n_words);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@ cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int6
                                   uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
 cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
+cudaError_t as_launch_unpack(const uint32_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32_t* d_tile, int64_t n, int64_t p0,
                                  int n_samples, cudaStream_t st);
 cudaError_t as_launch_thr_view(const float* d_thr, float* d_view, int64_t n, cudaStream_t st);
@@ -34,6 +35,12 @@ int as_call_chunk(int T, int64_t n_slots);
 cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
                            const uint8_t* d_ref, const float* d_thr_view, uint32_t cut, as_call* d_calls, int64_t cap,
                            unsigned long long* d_n_calls, cudaStream_t st);
+// as_sort.cu: call list housekeeping of the _host caller pipeline
+cudaError_t as_launch_call_slot_offset(as_call* d_calls, const unsigned long long* d_n_prev, const unsigned long long* d_n_now,
+                                       int64_t cap, int32_t off, cudaStream_t st);
+size_t as_sort_calls_scratch_bytes(int64_t n);
+cudaError_t as_launch_sort_calls(const as_call* d_calls, int64_t n, as_call* d_sorted, void* d_scratch, size_t scratch_bytes,
+                                 cudaStream_t st);
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
                                    double* q, cudaStream_t st);
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);

@@ -52,7 +52,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-wide", action="store_true", help="keep the e2e host tensors in uint32 even when uint16 is lossless")
+    ap.add_argument("--e2e-format", choices=["packed", "16", "32"], default="packed",
+                    help="host layout of the e2e leg: the packed wire format (8 B/record), the 16-bit one (16 B) or uint32 (32 B)")
+    ap.add_argument("--e2e-wide", action="store_true", help="same as --e2e-format 32")
     ap.add_argument("--call-kernel", type=int, default=11, help="include/amplisolve_b200.h as_set_call_kernel")
     ap.add_argument("--noise-kernel", type=int, default=1, help="include/amplisolve_b200.h as_set_noise_kernel")
     return ap.parse_args()
@@ -436,6 +438,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, ctx, normals, tumours, ref, twin_next, twin_head, rank, world, barrier)
+        if e2e["slots_per_gpu"] == P and e2e["calls_per_step"] != found:   # same data through the host C ABI: same call set
+            raise RuntimeError(f"e2e leg found {e2e['calls_per_step']} calls, the device-resident step {found}")
 
     result = None
     if rank == 0:
@@ -510,25 +514,56 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
             raise RuntimeError(L.as_last_error().decode())
         return p
 
-    # host tensors: the uint16 wire format of the _host16 entry points (records with a count >= 65534 escaped into a side
-    # list of wide records: lossless), or uint32 with --e2e-wide
-    narrow = not args.e2e_wide
-    esz = 2 if narrow else 4
-    bn, bt = S * 2 * Pe * 4 * esz, T * 2 * Pe * 4 * esz
+    # host tensors: the packed wire format of the _host_packed entry points (8 bytes per record; records that do not fit
+    # escaped into a side list of wide records: lossless), the 16-bit wire format, or uint32
+    fmt = "32" if args.e2e_wide else args.e2e_format
+    narrow = fmt == "16"
+    packed = fmt == "packed"
+    word = {"packed": 4, "16": 8, "32": 16}[fmt]            # bytes per (sample, strand, slot)
+    bn, bt = S * 2 * Pe * word, T * 2 * Pe * word
     hp_n, hp_t = pinned(bn), pinned(bt)
     ctype, ndt = (C.c_uint16, np.int16) if narrow else (C.c_uint32, np.int32)
-    h_norm = np.ctypeslib.as_array(C.cast(hp_n, C.POINTER(ctype)), shape=(S, 2, Pe, 4))
-    h_tum = np.ctypeslib.as_array(C.cast(hp_t, C.POINTER(ctype)), shape=(T, 2, Pe, 4))
+    shp = (lambda n: (n, 2, Pe)) if packed else (lambda n: (n, 2, Pe, 4))
+    h_norm = np.ctypeslib.as_array(C.cast(hp_n, C.POINTER(ctype)), shape=shp(S))
+    h_tum = np.ctypeslib.as_array(C.cast(hp_t, C.POINTER(ctype)), shape=shp(T))
     from amplisolve_b200.api import WIDE_DTYPE
+    others = torch.tensor([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]], device=d_normals.device)
+
+    def pack_block(blk):
+        """torch statement of the packed wire format (api.to_wire_packed) for one block of samples, on the device"""
+        v = blk.to(torch.int64) & 0xFFFFFFFF
+        m, j = v[..., 0], torch.zeros_like(v[..., 0])
+        for b in (1, 2, 3):                                  # first maximum: ties go to the lowest base index
+            gt = v[..., b] > m
+            j = torch.where(gt, b, j)
+            m = torch.where(gt, v[..., b], m)
+        mi = torch.gather(v, -1, others[j])
+        fits = (m <= 0xFFFF) & (mi <= 15).all(-1)
+        w = m | (j << 16) | (mi[..., 0] << 18) | (mi[..., 1] << 22) | (mi[..., 2] << 26)
+        absent = blk[:, 0, :, 0] == -1
+        esc = ~absent & ~(fits[:, 0] & fits[:, 1])
+        w = torch.where(esc[:, None, :], 0xFFFFFFFE, w)
+        w = torch.where(absent[:, None, :], 0xFFFFFFFF, w)
+        return w.to(torch.int32), esc                        # int64 -> int32 keeps the low 32 bits
 
     def to_host(dst_np, src):
         """untimed: bring a slot prefix of a device tensor to the pinned host tensor (and its wide records)"""
         dst = torch.from_numpy(dst_np.view(ndt))
         wides = []
-        for s0 in range(0, src.shape[0], 50):      # in sample blocks: bounded temporaries on the device
-            blk = src[s0:s0 + 50, :, :Pe, :]
-            if not narrow:
-                dst[s0:s0 + 50].copy_(blk)
+        for s0 in range(0, src.shape[0], 20):      # in sample blocks: bounded temporaries on the device
+            blk = src[s0:s0 + 20, :, :Pe, :]
+            if fmt == "32":
+                dst[s0:s0 + 20].copy_(blk)
+                continue
+            if packed:
+                w32, esc = pack_block(blk)
+                smp, slot = esc.nonzero(as_tuple=True)
+                w = np.zeros(len(smp), dtype=WIDE_DTYPE)
+                w["sample"], w["slot"] = (smp + s0).cpu().numpy(), slot.cpu().numpy()
+                w["fw"], w["bw"] = blk[smp, 0, slot].cpu().numpy(), blk[smp, 1, slot].cpu().numpy()
+                wides.append(w)
+                dst[s0:s0 + 20].copy_(w32)
+                del w32, esc
                 continue
             present = blk[:, 0, :, 0] >= 0                                   # absent words are -1 as int32
             big = present & ((blk[:, 0] >= 0xFFFE).any(-1) | (blk[:, 1] >= 0xFFFE).any(-1))
@@ -539,11 +574,20 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
             wides.append(w)
             n16 = blk.to(torch.int16)
             n16[smp, :, slot, :] = -2                                        # 0xFFFE: escaped
-            dst[s0:s0 + 50].copy_(n16)
+            dst[s0:s0 + 20].copy_(n16)
         return np.sort(np.concatenate(wides), order=["slot", "sample"]) if wides else np.zeros(0, WIDE_DTYPE)
 
-    w_norm = to_host(h_norm, d_normals)
-    w_tum = to_host(h_tum, d_tumours)
+    def pinned_copy(w):
+        """the side lists live in pinned memory like the count tensors (the C ABI accepts pageable lists too, slower)"""
+        if len(w) == 0:
+            return w, None
+        hp = pinned(w.nbytes)
+        dst = np.frombuffer((C.c_char * w.nbytes).from_address(hp.value), dtype=WIDE_DTYPE)
+        dst[:] = w
+        return dst, hp
+
+    w_norm, hp_wn = pinned_copy(to_host(h_norm, d_normals))
+    w_tum, hp_wt = pinned_copy(to_host(h_tum, d_tumours))
     h_ref = d_ref[:Pe].cpu().numpy()
     h_tn = h_th = None
     if d_twin_next is not None:
@@ -555,9 +599,25 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
     stats = {}
 
     def one():
-        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th, wide_records=w_norm, with_view=True)
-        calls = ctx.call_variants(h_tum, h_ref, noise["thr_view"], cut, cap=cap, wide_records=w_tum)
+        ta = time.perf_counter()
+        noise = ctx.estimate_thresholds(h_norm, Cv, cut, h_tn, h_th, wide_records=w_norm, with_view=True, pinned_outputs=True)
+        tb = time.perf_counter()
+        calls = ctx.call_variants(h_tum, h_ref, noise["thr_view"], cut, cap=cap, wide_records=w_tum, pinned_outputs=True)
         stats["calls"] = len(calls)
+        stats["noise_ms"], stats["call_ms"] = (tb - ta) * 1e3, (time.perf_counter() - tb) * 1e3
+
+    # context for the e2e number: what a plain pinned host -> device copy achieves on this box
+    hb = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    db = torch.empty(1 << 30, dtype=torch.uint8, device=d_normals.device)
+    db.copy_(hb, non_blocking=True)
+    ec = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ec[0].record()
+    for _ in range(3):
+        db.copy_(hb, non_blocking=True)
+    ec[1].record()
+    torch.cuda.synchronize()
+    pcie_gbs = 3 * (1 << 30) / (ec[0].elapsed_time(ec[1]) * 1e-3) / 1e9
+    del hb, db
 
     one()  # warm-up (allocates the tile buffers)
     barrier()
@@ -571,13 +631,19 @@ def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, ra
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-    L.as_host_free(hp_n)
-    L.as_host_free(hp_t)
+    n_esc = len(w_norm) + len(w_tum)
+    del w_norm, w_tum
+    for hp in (hp_n, hp_t, hp_wn, hp_wt):
+        if hp is not None:
+            L.as_host_free(hp)
     return {"value": 6.0 * T * Pe * world / dt, "unit": "Poisson tests/s", "ms_per_step": dt * 1e3,
-            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + 40 * (len(w_norm) + len(w_tum))), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
-            "slots_per_gpu": Pe, "host_dtype": (f"uint16 wire format + {len(w_norm) + len(w_tum)} escaped wide records (lossless)" if narrow else "uint32"),
-            "api": ("as_noise_estimate_host16 + as_call_variants_host16" if narrow else
-                    "as_noise_estimate_host + as_call_variants_host") + ", pinned host count tensors",
+            "h2d_bytes_per_step": int(bn + bt + Pe * 33 + 40 * n_esc), "d2h_bytes_per_step": int(Pe * 72 + Pe * 32 + stats["calls"] * 48),
+            "slots_per_gpu": Pe, "calls_per_step": stats["calls"], "noise_call_ms": stats["noise_ms"], "caller_call_ms": stats["call_ms"], "pcie_h2d_gbs_measured": pcie_gbs,
+            "h2d_gbs_achieved": (bn + bt) / dt / 1e9,
+            "host_dtype": {"packed": f"packed wire format (8 B/record: 16-bit major + three 4-bit minor counts per strand) + {n_esc} escaped wide records ({n_esc / ((S + T) * Pe):.2e} of the records; lossless)",
+                           "16": f"uint16 wire format + {n_esc} escaped wide records (lossless)", "32": "uint32"}[fmt],
+            "api": {"packed": "as_noise_estimate_host_packed + as_call_variants_host_packed", "16": "as_noise_estimate_host16 + as_call_variants_host16",
+                    "32": "as_noise_estimate_host + as_call_variants_host"}[fmt] + ", pinned host count tensors",
             "timer": "host wall clock around the blocking C-ABI calls, max over ranks"}
 
 

@@ -130,6 +130,30 @@ int as_noise_estimate_host16(as_ctx* ctx, const uint16_t* counts, const as_wide_
                              int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut, float* thr,
                              float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view);
 
+/* The packed wire format of the _host_packed entry points: uint32 packed[sample][strand][slot], ONE word per
+ * (sample, strand, slot) = 8 bytes per record, a quarter of the uint32 layout.  A pileup row is one large count (the base
+ * the sample carries) and three small ones (sequencing errors), so the word holds
+ *     bits  0..15  the largest of the four counts ("major"; ties go to the lowest base index)
+ *     bits 16..17  the base index of the major
+ *     bits 18..21, 22..25, 26..29  the other three counts in ascending base order, each 0..15
+ *     bits 30..31  zero
+ * AS_PACKED_ABSENT in both strand words = no ASEQ row.  A record that does not fit (major > 65535 or another count > 15 on
+ * either strand: germline / somatic variants, very noisy positions, ultra-deep coverage) is ESCAPED -- AS_PACKED_ESCAPE in
+ * both words -- and travels in the side list of as_wide_record sorted by slot, exactly like the 16-bit format.  Lossless
+ * for every input; the tile is unpacked to the uint32 layout on the device, kernels and results are the same.  Panels
+ * where more than a few per cent of the records escape (e.g. 50,000x coverage) are better served by the 16-bit format. */
+#define AS_PACKED_ABSENT 0xFFFFFFFFu
+#define AS_PACKED_ESCAPE 0xFFFFFFFEu
+/* Host helper: uint32 counts[n_samples][2][P][4] -> packed[n_samples][2][P] + wide records (sorted by slot, then sample).
+ * *n_wide receives the number of escaped records; AS_EOVERFLOW when it exceeds wide_cap (call again with a larger list;
+ * packed is complete either way).  Multi-threaded over samples; no GPU needed. */
+int as_pack_counts(const uint32_t* counts, int32_t n_samples, int64_t P, uint32_t* packed, as_wide_record* wide,
+                   int64_t wide_cap, int64_t* n_wide);
+int as_noise_estimate_host_packed(as_ctx* ctx, const uint32_t* packed, const as_wide_record* wide, int64_t n_wide, int32_t S,
+                                  int64_t P, const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut,
+                                  float* thr, float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec,
+                                  float* thr_view);
+
 /* The noise table crosses to the caller as "%f" text (EE:1787 -> std::stof at VC:889-890) with
  * "-1_-1" replaced by "0.01_0.01" (EE:2680-2684).  This applies exactly that mapping to thr
  * [n] floats in place of the text round trip: NaN -> 0.01f, v -> strtof(sprintf("%f", v)). */
@@ -153,6 +177,10 @@ int as_call_variants_host(as_ctx* ctx, const uint32_t* counts, int32_t T, int64_
 int as_call_variants_host16(as_ctx* ctx, const uint16_t* counts, const as_wide_record* wide, int64_t n_wide, int32_t T,
                             int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls, int64_t cap,
                             int64_t* n_calls);
+
+int as_call_variants_host_packed(as_ctx* ctx, const uint32_t* packed, const as_wide_record* wide, int64_t n_wide, int32_t T,
+                                 int64_t P, const uint8_t* ref, const float* thr_view, int32_t cut, as_call* calls,
+                                 int64_t cap, int64_t* n_calls);
 
 /* Element-wise Poisson test on the device: p[i] = the double p-value of VC:3858-3866 and
  * q[i] = the Q score of VC:3868-3882 for (k[i], rd[i], err[i]).  Host pointers.  Used by the

@@ -297,6 +297,46 @@ def test_wire16_host_entry_points_equal_the_32_bit_ones(ctx):
             ctx.set_host_tile_slots(0)
 
 
+def test_packed_host_entry_points_equal_the_32_bit_ones(ctx):
+    """as_noise_estimate_host_packed / as_call_variants_host_packed: same kernels behind the 8-bytes-per-record PCIe
+    format (16-bit major count + three 4-bit minors per strand word); records that do not fit -- variants, noisy
+    positions, counts beyond 16 bits -- travel in the side list.  Escaped twin members that straddle an upload tile are
+    read back through the host-side decoder."""
+    from amplisolve_b200 import pack_counts
+    _, slots, pos_id, U = synth.make_panel(30, seed=61, overlap_frac=0.5)
+    P = len(slots)
+    normals, ref = synth.make_counts(13, P, depth=3000, seed=61, pos_id=pos_id, big_rate=0.01)
+    tumours, _ = synth.make_counts(10, P, depth=3000, seed=62, ref=ref, pos_id=pos_id, somatic_rate=0.02, big_rate=0.01)
+    tumours[3, :, 17, :] = [[900, 0, 1, 2], [65535, 15, 15, 15]]      # the largest record the packed word carries
+    tumours[4, :, 18, :] = [[3, 0, 800, 2], [15, 15, 65535, 15]]
+    tumours[5, :, 19, :] = [[16, 0, 900, 0], [1, 0, 900, 0]]          # a minor count of 16: escaped
+    tumours[6, :, 20, :] = [[0, 0, 0, 65536], [0, 0, 1, 900]]         # a major count beyond 16 bits: escaped
+    normals[5, :, 40, :] = [[7, 7, 7, 7], [900, 1, 1, 1]]             # all equal: the major is base 0
+    nxt, head = ctx_twins(pos_id)
+    pn, nw = pack_counts(normals)
+    pt, tw = pack_counts(tumours)
+    assert pn.shape == (13, 2, P) and len(nw) > 5 and len(tw) > 5
+    assert pt[3, 1, 17] < 0xFFFFFFFE and pt[4, 1, 18] < 0xFFFFFFFE and (pt[5, :, 19] == 0xFFFFFFFE).all() and (pt[6, :, 20] == 0xFFFFFFFE).all()
+    for tile in (0, 256):
+        ctx.set_host_tile_slots(tile)
+        try:
+            wide = ctx.estimate_thresholds(normals, 0.002, 100, nxt, head, with_view=True)
+            packed = ctx.estimate_thresholds(pn, 0.002, 100, nxt, head, wide_records=nw, with_view=True)
+            for k in wide:
+                assert np.array_equal(wide[k].view(np.uint8), packed[k].view(np.uint8)), k
+            a = ctx.call_variants(tumours, ref, wide["thr_view"], 100)
+            b = ctx.call_variants(pt, ref, wide["thr_view"], 100, wide_records=tw)
+            assert len(a) > 0 and a.tobytes() == b.tobytes()
+        finally:
+            ctx.set_host_tile_slots(0)
+    # an all-absent panel and an empty one
+    empty = np.full((3, 2, 130, 4), 0xFFFFFFFF, np.uint32)
+    pe, we = pack_counts(empty)
+    assert len(we) == 0 and (pe == 0xFFFFFFFF).all()
+    out = ctx.estimate_thresholds(pe, 0.002, 100)
+    assert (out["nrec"] == 0).all() and np.isnan(out["thr"]).all()
+
+
 def test_device_pipeline_matches_host_entry_points(ctx):
     """_dev entry points (inputs resident in HBM, torch tensors) == _host entry points, incl. slot ranges."""
     import torch

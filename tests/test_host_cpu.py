@@ -49,6 +49,51 @@ def test_hash_iteration_order_equals_libstdcxx_model():
     assert [n5[i][2:4] for i in hash_iteration_order(n5)] == ["N5", "N3", "N2", "N4", "N1"]
 
 
+def unpack_numpy(word):
+    """numpy decoder of the packed wire format (include/amplisolve_b200.h), independent of the library's."""
+    word = np.asarray(word, np.uint32)
+    m, j = word & 0xFFFF, (word >> 16) & 3
+    minors = np.stack([(word >> 18) & 15, (word >> 22) & 15, (word >> 26) & 15], -1)
+    out = np.empty(word.shape + (4,), np.uint32)
+    for b in range(4):
+        k = np.where(b < j, b, b - 1).clip(0, 2)                 # index among the minors of base b when b != j
+        out[..., b] = np.where(j == b, m, np.take_along_axis(minors, k[..., None], -1)[..., 0])
+    out[word >= 0xFFFFFFFE] = 0xFFFFFFFF
+    return out
+
+
+def test_packed_wire_format_is_lossless():
+    """as_pack_counts (the library's threaded encoder, host code) == the numpy statement of the format, and decoding the
+    words + patching the escaped records gives back the uint32 tensor bit for bit."""
+    from amplisolve_b200 import pack_counts, to_wire_packed
+    from tests import synth
+    rng = np.random.default_rng(8)
+    _, slots, pos_id, U = synth.make_panel(20, seed=8)
+    P = len(slots)
+    counts, _ = synth.make_counts(9, P, depth=3000, seed=8, pos_id=pos_id, big_rate=0.02, somatic_rate=0.02)
+    edge = np.array([[65535, 15, 15, 15], [15, 65535, 15, 15], [0, 0, 0, 0], [16, 16, 16, 16], [65536, 0, 0, 0], [1, 1, 1, 1],
+                     [0, 16, 0, 70000], [15, 15, 15, 15], [0x7FFFFFFF, 0, 0, 0]], np.uint32)
+    for i, e in enumerate(edge):
+        counts[i % 9, rng.integers(0, 2), 3 + i] = e
+    packed, wide = pack_counts(counts)
+    ref_packed, ref_wide = to_wire_packed(counts)
+    assert np.array_equal(packed, ref_packed) and wide.tobytes() == ref_wide.tobytes()
+    assert 0 < len(wide) < counts.shape[0] * P // 4
+    back = unpack_numpy(packed)
+    assert (back[wide["sample"], 0, wide["slot"]] == 0xFFFFFFFF).all()     # escaped words decode as absent until patched
+    back[wide["sample"], 0, wide["slot"]] = wide["fw"]
+    back[wide["sample"], 1, wide["slot"]] = wide["bw"]
+    assert np.array_equal(back, counts)
+    # capacity protocol: too small a list reports the count and AS_EOVERFLOW
+    import ctypes as C
+    from amplisolve_b200 import api
+    n = C.c_int64(0)
+    small = np.zeros(1, api.WIDE_DTYPE)
+    rc = api.lib().as_pack_counts(counts.ctypes.data_as(C.c_void_p), counts.shape[0], P, packed.ctypes.data_as(C.c_void_p),
+                                  small.ctypes.data_as(C.c_void_p), 1, C.byref(n))
+    assert rc == -5 and n.value == len(wide)
+
+
 def test_twin_links():
     from amplisolve_b200 import twin_links
     nxt, head = twin_links([0, 1, 2, 1, 3, 0, 1])

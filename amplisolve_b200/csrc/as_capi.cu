@@ -177,7 +177,7 @@ int as_host_free(void* p) {
 }
 
 int as_set_call_kernel(as_ctx* c, int variant) {
-    if (!c || variant < -1 || variant > 12) return fail(AS_EINVAL, "bad call kernel variant");
+    if (!c || variant < -1 || variant > 16) return fail(AS_EINVAL, "bad call kernel variant");
     c->call_variant = variant < 0 ? AS_DEFAULT_CALL_KERNEL : variant;
     return AS_OK;
 }

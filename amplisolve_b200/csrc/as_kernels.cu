@@ -719,8 +719,17 @@ __device__ __forceinline__ void stage2_batch_staged(const StagedCand* __restrict
 // candidates into 16-bit (record, lane, base) entries.  Full warps then revisit the candidates in the still
 // resident stage for the exact m >= k screen; survivors go to the per-warp queue of fp64 series evaluations
 // (two lanes per candidate, as in call_queued_kernel).
-template <int K, int STAGES>
-__global__ void __launch_bounds__(AS_CTA_THREADS)
+//
+// PRE (integer pre-screen in the scan): the thread keeps, for its slot and each strand, R = floor(e_min * 2^32) of the
+// SMALLEST threshold among the callable alt bases.  m_lo = umulhi(depth, R) <= depth * e_min <= depth * e_b (the real
+// product) for every alt base b, so k <= m_lo and m_lo >= 2 imply m = rn(depth * e_b) >= k (k is an integer, rounding is
+// monotone) and m > 1: exactly the condition under which strand_can_pass is false.  Such (record, base) pairs are dropped
+// in the scan -- the "alt reads > 0" test k > 0 simply becomes k > m_lo, at the price of one multiply per strand -- and
+// never become candidates; pairs between m_lo and their own base's m still do and meet the exact fp64 screen in the
+// revisit, so the call set is unchanged.  The candidate rate falls from 3 % (c3) / 15 % (c5 shape) of the pairs by an
+// order of magnitude or more.
+template <int K, int STAGES, bool PRE>
+__global__ void __launch_bounds__(AS_CTA_THREADS, PRE ? 7 : 1)
 call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
                    const uint8_t* __restrict__ ref, const float* __restrict__ thr_view, uint32_t cut,
                    as_call* __restrict__ calls, int64_t cap, unsigned long long* __restrict__ n_calls) {
@@ -743,9 +752,30 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     const int lane = tid & 31, warp = tid >> 5;
     const int64_t p = tile0 + tid;
     uint32_t notref = 0;
+    uint32_t Rf = 0, Rb = 0;  // PRE: floor(e_min * 2^32) per strand; 0 never screens anything out
     if (tid < n_slots) {
         const uint32_t r = ref[p];
         if (r <= 3) notref = 0xfu & ~(1u << r);
+        if (PRE && r <= 3) {
+            const float4 a = *reinterpret_cast<const float4*>(thr_view + p * 8);
+            const float4 b = *reinterpret_cast<const float4*>(thr_view + p * 8 + 4);
+            const float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            Rf = Rb = 0xFFFFFFFFu;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if ((uint32_t)i == r) continue;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const float raw = e[2 * i + s];
+                    if (raw == -1.0f) continue;  // no threshold: never a call (VC:3844-3849), puts no bound on the minimum
+                    const float ee = effective_err(raw);
+                    // e * 2^32 is exact (power-of-two scaling) and < 2^32 for e < 1; anything else (negative, NaN,
+                    // e >= 1) switches the pre-screen off for the strand: the exact test decides
+                    const uint32_t R = (ee > 0.0f && ee < 1.0f) ? __float2uint_rz(ee * 4294967296.0f) : 0u;
+                    if (s == 0) Rf = min(Rf, R); else Rb = min(Rb, R);
+                }
+            }
+        }
     }
     uint16_t* cand = cand_all[warp];
     StagedCand* q2 = q2_all[warp];
@@ -766,8 +796,18 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                 const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid];
                 const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid];
                 const uint32_t FW = fw.x + fw.y + fw.z + fw.w, BW = bw.x + bw.y + bw.z + bw.w;
-                const uint32_t m = ((min(fw.x, bw.x) != 0) ? 1u : 0u) | ((min(fw.y, bw.y) != 0) ? 2u : 0u) |
-                                   ((min(fw.z, bw.z) != 0) ? 4u : 0u) | ((min(fw.w, bw.w) != 0) ? 8u : 0u);
+                uint32_t m;
+                if (PRE) {
+                    // a strand test with k <= m_lo (and m_lo >= 2) cannot pass; m_lo = 0 leaves the plain k > 0 test
+                    uint32_t mf = __umulhi(FW, Rf), mb = __umulhi(BW, Rb);
+                    mf = mf >= 2u ? mf : 0u;
+                    mb = mb >= 2u ? mb : 0u;
+                    m = ((fw.x > mf && bw.x > mb) ? 1u : 0u) | ((fw.y > mf && bw.y > mb) ? 2u : 0u) |
+                        ((fw.z > mf && bw.z > mb) ? 4u : 0u) | ((fw.w > mf && bw.w > mb) ? 8u : 0u);
+                } else {
+                    m = ((min(fw.x, bw.x) != 0) ? 1u : 0u) | ((min(fw.y, bw.y) != 0) ? 2u : 0u) |
+                        ((min(fw.z, bw.z) != 0) ? 4u : 0u) | ((min(fw.w, bw.w) != 0) ? 8u : 0u);
+                }
                 const bool ok = (int32_t)fw.x >= 0 && min(FW, BW) >= cut;
                 mask |= (ok ? m : 0u) << (4 * j);
             }
@@ -1062,7 +1102,7 @@ int as_call_chunk(int T, int64_t n_slots) {
     return (int)(chunk < 1 ? 1 : chunk);
 }
 
-template <int K, int STAGES>
+template <int K, int STAGES, bool PRE = false>
 static cudaError_t launch_call_staged(dim3 grid, const uint4* c, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
                                       const uint8_t* ref, const float* tv, uint32_t cut, as_call* calls, int64_t cap,
                                       unsigned long long* n, cudaStream_t st) {
@@ -1071,11 +1111,11 @@ static cudaError_t launch_call_staged(dim3 grid, const uint4* c, int T, int64_t 
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(call_staged_kernel<K, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(call_staged_kernel<K, STAGES, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
     }
-    call_staged_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(c, T, P, p0, p1, chunk, ref, tv, cut, calls, cap, n);
+    call_staged_kernel<K, STAGES, PRE><<<grid, AS_CTA_THREADS, smem, st>>>(c, T, P, p0, p1, chunk, ref, tv, cut, calls, cap, n);
     return cudaGetLastError();
 }
 
@@ -1100,6 +1140,10 @@ cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t
         case 10: return launch_call_staged<3, 3>(grid, AS_CALL_ARGS, st);
         case 11: return launch_call_staged<3, 2>(grid, AS_CALL_ARGS, st);
         case 12: return launch_call_staged<6, 2>(grid, AS_CALL_ARGS, st);
+        case 13: return launch_call_staged<3, 2, true>(grid, AS_CALL_ARGS, st);
+        case 14: return launch_call_staged<4, 2, true>(grid, AS_CALL_ARGS, st);
+        case 15: return launch_call_staged<2, 2, true>(grid, AS_CALL_ARGS, st);
+        case 16: return launch_call_staged<4, 3, true>(grid, AS_CALL_ARGS, st);
         default: return launch_call_staged<4, 3>(grid, AS_CALL_ARGS, st);
     }
 #undef AS_CALL_ARGS

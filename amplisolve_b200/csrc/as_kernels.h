@@ -15,7 +15,7 @@
  * thread scans its own rows, the two states are merged exactly after the sample loop (as_noise.cuh pair_merge).
  * 0: every twin group goes to noise_pair_kernel / noise_twin_kernel. */
 #define AS_INTILE_TWINS 1
-#define AS_DEFAULT_CALL_KERNEL 11 /* TMA-staged, 3 samples per stage, 2 stages (7 CTAs/SM): best of the measured sweeps */
+#define AS_DEFAULT_CALL_KERNEL 13 /* TMA-staged, 3 samples per stage, 2 stages (7 CTAs/SM), integer pre-screen in the scan: best of the measured sweeps on the c3 and the c5 shape */
 #define AS_DEFAULT_NOISE_KERNEL 1 /* TMA-staged, 4 samples per stage, 3 stages */
 
 cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,

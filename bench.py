@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--e2e-format", choices=["packed", "16", "32"], default="packed",
                     help="host layout of the e2e leg: the packed wire format (8 B/record), the 16-bit one (16 B) or uint32 (32 B)")
     ap.add_argument("--e2e-wide", action="store_true", help="same as --e2e-format 32")
-    ap.add_argument("--call-kernel", type=int, default=11, help="include/amplisolve_b200.h as_set_call_kernel")
+    ap.add_argument("--call-kernel", type=int, default=13, help="include/amplisolve_b200.h as_set_call_kernel")
     ap.add_argument("--noise-kernel", type=int, default=1, help="include/amplisolve_b200.h as_set_noise_kernel")
     return ap.parse_args()
 
@@ -468,7 +468,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": {0: "call_naive_kernel", 1: "call_queued_kernel"}.get(args.call_kernel, "call_staged_kernel"),
                          "achieved": call_bytes / (t_call * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak,
-                         "traffic": ncu_traffic("call_staged_kernel", default_wl and args.call_kernel == 11), "peak_source": peak_src,
+                         "traffic": ncu_traffic("call_staged_kernel", default_wl and args.call_kernel == 13), "peak_source": peak_src,
                          "algorithmic_bytes": call_bytes},
             "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel" if args.noise_kernel == 0 else "noise_staged_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": noise_bytes / (t_noise * 1e-3) / 1e9 / peak,

@@ -80,7 +80,8 @@ int as_host_alloc(void** out, size_t bytes);
 int as_host_free(void* p);
 /* Kernel variants (the tests cross-check them against each other and the oracle; -1 = default):
  *   caller: 0 = straightforward, 1 = per-warp queues over direct loads, 2..12 = TMA-staged with
- *           (samples per stage, stages) = (4,3), (4,2), (4,4), (8,2), (8,3), (2,2), (2,3), (2,4), (3,3), (3,2) default, (6,2)
+ *           (samples per stage, stages) = (4,3), (4,2), (4,4), (8,2), (8,3), (2,2), (2,3), (2,4), (3,3), (3,2), (6,2)
+ *           13..16 = TMA-staged with the integer pre-screen in the scan: (3,2) default, (4,2), (2,2), (4,3)
  *   noise : 0 = direct loads, 1..6 = TMA-staged with (4,3) default, (4,4), (2,4), (8,2), (8,3), (4,2) */
 int as_set_call_kernel(as_ctx* ctx, int variant);
 int as_set_noise_kernel(as_ctx* ctx, int variant);

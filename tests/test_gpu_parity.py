@@ -206,7 +206,7 @@ def check_calls(got, want, rows_slot):
         assert np.allclose(got["q_" + side], want["q_" + side], rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("variant", [11, 3, 2, 1, 0, 5, 7])
+@pytest.mark.parametrize("variant", [11, 13, 3, 2, 1, 0, 5, 7, 14, 15, 16])
 @pytest.mark.parametrize("T,n_amp,depth,cut,seed", [
     (3, 30, 1800, 100, 21),
     (24, 16, 5000, 100, 22),
@@ -239,6 +239,48 @@ def test_calls_match_oracle(ctx, variant, T, n_amp, depth, cut, seed):
     rows_slot = [np.nonzero(present[s])[0] for s in range(T)]
     assert len(want) > 0
     check_calls(got, want, rows_slot)
+
+
+@pytest.mark.parametrize("variant", [13, 14, 11])
+def test_integer_prescreen_boundaries(ctx, variant):
+    """The integer pre-screen of the staged caller (umulhi(depth, floor(e * 2^32)) >= max(k, 2) drops the pair in the
+    scan) must never drop a pair the exact screen m = rn(depth * e) >= k && m > 1 of VC:3728 keeps.  Records sit on and
+    around the boundary k = depth * e for thresholds where the product is an exact integer (e = 2^-9, 2^-7), where it is
+    not (0.002, 0.0010008 through err == 0), for m <= 1 (tiny e), for e = -1 and for e close to 1; the call set has to
+    equal the straightforward kernel's (variant 0, no screens at all) and the oracle's."""
+    rng = np.random.default_rng(77)
+    es = np.array([2.0 ** -9, 2.0 ** -7, 0.002, 0.0, 0.01, 1e-6, 3e-4, -1.0, 0.05, 0.999], np.float32)
+    P, T = 640, 40
+    ref = rng.integers(0, 4, P).astype(np.uint8)
+    thr = np.empty((P, 4, 2), np.float32)
+    thr[:, :, 0] = es[rng.integers(0, len(es), (P, 4))]
+    thr[:, :, 1] = np.where(rng.random((P, 4)) < 0.7, thr[:, :, 0], es[rng.integers(0, len(es), (P, 4))])
+    same = rng.random(P) < 0.4      # one threshold for the whole slot: the pre-screen's bound (the smallest threshold of the
+    thr[same] = es[rng.integers(0, len(es), same.sum())][:, None, None]   # strand) then coincides with every base's own
+    tumours = np.zeros((T, 2, P, 4), np.uint32)
+    depth = (rng.choice([512, 1024, 2048, 3000, 5000, 65536, 100000, 1 << 20], (T, 2, P)) * rng.integers(1, 4, (T, 2, P))).astype(np.int64)
+    for st in (0, 1):
+        for b in range(4):
+            e = np.where(thr[:, b, st] == 0, np.float32(0.0010008), thr[:, b, st]).astype(np.float64)
+            m = depth[:, st] * np.maximum(e, 0)[None, :]
+            k = np.floor(m).astype(np.int64) + rng.integers(-2, 4, (T, P))        # on and around the boundary
+            k = np.where(rng.random((T, P)) < 0.15, rng.integers(0, 4, (T, P)), k)  # and tiny counts (m <= 1 region)
+            tumours[:, st, :, b] = np.clip(k, 0, depth[:, st] // 8)
+    for st in (0, 1):   # the reference base takes the rest of the depth
+        rest = depth[:, st] - tumours[:, st].sum(-1) + tumours[:, st, np.arange(P), ref]
+        tumours[:, st, np.arange(P), ref] = np.maximum(rest, 0)
+    pos_id = np.arange(P, dtype=np.int32)
+    ctx.set_call_kernel(0)
+    try:
+        plain = ctx.call_variants(tumours, ref, thr, 100)
+        ctx.set_call_kernel(variant)
+        got = ctx.call_variants(tumours, ref, thr, 100)
+    finally:
+        ctx.set_call_kernel(-1)
+    assert len(plain) > 500
+    assert plain.tobytes() == got.tobytes()
+    want, _, _ = oracle_calls(tumours, pos_id, P, ref, thr, 100)
+    check_calls(got, want, [np.arange(P) for _ in range(T)])
 
 
 @pytest.mark.parametrize("tile", [128, 512, 1024])

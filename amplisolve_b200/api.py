@@ -30,7 +30,7 @@ EXPORTS = [
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
     "as_call_variants_host16", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
-    "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_error_estimation_main",
+    "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
 
@@ -161,6 +161,7 @@ def lib():
     L.as_synth_counts_dev.argtypes = [vp, vp, i32, i64, vp, C.POINTER(SynthParams), vp]
     L.as_synth_twin_links_dev.argtypes = [vp, i64, C.POINTER(SynthParams), vp, vp, vp]
     L.as_hash_iteration_order.argtypes = [C.POINTER(C.c_char_p), i32, vp]
+    L.as_fisher_tests_host.argtypes = [vp, vp, i64, vp]
     L.as_fisher_test.restype = C.c_double
     L.as_fisher_test.argtypes = [i32, i32, i32, i32]
     for name in ("as_error_estimation_main", "as_variant_calling_main"):
@@ -349,6 +350,13 @@ class Context:
         p, q = np.empty(k.shape, np.float64), np.empty(k.shape, np.float64)
         _check(lib().as_poisson_test_host(self._h, _hp(k), _hp(rd), _hp(err), k.size, _hp(p), _hp(q)))
         return p, q
+
+    def fisher_tests(self, tables):
+        """tables [n][4] = (FW, BW, alt_fw, alt_bw) -> p [n]: fisherTest of VC:3797-3814 for every row, on the device."""
+        tables = _np(tables, np.int32).reshape(-1, 4)
+        p = np.empty(len(tables), np.float64)
+        _check(lib().as_fisher_tests_host(self._h, _hp(tables), len(tables), _hp(p)))
+        return p
 
     def kf_gammaq(self, s, z):
         s, z = _np(s, np.float64), _np(z, np.float64)

@@ -18,7 +18,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libamplisolve_b200.so"
 BIN = PKG / "bin"
-CU_SOURCES = ["as_kernels.cu", "as_capi.cu", "as_sort.cu"]
+CU_SOURCES = ["as_kernels.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu"]
 CXX_SOURCES = ["as_host.cpp"]
 HEADERS = ["as_device.cuh", "as_noise.cuh", "as_pipeline.cuh", "as_kernels.h", "as_wire.h", "../../include/amplisolve_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

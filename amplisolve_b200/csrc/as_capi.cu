@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <ctime>
 #include <cstdlib>
@@ -95,6 +96,8 @@ struct as_ctx {
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
     DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls, sortbuf;  // _host pipelines
+    DevBuf lgtab;                                                              // lgamma(i + 1), i < lg_n (as_fisher_tests_host)
+    int64_t lg_n = 0;
     PinnedGrow h_links, h_small;                                              // _host pipelines, host side
 };
 
@@ -152,7 +155,7 @@ void as_destroy(as_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release(); c->sortbuf.release();
-    c->h_links.release(); c->h_small.release();
+    c->h_links.release(); c->h_small.release(); c->lgtab.release();
     for (int i = 0; i < 2; ++i) {
         c->tile[i].release(); c->tile16[i].release(); c->wide[i].release(); c->out[i].release(); c->aux[i].release();
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
@@ -773,6 +776,63 @@ int as_poisson_test_host(as_ctx* c, const int32_t* k, const int32_t* rd, const f
     CU(cudaMemcpyAsync(p, d_p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(q, d_q, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return AS_OK;
+}
+
+// Fisher strand-bias tests of n calls (VC:902, VC:3797-3814) on the device; see include/amplisolve_b200.h
+extern "C" double as_fisher_test(int32_t fw, int32_t bw, int32_t alt_fw, int32_t alt_bw);  // as_host.cpp
+int as_fisher_tests_host(as_ctx* c, const int32_t* tables, int64_t n, double* p) {
+    if (!c || n < 0 || (n > 0 && (!tables || !p))) return fail(AS_EINVAL, "bad argument");
+    if (n == 0) return AS_OK;
+    PhaseClock clk;
+    const int64_t LG_CAP = (int64_t)1 << 26;
+    int64_t max_N = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t* t = tables + i * 4;
+        if (t[0] < 0 || t[1] < 0 || t[2] < 0 || t[3] < 0) return fail(AS_EINVAL, "table %lld has a negative count", (long long)i);
+        const int64_t N = (int64_t)t[0] + t[1] + t[2] + t[3];
+        if (N <= LG_CAP) max_N = std::max(max_N, N);
+    }
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->exec_stream;
+    if (max_N + 2 > c->lg_n) {  // extend the table: the host's own lgamma, a few threads
+        const int64_t want = max_N + 2;
+        std::vector<double> lg((size_t)want);
+        const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 16u), want / 4096));
+        auto work = [&](int k) {
+            for (int64_t i = want * k / nth, e = want * (k + 1) / nth; i < e; ++i) {
+                int sign = 0;
+                lg[(size_t)i] = lgamma_r((double)i + 1.0, &sign);
+            }
+        };
+        std::vector<std::thread> th;
+        for (int k = 1; k < nth; ++k) th.emplace_back(work, k);
+        work(0);
+        for (auto& x : th) x.join();
+        CU(c->lgtab.need((size_t)want * 8));
+        CU(cudaMemcpy(c->lgtab.p, lg.data(), (size_t)want * 8, cudaMemcpyHostToDevice));
+        c->lg_n = want;
+    }
+    clk.lap("fisher.lgamma_table");
+    CU(c->misc.need((size_t)n * 24 + 64));
+    int32_t* d_t = (int32_t*)c->misc.p;
+    double* d_p = (double*)((char*)c->misc.p + (((size_t)n * 16 + 63) & ~(size_t)63));
+    CU(cudaMemcpyAsync(d_t, tables, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    std::vector<int64_t> on_host;  // tables beyond the lgamma table
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t* t = tables + i * 4;
+        if ((int64_t)t[0] + t[1] + t[2] + t[3] > LG_CAP) on_host.push_back(i);
+    }
+    if (!on_host.empty()) {  // the kernel must not index past the table: give those warps an empty table
+        std::vector<int32_t> zero(4, 0);
+        for (int64_t i : on_host) CU(cudaMemcpyAsync(d_t + i * 4, zero.data(), 16, cudaMemcpyHostToDevice, st));
+    }
+    CU(as_launch_fisher(d_t, n, (const double*)c->lgtab.p, d_p, st));
+    c->launches += 1;
+    CU(cudaMemcpyAsync(p, d_p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int64_t i : on_host) p[i] = as_fisher_test(tables[i * 4], tables[i * 4 + 1], tables[i * 4 + 2], tables[i * 4 + 3]);
+    clk.lap("fisher.device");
     return AS_OK;
 }
 

@@ -510,29 +510,13 @@ struct PhaseTimer {
 // ---------------------------------------------------------------------------------------------------
 // two-sided Fisher exact test as VC:3797-3814.  Boost.Math 1.61 is not part of the reference tree
 // (.MISSING_LARGE_BLOBS); the pdf is C(r,k) C(N-r,n-k) / C(N,n) through lgamma, like the oracle's stand-in.
-// lgamma(i + 1) for small integers is looked up (same function values, so bit-identical to calling lgamma each time;
-// a germline call at depth 5000 otherwise costs ~45,000 lgamma evaluations).
-struct LgTable {
-    std::vector<double> v;
-    void build(size_t n_max) {
-        if (n_max + 2 <= v.size()) return;
-        const size_t old = v.size();
-        v.resize(n_max + 2);
-        parallel_for(v.size() - old, [&](size_t i) {
-            int sign = 0;
-            v[old + i] = lgamma_r((double)(old + i) + 1.0, &sign);
-        });
-    }
-    double operator()(double x) const {  // lgamma(x + 1) for a non-negative integer-valued x
-        const size_t i = (size_t)x;
-        if (i < v.size()) return v[i];
-        int sign = 0;
-        return lgamma_r(x + 1.0, &sign);
-    }
-};
-LgTable g_lg;
-
-double log_choose(double n, double k) { return g_lg(n) - g_lg(k) - g_lg(n - k); }
+// This scalar form backs as_fisher_test (the checker the Boost pin runs against); the programs evaluate all calls at once
+// on the device (as_fisher_tests_host, as_fisher.cu) from the same lgamma values.
+inline double lg1(double x) {  // lgamma(x + 1)
+    int sign = 0;
+    return lgamma_r(x + 1.0, &sign);
+}
+double log_choose(double n, double k) { return lg1(n) - lg1(k) - lg1(n - k); }
 double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {
     return exp(log_choose(r, k) + log_choose((double)N - r, (double)n - k) - log_choose(N, n));
 }
@@ -1075,29 +1059,27 @@ int as_variant_calling_main(int argc, char** argv) {
             return a.alt < b.alt;
         });
     }
-    as_destroy(ctx);
     timer.lap("caller_gpu", 6.0 * (double)T * (double)P, "tests");
 
-    // Fisher strand-bias p of every call (VC:902), in parallel: independent per call, deterministic
+    // Fisher strand-bias p of every call (VC:902) on the device: one warp per call's 2x2 table
     // the eight strand counts of a call's record
     auto record = [&](const as_call& c, uint32_t (&fw)[4], uint32_t (&bw)[4]) { counts.record(c.sample, c.slot, P, fw, bw); };
     std::vector<double> fisher_p(calls.size());
     {
-        size_t max_depth = 0;
-        for (const as_call& c : calls) {
+        std::vector<int32_t> tables(calls.size() * 4);
+        parallel_for(calls.size(), [&](size_t i) {
+            const as_call& c = calls[i];
             uint32_t fw[4], bw[4];
             record(c, fw, bw);
-            max_depth = std::max<size_t>(max_depth, (size_t)fw[0] + fw[1] + fw[2] + fw[3] + bw[0] + bw[1] + bw[2] + bw[3]);
-        }
-        g_lg.build(std::min<size_t>(max_depth, (size_t)1 << 26));
+            tables[i * 4 + 0] = (int32_t)(fw[0] + fw[1] + fw[2] + fw[3]);  // fisherTest(FW, BW, alt_fw, alt_bw)
+            tables[i * 4 + 1] = (int32_t)(bw[0] + bw[1] + bw[2] + bw[3]);
+            tables[i * 4 + 2] = (int32_t)fw[c.alt];
+            tables[i * 4 + 3] = (int32_t)bw[c.alt];
+        });
+        const int frc = as_fisher_tests_host(ctx, tables.data(), (int64_t)calls.size(), fisher_p.data());
+        as_destroy(ctx);
+        if (frc != AS_OK) return report_gpu_error("as_fisher_tests_host");
     }
-    parallel_for(calls.size(), [&](size_t i) {
-        const as_call& c = calls[i];
-        uint32_t fw[4], bw[4];
-        record(c, fw, bw);
-        fisher_p[i] = fisher_test((int)(fw[0] + fw[1] + fw[2] + fw[3]), (int)(bw[0] + bw[1] + bw[2] + bw[3]), (int)fw[c.alt],
-                                  (int)bw[c.alt]);
-    });
     timer.lap("fisher_tests", (double)calls.size(), "calls");
 
     // ---- writers (VC:662-688, VC:1040-1066)

@@ -41,6 +41,8 @@ cudaError_t as_launch_call_slot_offset(as_call* d_calls, const unsigned long lon
 size_t as_sort_calls_scratch_bytes(int64_t n);
 cudaError_t as_launch_sort_calls(const as_call* d_calls, int64_t n, as_call* d_sorted, void* d_scratch, size_t scratch_bytes,
                                  cudaStream_t st);
+// as_fisher.cu: Fisher strand-bias tests, one warp per table {FW, BW, alt_fw, alt_bw}; d_lg[i] = lgamma(i + 1)
+cudaError_t as_launch_fisher(const int32_t* d_tables, int64_t n, const double* d_lg, double* d_p, cudaStream_t st);
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
                                    double* q, cudaStream_t st);
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);

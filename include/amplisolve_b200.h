@@ -228,6 +228,14 @@ int as_hash_iteration_order(const char* const* keys, int32_t n, int32_t* order_o
  * GPU needed.  Returns -1 for a negative argument. */
 double as_fisher_test(int32_t fw, int32_t bw, int32_t alt_fw, int32_t alt_bw);
 
+/* The same test for n tables at once on the device: tables [n][4] = {fw, bw, alt_fw, alt_bw}, p [n].
+ * One warp per table, lanes over the support of the hypergeometric distribution; the log-domain terms come from a
+ * lgamma table filled by the host (bit-identical to as_fisher_test), exp is the device's, the partial sums of the 32
+ * lanes are added in ascending k: p agrees with as_fisher_test to a few ulp (tests: <= 1e-13 relative, identical
+ * printed strings and YES/NO flags).  Tables whose N = fw + bw + alt_fw + alt_bw exceeds 2^26 are evaluated on the host.
+ * Host pointers.  as_variant_calling_main uses this for the FisherPvalue column. */
+int as_fisher_tests_host(as_ctx* ctx, const int32_t* tables, int64_t n, double* p);
+
 /* Whole programs, argv-compatible with the reference (EE:241-520, VC:199-360).  Exit status is
  * the return value; like the reference, usage errors print the usage text and return 0. */
 int as_error_estimation_main(int argc, char** argv);

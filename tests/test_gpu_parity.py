@@ -379,6 +379,34 @@ def test_packed_host_entry_points_equal_the_32_bit_ones(ctx):
     assert (out["nrec"] == 0).all() and np.isnan(out["thr"]).all()
 
 
+def test_device_fisher_equals_host_and_boost(ctx):
+    """as_fisher_tests_host (one warp per 2x2 table) against the scalar host form as_fisher_test and the
+    Boost.Math-pinned fixture: p within 1e-13 relative of the host's (same lgamma values, device exp, lane-ordered sum),
+    identical FisherPvalue strings at the two precisions the reference prints, identical YES/NO flags."""
+    from amplisolve_b200 import fisher_test
+    from tests import golden_util as gu
+    g = np.load(gu.GOLDEN / "fisher_boost.npz")
+    tables = np.stack([g["fw"], g["bw"], g["alt_fw"], g["alt_bw"]], 1).astype(np.int32)
+    extra = np.array([[0, 0, 0, 0], [1, 0, 0, 0], [5, 5, 5, 5], [100, 100, 0, 0], [100, 0, 0, 100], [3, 2000, 3, 0],
+                      [70000, 70000, 35000, 35001]], np.int32)
+    tables = np.concatenate([tables, extra])
+    got = ctx.fisher_tests(tables)
+    host = np.array([fisher_test(*t) for t in tables.tolist()])
+    normal = host > 1e-290
+    assert np.all(np.abs(got - host)[normal] <= 1e-13 * host[normal])
+    assert np.all(got[~normal] < 1e-290)
+    for digits in (6, 4):
+        assert [gu.fmt_g(x, digits) for x in got[normal]] == [gu.fmt_g(x, digits) for x in host[normal]]
+    boost = g["p_boost"]
+    nb = len(boost)
+    okb = boost > 1e-300
+    assert np.all(np.abs(got[:nb] - boost)[okb] <= 2e-9 * boost[okb])
+    for p_value in (np.float32(0.05), np.float32(0.01)):
+        assert np.array_equal(got <= p_value, host <= p_value)
+        assert np.array_equal(got[:nb] <= p_value, boost <= p_value)
+    assert ctx.fisher_tests(np.zeros((0, 4), np.int32)).shape == (0,)
+
+
 def test_device_pipeline_matches_host_entry_points(ctx):
     """_dev entry points (inputs resident in HBM, torch tensors) == _host entry points, incl. slot ranges."""
     import torch

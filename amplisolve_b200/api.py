@@ -29,7 +29,7 @@ EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
-    "as_call_variants_host16", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
+    "as_call_variants_host16", "as_call_variants_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
@@ -151,6 +151,7 @@ def lib():
     L.as_noise_estimate_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     L.as_thresholds_caller_view_dev.argtypes = [vp, vp, vp, i64, vp]
     L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
+    L.as_call_variants_sweep_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, i32, vp, i64, vp, vp]
     L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.as_call_variants_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.as_noise_estimate_host_packed.argtypes = L.as_noise_estimate_host16.argtypes
@@ -404,6 +405,18 @@ class Context:
         cap = calls.numel() * calls.element_size() // CALL_DTYPE.itemsize
         _check(lib().as_call_variants_dev(self._h, _dp(counts), T, P, b, e, _dp(ref), _dp(thr_view),
                                           int(coverage_cutoff), _dp(calls), cap, _dp(n_calls), self._stream(stream)))
+
+    def call_variants_sweep_dev(self, counts, ref, thr_views, coverage_cutoff, calls, n_calls, slot_range=None, stream=None):
+        """Noise-floor sweep: thr_views torch float32 [n_c][P][4][2]; calls torch uint8 CUDA tensor of n_c*cap*48 bytes
+        (list ci at [ci*cap, (ci+1)*cap)); n_calls torch int64 CUDA tensor [n_c] (added to).  One pass over counts."""
+        T, two, P, four = counts.shape
+        n_c = thr_views.shape[0]
+        assert thr_views.shape == (n_c, P, 4, 2) and thr_views.is_contiguous() and n_calls.numel() == n_c
+        b, e = slot_range if slot_range is not None else (0, P)
+        cap = calls.numel() * calls.element_size() // CALL_DTYPE.itemsize // n_c
+        _check(lib().as_call_variants_sweep_dev(self._h, _dp(counts), T, P, b, e, _dp(ref), _dp(thr_views), n_c,
+                                                int(coverage_cutoff), _dp(calls), cap, _dp(n_calls), self._stream(stream)))
+        return cap
 
     def synth_counts_dev(self, n_samples, P, *, seed, mean_depth, somatic_rate=0.0, sample_offset=0, slot_offset=0,
                          depth_sigma=0.5, germline_rate=1e-3, vaf=(0.01, 0.2), absent_rate=0.0, want_ref=True,

@@ -579,10 +579,26 @@ int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t
     int rc = check_common(c, d_counts, T, P, b, e, cut);
     if (rc) return rc;
     if (!d_ref || !d_thr_view || !d_n_calls || (!d_calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
-    if (T >= (1 << 30)) return fail(AS_EINVAL, "at most 2^30-1 samples per call");
+    if (T >= (1 << 27)) return fail(AS_EINVAL, "at most 2^27-1 samples per call");
     CU(cudaSetDevice(c->device));
     CU(as_launch_call(c->call_variant, d_counts, T, P, b, e, d_ref, d_thr_view, (uint32_t)cut, d_calls, cap, d_n_calls,
                       (cudaStream_t)stream));
+    c->launches += 1;
+    return AS_OK;
+}
+
+int as_call_variants_sweep_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t P, int64_t b, int64_t e,
+                               const uint8_t* d_ref, const float* d_thr_views, int32_t n_c, int32_t cut, as_call* d_calls,
+                               int64_t cap, unsigned long long* d_n_calls, void* stream) {
+    int rc = check_common(c, d_counts, T, P, b, e, cut);
+    if (rc) return rc;
+    if (!d_ref || !d_thr_views || !d_n_calls || (!d_calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
+    if (n_c < 1 || n_c > 8) return fail(AS_EINVAL, "a sweep takes 1..8 threshold tables");
+    if (T >= (1 << 27)) return fail(AS_EINVAL, "at most 2^27-1 samples per call");
+    if (c->call_variant < 2 && n_c > 1) return fail(AS_EINVAL, "the sweep needs a TMA-staged caller variant (>= 2)");
+    CU(cudaSetDevice(c->device));
+    CU(as_launch_call_sweep(c->call_variant, d_counts, T, P, b, e, d_ref, d_thr_views, n_c, P * 8, (uint32_t)cut, d_calls, cap,
+                            d_n_calls, (cudaStream_t)stream));
     c->launches += 1;
     return AS_OK;
 }

@@ -465,10 +465,53 @@ __device__ __forceinline__ void load_slot_const(CallSlotConst& c, const float* _
 // reference's Q never reaches 5 (p = P(X >= k) >= 1/2 for a Poisson mean m >= k; validated against the
 // compiled reference including the region where its 99-step cap leaves the fraction unconverged,
 // tests/test_screens.py), so such a strand test can only veto the call.
+//
+// Second exact screen, for small k: p = P(X >= k | m) grows with m, so there is a critical mean m*(k) with
+// p(k, m*) = P* (the largest p whose Q reaches 5, as_device.cuh) and a strand test with m above it cannot pass.
+// AS_MCRIT[k-1] = m*(k) * (1 + 1e-9), k = 1..64, m* solved to 40 digits (mpmath; scripts/critical_means.py).  Between
+// m*(k) and k the reference evaluates the series of VC:3785-3794 (z < s), whose p is within 1.5e-13 relative of the exact
+// value there (measured against mpmath over k = 1..64); the 1e-9 margin in m is a margin of >= 5e-10 relative in p, so
+// m >= AS_MCRIT[k-1] implies that the reference's own p exceeds P*.  Pairs inside the margin go to the series as before.
+// This matters where depth * e is of order 1 (low noise floors, shallow positions): there "m >= k" never fires and
+// every candidate with one or two alt reads would otherwise cost a full fp64 series only to be rejected.
+__device__ const double AS_MCRIT[64] = {
+    0.3801304084463019, 1.1417568666028408, 1.9737827925528142, 2.836655303617698,
+    3.717842035557975, 4.6115129863431354, 5.514398678438836, 6.4244483020565735,
+    7.340275226714001, 8.26088993116463, 9.185556927304383, 10.113711843311759,
+    11.044910368246212, 11.978795260900911, 12.915074175299806, 13.853504259954532,
+    14.793881161100241, 15.736030981805042, 16.679804280096405, 17.62507150754917,
+    18.571719486996063, 19.519648653852276, 20.468770867935323, 21.419007657863915,
+    22.370288797876483, 23.322551143218725, 24.275737668892344, 25.229796669971126,
+    26.184681091478662, 27.14034796305633, 28.096757919060714, 29.05387478882073,
+    30.01166524490941, 30.97009849969475, 31.929146042307917, 32.888781409637,
+    33.84897998611586, 34.80971882800224, 35.77097650858012, 36.73273298131915,
+    37.694969458508524, 38.657668303278726, 39.62081293324896, 40.58438773430595,
+    41.548377983241544, 42.51276977816144, 43.4775499757315, 44.44270613445805,
+    45.40822646330781, 46.37409977506551, 47.34031544390594, 48.30686336672417,
+    49.273733927824765, 50.240917966620174, 51.208406748030676, 52.17619193531465,
+    53.14426556508969, 54.11262002433242, 55.08124802916871, 56.05014260528682,
+    57.019297069824276, 57.988705014595105, 58.95836029053817, 59.92825699327966,
+};
+
 __device__ __forceinline__ bool strand_can_pass(uint32_t k, uint32_t depth, float err) {
     if (err == -1.0f) return false;  // VC:3844-3849: Q = -888
     const double m = __dmul_rn((double)depth, (double)effective_err(err));
-    return !(m >= (double)k && m > 1.0);
+    if (m >= (double)k && m > 1.0) return false;
+    if (k >= 1u && k <= 64u && m >= AS_MCRIT[k - 1u]) return false;
+    return true;
+}
+
+// Integer pre-screen of the staged caller's scan.  R = floor(e_min * 2^32) for the smallest threshold e_min of the strand;
+// m16 = floor(16 * depth * e_min) in sixteenths (depth saturates at 2^28: a smaller product is still a lower bound).
+// Returns K such that a strand test with 1 <= k <= K cannot pass for any alt base (real mean m >= m16 / 16):
+//   K = floor(m16/16 + 9/16) when that is <= 64: m >= K - 9/16 >= m*(K)(1 + 1e-9) = AS_MCRIT[K-1] (checked for K = 1..64 in
+//       tests/test_host_cpu.py), the critical-mean screen of strand_can_pass;
+//   K = floor(m16/16) otherwise: m >= k and m > 1, the continued-fraction screen.
+__device__ __forceinline__ uint32_t prescreen_k(uint32_t depth, uint32_t R) {
+    const uint32_t d16 = depth > 0x0FFFFFFFu ? 0xFFFFFFFFu : depth << 4;
+    const uint32_t m16 = __umulhi(d16, R);
+    const uint32_t lo = m16 >> 4, hi = lo + (((m16 & 15u) + 9u) >> 4);
+    return hi <= 64u ? hi : lo;
 }
 
 __device__ __forceinline__ void emit_call(as_call* __restrict__ calls, unsigned long long* __restrict__ n_calls,
@@ -672,38 +715,48 @@ call_queued_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
 // evaluated -- survivors are a few per ten thousand records -- so that five CTAs fit one SM).
 struct StagedCand {
     uint32_t k_fw, d_fw, k_bw, d_bw;
-    uint32_t sample_alt;  // sample | alt << 30
+    uint32_t sample_alt;  // sample | threshold table (noise-floor sweep) << 27 | alt << 30
     int32_t slot;
 };
 static_assert(sizeof(StagedCand) == 24, "StagedCand is three 8-byte words");
 
+// n_c threshold tables (noise-floor sweep), c_stride floats apart; table ci owns the list calls + ci * cap and the
+// counter n_calls[ci].  n_c == 1 is the plain caller.
 __device__ __forceinline__ void stage2_batch_staged(const StagedCand* __restrict__ q2, int n_pairs,
                                                     const uint8_t* __restrict__ ref, const float* __restrict__ thr_view,
-                                                    as_call* __restrict__ calls, int64_t cap,
+                                                    int n_c, int64_t c_stride, as_call* __restrict__ calls, int64_t cap,
                                                     unsigned long long* __restrict__ n_calls) {
     const int lane = threadIdx.x & 31;
     const int pair = lane >> 1, strand = lane & 1;
     double p = 1.0;
     StagedCand c;
+    int ci = 0;
     const bool have = pair < n_pairs;
     if (have) {
         c = q2[pair];
-        const float e = thr_view[(int64_t)c.slot * 8 + 2 * (c.sample_alt >> 30) + strand];
+        ci = (int)((c.sample_alt >> 27) & 7u);
+        const float e = thr_view[(int64_t)ci * c_stride + (int64_t)c.slot * 8 + 2 * (c.sample_alt >> 30) + strand];
         p = strand == 0 ? poisson_p((int)c.k_fw, (int)c.d_fw, e) : poisson_p((int)c.k_bw, (int)c.d_bw, e);
     }
     const double p_other = __shfl_xor_sync(0xffffffffu, p, 1);
     const bool is_call = have && strand == 0 && q_at_least_5(p) && q_at_least_5(p_other);
     const unsigned votes = __ballot_sync(0xffffffffu, is_call);
     if (votes == 0) return;
-    const int leader = __ffs(votes) - 1;
-    unsigned long long base = 0;
-    if (lane == leader) base = atomicAdd(n_calls, (unsigned long long)__popc(votes));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    unsigned long long idx;
+    if (n_c == 1) {  // one list: one atomic per batch
+        const int leader = __ffs(votes) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(n_calls, (unsigned long long)__popc(votes));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        idx = base + __popc(votes & ((1u << lane) - 1u));
+    } else {         // one list per threshold table; calls are rare enough for one atomic each
+        idx = is_call ? atomicAdd(n_calls + ci, 1ull) : 0ull;
+        calls += (int64_t)ci * cap;
+    }
     if (is_call) {
-        const unsigned long long idx = base + __popc(votes & ((1u << lane) - 1u));
         if ((int64_t)idx < cap) {
             as_call o;
-            o.sample = (int32_t)(c.sample_alt & 0x3fffffffu);
+            o.sample = (int32_t)(c.sample_alt & 0x7ffffffu);
             o.slot = c.slot;
             o.alt = (int32_t)(c.sample_alt >> 30);
             o.ref = ref[c.slot];
@@ -721,18 +774,21 @@ __device__ __forceinline__ void stage2_batch_staged(const StagedCand* __restrict
 // (two lanes per candidate, as in call_queued_kernel).
 //
 // PRE (integer pre-screen in the scan): the thread keeps, for its slot and each strand, R = floor(e_min * 2^32) of the
-// SMALLEST threshold among the callable alt bases.  m_lo = umulhi(depth, R) <= depth * e_min <= depth * e_b (the real
-// product) for every alt base b, so k <= m_lo and m_lo >= 2 imply m = rn(depth * e_b) >= k (k is an integer, rounding is
-// monotone) and m > 1: exactly the condition under which strand_can_pass is false.  Such (record, base) pairs are dropped
-// in the scan -- the "alt reads > 0" test k > 0 simply becomes k > m_lo, at the price of one multiply per strand -- and
-// never become candidates; pairs between m_lo and their own base's m still do and meet the exact fp64 screen in the
-// revisit, so the call set is unchanged.  The candidate rate falls from 3 % (c3) / 15 % (c5 shape) of the pairs by an
-// order of magnitude or more.
-template <int K, int STAGES, bool PRE>
-__global__ void __launch_bounds__(AS_CTA_THREADS, PRE ? 7 : 1)
+// SMALLEST threshold among the callable alt bases (and among the tables of a sweep).  prescreen_k turns the strand depth
+// into a bound K: a strand test with 1 <= k <= K cannot reach Q >= 5 whatever the base, because its mean
+// m = rn(depth * e_b) >= depth * e_min lies above the critical mean of strand_can_pass (or on the continued-fraction
+// branch).  Such (record, base) pairs are dropped in the scan -- the "alt reads > 0" test k > 0 simply becomes k > K, at
+// the price of one multiply per strand -- and never become candidates; pairs between K and their own base's bound still
+// do and meet the exact fp64 screens in the revisit, so the call set is unchanged.  The candidate rate falls from 3 % (c3)
+// / 15 % (c5 shape) of the pairs by one to two orders of magnitude.
+// SWEEP: n_c_arg threshold tables, c_stride floats apart (noise-floor sweep: the tumour tensor is read once for all of
+// them); otherwise one table and the loops over tables fold away.
+template <int K, int STAGES, bool PRE, bool SWEEP>
+__global__ void __launch_bounds__(AS_CTA_THREADS, SWEEP ? 6 : (PRE ? 7 : 1))
 call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
-                   const uint8_t* __restrict__ ref, const float* __restrict__ thr_view, uint32_t cut,
-                   as_call* __restrict__ calls, int64_t cap, unsigned long long* __restrict__ n_calls) {
+                   const uint8_t* __restrict__ ref, const float* __restrict__ thr_view, int n_c_arg, int64_t c_stride,
+                   uint32_t cut, as_call* __restrict__ calls, int64_t cap, unsigned long long* __restrict__ n_calls) {
+    const int n_c = SWEEP ? n_c_arg : 1;
     static_assert(K * 4 <= 32, "candidate mask is one 32-bit word per thread and stage");
     constexpr int CAND_CAP = K * 32 * 3;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -757,10 +813,11 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
         const uint32_t r = ref[p];
         if (r <= 3) notref = 0xfu & ~(1u << r);
         if (PRE && r <= 3) {
-            const float4 a = *reinterpret_cast<const float4*>(thr_view + p * 8);
-            const float4 b = *reinterpret_cast<const float4*>(thr_view + p * 8 + 4);
-            const float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             Rf = Rb = 0xFFFFFFFFu;
+            for (int ci = 0; ci < n_c; ++ci) {  // the smallest threshold over the alt bases and over the tables of a sweep
+            const float4 a = *reinterpret_cast<const float4*>(thr_view + ci * c_stride + p * 8);
+            const float4 b = *reinterpret_cast<const float4*>(thr_view + ci * c_stride + p * 8 + 4);
+            const float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if ((uint32_t)i == r) continue;
@@ -774,6 +831,7 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                     const uint32_t R = (ee > 0.0f && ee < 1.0f) ? __float2uint_rz(ee * 4294967296.0f) : 0u;
                     if (s == 0) Rf = min(Rf, R); else Rb = min(Rb, R);
                 }
+            }
             }
         }
     }
@@ -798,10 +856,8 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                 const uint32_t FW = fw.x + fw.y + fw.z + fw.w, BW = bw.x + bw.y + bw.z + bw.w;
                 uint32_t m;
                 if (PRE) {
-                    // a strand test with k <= m_lo (and m_lo >= 2) cannot pass; m_lo = 0 leaves the plain k > 0 test
-                    uint32_t mf = __umulhi(FW, Rf), mb = __umulhi(BW, Rb);
-                    mf = mf >= 2u ? mf : 0u;
-                    mb = mb >= 2u ? mb : 0u;
+                    // a strand test with k <= K(m_lo) cannot pass; K = 0 leaves the plain k > 0 test
+                    const uint32_t mf = prescreen_k(FW, Rf), mb = prescreen_k(BW, Rb);
                     m = ((fw.x > mf && bw.x > mb) ? 1u : 0u) | ((fw.y > mf && bw.y > mb) ? 2u : 0u) |
                         ((fw.z > mf && bw.z > mb) ? 4u : 0u) | ((fw.w > mf && bw.w > mb) ? 8u : 0u);
                 } else {
@@ -836,38 +892,57 @@ call_staged_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
                 const int i = base + lane;
                 uint4 w0 = make_uint4(0, 0, 0, 0);  // the StagedCand as a 16-byte and an 8-byte word
                 uint2 w1 = make_uint2(0, 0);
-                bool surv = false;
+                const float* ethr = thr_view;       // thresholds of the candidate's (slot, base): a rare read, served by L2
                 if (i < total) {
                     const uint32_t e = cand[i];
                     const int src = e & 31, bit = e >> 5, j = bit >> 2, b = bit & 3;
                     const int col = warp * 32 + src;
                     const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + col];
                     const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + col];
-                    // thresholds of the candidate's slot: a rare read, served by L2
-                    const float2 ee = *reinterpret_cast<const float2*>(thr_view + (tile0 + col) * 8 + 2 * b);
+                    ethr = thr_view + (tile0 + col) * 8 + 2 * b;
                     w0 = make_uint4(comp(fw, b), fw.x + fw.y + fw.z + fw.w, comp(bw, b), bw.x + bw.y + bw.z + bw.w);
                     w1 = make_uint2((uint32_t)(t + j) | ((uint32_t)b << 30), (uint32_t)(tile0 + col));
-                    surv = strand_can_pass(w0.x, w0.y, ee.x) && strand_can_pass(w0.z, w0.w, ee.y);
                 }
-                const unsigned votes = __ballot_sync(0xffffffffu, surv);
-                if (surv) {
-                    uint2* dst = reinterpret_cast<uint2*>(q2 + n2 + __popc(votes & ((1u << lane) - 1u)));
-                    dst[0] = make_uint2(w0.x, w0.y);
-                    dst[1] = make_uint2(w0.z, w0.w);
-                    dst[2] = w1;
+                // one exact screen per threshold table of a sweep; the threshold reads of all tables are issued together
+                // (independent L2 reads), the queue pushes follow table by table
+                uint32_t smask = 0;
+                if (i < total) {
+                    if (SWEEP) {
+#pragma unroll
+                        for (int ci = 0; ci < 8; ++ci) {
+                            if (ci < n_c) {
+                                const float2 ee = *reinterpret_cast<const float2*>(ethr + ci * c_stride);
+                                smask |= (strand_can_pass(w0.x, w0.y, ee.x) && strand_can_pass(w0.z, w0.w, ee.y)) ? (1u << ci) : 0u;
+                            }
+                        }
+                    } else {
+                        const float2 ee = *reinterpret_cast<const float2*>(ethr);
+                        smask = (strand_can_pass(w0.x, w0.y, ee.x) && strand_can_pass(w0.z, w0.w, ee.y)) ? 1u : 0u;
+                    }
                 }
-                n2 += __popc(votes);
-                __syncwarp();
-                while (n2 >= 16) {
-                    stage2_batch_staged(q2 + (n2 - 16), 16, ref, thr_view, calls, cap, n_calls);
-                    n2 -= 16;
+                if (SWEEP && __ballot_sync(0xffffffffu, smask != 0) == 0) continue;
+                for (int ci = 0; ci < n_c; ++ci) {
+                    const bool surv = (smask >> ci) & 1u;
+                    const unsigned votes = __ballot_sync(0xffffffffu, surv);
+                    if (surv) {
+                        uint2* dst = reinterpret_cast<uint2*>(q2 + n2 + __popc(votes & ((1u << lane) - 1u)));
+                        dst[0] = make_uint2(w0.x, w0.y);
+                        dst[1] = make_uint2(w0.z, w0.w);
+                        dst[2] = make_uint2(w1.x | ((uint32_t)ci << 27), w1.y);
+                    }
+                    n2 += __popc(votes);
                     __syncwarp();
+                    while (n2 >= 16) {
+                        stage2_batch_staged(q2 + (n2 - 16), 16, ref, thr_view, n_c, c_stride, calls, cap, n_calls);
+                        n2 -= 16;
+                        __syncwarp();
+                    }
                 }
             }
         }
         ring.consumer_release(it);
     }
-    if (n2 > 0) stage2_batch_staged(q2, n2, ref, thr_view, calls, cap, n_calls);
+    if (n2 > 0) stage2_batch_staged(q2, n2, ref, thr_view, n_c, c_stride, calls, cap, n_calls);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1102,51 +1177,69 @@ int as_call_chunk(int T, int64_t n_slots) {
     return (int)(chunk < 1 ? 1 : chunk);
 }
 
-template <int K, int STAGES, bool PRE = false>
-static cudaError_t launch_call_staged(dim3 grid, const uint4* c, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
-                                      const uint8_t* ref, const float* tv, uint32_t cut, as_call* calls, int64_t cap,
-                                      unsigned long long* n, cudaStream_t st) {
+template <int K, int STAGES, bool PRE, bool SWEEP>
+static cudaError_t launch_call_staged_impl(dim3 grid, const uint4* c, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
+                                      const uint8_t* ref, const float* tv, int n_c, int64_t c_stride, uint32_t cut,
+                                      as_call* calls, int64_t cap, unsigned long long* n, cudaStream_t st) {
     static bool configured[AS_MAX_DEVICES] = {};  // the attribute is per device
     const int smem = StageRing<K, STAGES>::kStageBytes * STAGES;
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(call_staged_kernel<K, STAGES, PRE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(call_staged_kernel<K, STAGES, PRE, SWEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
     }
-    call_staged_kernel<K, STAGES, PRE><<<grid, AS_CTA_THREADS, smem, st>>>(c, T, P, p0, p1, chunk, ref, tv, cut, calls, cap, n);
+    call_staged_kernel<K, STAGES, PRE, SWEEP><<<grid, AS_CTA_THREADS, smem, st>>>(c, T, P, p0, p1, chunk, ref, tv, n_c, c_stride, cut, calls,
+                                                                           cap, n);
     return cudaGetLastError();
+}
+
+template <int K, int STAGES, bool PRE = false>
+static cudaError_t launch_call_staged(dim3 grid, const uint4* c, int T, int64_t P, int64_t p0, int64_t p1, int chunk,
+                                      const uint8_t* ref, const float* tv, int n_c, int64_t c_stride, uint32_t cut,
+                                      as_call* calls, int64_t cap, unsigned long long* n, cudaStream_t st) {
+    if (n_c == 1) return launch_call_staged_impl<K, STAGES, PRE, false>(grid, c, T, P, p0, p1, chunk, ref, tv, 1, 0, cut, calls, cap, n, st);
+    // sweeps run on the default geometry with the pre-screen, whatever variant is selected
+    return launch_call_staged_impl<3, 2, true, true>(grid, c, T, P, p0, p1, chunk, ref, tv, n_c, c_stride, cut, calls, cap, n, st);
+}
+
+cudaError_t as_launch_call_sweep(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
+                                 const uint8_t* d_ref, const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut,
+                                 as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, cudaStream_t st) {
+    if (p1 <= p0 || T <= 0 || n_c <= 0) return cudaSuccess;
+    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
+    const int chunk = as_call_chunk(T, p1 - p0);
+    dim3 grid(cdiv64(p1 - p0, AS_CALL_THREADS), (unsigned)((T + chunk - 1) / chunk));
+#define AS_CALL_ARGS c, T, P, p0, p1, chunk, d_ref, d_thr_views, cut, d_calls, cap, d_n_calls
+#define AS_SWEEP_ARGS c, T, P, p0, p1, chunk, d_ref, d_thr_views, n_c, c_stride, cut, d_calls, cap, d_n_calls
+    switch (variant) {
+        case 0: if (n_c != 1) return cudaErrorInvalidValue; call_naive_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
+        case 1: if (n_c != 1) return cudaErrorInvalidValue; call_queued_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
+        case 3: return launch_call_staged<4, 2>(grid, AS_SWEEP_ARGS, st);
+        case 4: return launch_call_staged<4, 4>(grid, AS_SWEEP_ARGS, st);
+        case 5: return launch_call_staged<8, 2>(grid, AS_SWEEP_ARGS, st);
+        case 6: return launch_call_staged<8, 3>(grid, AS_SWEEP_ARGS, st);
+        case 7: return launch_call_staged<2, 2>(grid, AS_SWEEP_ARGS, st);
+        case 8: return launch_call_staged<2, 3>(grid, AS_SWEEP_ARGS, st);
+        case 9: return launch_call_staged<2, 4>(grid, AS_SWEEP_ARGS, st);
+        case 10: return launch_call_staged<3, 3>(grid, AS_SWEEP_ARGS, st);
+        case 11: return launch_call_staged<3, 2>(grid, AS_SWEEP_ARGS, st);
+        case 12: return launch_call_staged<6, 2>(grid, AS_SWEEP_ARGS, st);
+        case 13: return launch_call_staged<3, 2, true>(grid, AS_SWEEP_ARGS, st);
+        case 14: return launch_call_staged<4, 2, true>(grid, AS_SWEEP_ARGS, st);
+        case 15: return launch_call_staged<2, 2, true>(grid, AS_SWEEP_ARGS, st);
+        case 16: return launch_call_staged<4, 3, true>(grid, AS_SWEEP_ARGS, st);
+        default: return launch_call_staged<4, 3>(grid, AS_SWEEP_ARGS, st);
+    }
+#undef AS_CALL_ARGS
+#undef AS_SWEEP_ARGS
 }
 
 cudaError_t as_launch_call(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
                            const uint8_t* d_ref, const float* d_thr_view, uint32_t cut, as_call* d_calls, int64_t cap,
                            unsigned long long* d_n_calls, cudaStream_t st) {
-    if (p1 <= p0 || T <= 0) return cudaSuccess;
-    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
-    const int chunk = as_call_chunk(T, p1 - p0);
-    dim3 grid(cdiv64(p1 - p0, AS_CALL_THREADS), (unsigned)((T + chunk - 1) / chunk));
-#define AS_CALL_ARGS c, T, P, p0, p1, chunk, d_ref, d_thr_view, cut, d_calls, cap, d_n_calls
-    switch (variant) {
-        case 0: call_naive_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
-        case 1: call_queued_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
-        case 3: return launch_call_staged<4, 2>(grid, AS_CALL_ARGS, st);
-        case 4: return launch_call_staged<4, 4>(grid, AS_CALL_ARGS, st);
-        case 5: return launch_call_staged<8, 2>(grid, AS_CALL_ARGS, st);
-        case 6: return launch_call_staged<8, 3>(grid, AS_CALL_ARGS, st);
-        case 7: return launch_call_staged<2, 2>(grid, AS_CALL_ARGS, st);
-        case 8: return launch_call_staged<2, 3>(grid, AS_CALL_ARGS, st);
-        case 9: return launch_call_staged<2, 4>(grid, AS_CALL_ARGS, st);
-        case 10: return launch_call_staged<3, 3>(grid, AS_CALL_ARGS, st);
-        case 11: return launch_call_staged<3, 2>(grid, AS_CALL_ARGS, st);
-        case 12: return launch_call_staged<6, 2>(grid, AS_CALL_ARGS, st);
-        case 13: return launch_call_staged<3, 2, true>(grid, AS_CALL_ARGS, st);
-        case 14: return launch_call_staged<4, 2, true>(grid, AS_CALL_ARGS, st);
-        case 15: return launch_call_staged<2, 2, true>(grid, AS_CALL_ARGS, st);
-        case 16: return launch_call_staged<4, 3, true>(grid, AS_CALL_ARGS, st);
-        default: return launch_call_staged<4, 3>(grid, AS_CALL_ARGS, st);
-    }
-#undef AS_CALL_ARGS
+    return as_launch_call_sweep(variant, d_counts, T, P, p0, p1, d_ref, d_thr_view, 1, 0, cut, d_calls, cap, d_n_calls, st);
 }
 
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,

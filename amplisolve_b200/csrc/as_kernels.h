@@ -43,6 +43,10 @@ cudaError_t as_launch_sort_calls(const as_call* d_calls, int64_t n, as_call* d_s
                                  cudaStream_t st);
 // as_fisher.cu: Fisher strand-bias tests, one warp per table {FW, BW, alt_fw, alt_bw}; d_lg[i] = lgamma(i + 1)
 cudaError_t as_launch_fisher(const int32_t* d_tables, int64_t n, const double* d_lg, double* d_p, cudaStream_t st);
+// n_c threshold tables c_stride floats apart (noise-floor sweep): list ci at d_calls + ci * cap, counter d_n_calls[ci]
+cudaError_t as_launch_call_sweep(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
+                                 const uint8_t* d_ref, const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut,
+                                 as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, cudaStream_t st);
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
                                    double* q, cudaStream_t st);
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);

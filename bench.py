@@ -51,6 +51,7 @@ def parse_args():
                     help="capture the device-resident step once and replay it (for small panels, where launches dominate)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the noise-floor sweep leg (C_value 0.001 .. 0.005, configs[3])")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-format", choices=["packed", "16", "32"], default="packed",
                     help="host layout of the e2e leg: the packed wire format (8 B/record), the 16-bit one (16 B) or uint32 (32 B)")
@@ -434,6 +435,56 @@ def run_ours(args):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     total_ms, t_noise_max, t_call_max = [float(x) for x in tmax.tolist()]
 
+    # ---- noise-floor sweep of configs[3] (C_value 0.001 .. 0.005) on the same resident shard: one pass over the
+    # tumours for all five threshold tables vs one caller pass per value (reported beside the headline, not part of it)
+    sweep = None
+    if not args.no_sweep and args.call_kernel >= 2:
+        c_values = [0.001, 0.002, 0.003, 0.004, 0.005]
+        views = torch.empty((len(c_values),) + tuple(view.shape), dtype=torch.float32, device=dev)
+        s_calls = torch.empty(len(c_values) * cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        s_n = torch.zeros(len(c_values), dtype=torch.int64, device=dev)
+
+        def sweep_noise():
+            for ci, cv in enumerate(c_values):
+                ctx.estimate_thresholds_dev(normals, cv, cut, out, twin_next, twin_head)
+                ctx.thresholds_caller_view_dev(out["thr"], views[ci])
+
+        def sweep_fused():
+            s_n.zero_()
+            ctx.call_variants_sweep_dev(tumours, ref, views, cut, s_calls, s_n)
+
+        def sweep_separate():
+            for ci in range(len(c_values)):
+                n_calls.zero_()
+                ctx.call_variants_dev(tumours, ref, views[ci], cut, calls, n_calls)
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                fn()
+            a, b = ev(), ev()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        t_sn = timed(sweep_noise)
+        t_sf = timed(sweep_fused)
+        found_fused = [int(x) for x in s_n.tolist()]
+        t_ss = timed(sweep_separate)
+        tt = torch.tensor([t_sn, t_sf, t_ss], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_sn, t_sf, t_ss = [float(x) for x in tt.tolist()]
+        sweep = {"C_values": c_values, "noise_ms_all_values": t_sn, "caller_ms_fused_one_pass": t_sf,
+                 "caller_ms_one_pass_per_value": t_ss, "calls_per_value_rank0": found_fused,
+                 "tests_per_s_fused": 6.0 * T * P * world * len(c_values) / ((t_sn + t_sf) * 1e-3),
+                 "tests_per_s_separate": 6.0 * T * P * world * len(c_values) / ((t_sn + t_ss) * 1e-3),
+                 "api": "as_call_variants_sweep_dev (tumour tensor read once for all threshold tables)"}
+        del views, s_calls
+
     # ---- end to end through the host-buffer C ABI ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -478,6 +529,8 @@ def run_ours(args):
         }
         if gather_ms is not None:
             result["calls_gather"] = {"ms": gather_ms, "calls_total": n_merged, "transport": "NCCL all_gather of the compacted call lists, once per job"}
+        if sweep is not None:
+            result["noise_floor_sweep"] = sweep
         if e2e is not None:
             result["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -172,6 +172,15 @@ int as_thresholds_caller_view_dev(as_ctx* ctx, const float* d_thr, float* d_thr_
 int as_call_variants_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t T, int64_t P, int64_t slot_begin,
                          int64_t slot_end, const uint8_t* d_ref, const float* d_thr_view, int32_t cut,
                          as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, void* stream);
+/* Noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): the caller for n_c threshold tables in ONE pass over
+ * the tumour tensor.  d_thr_views [n_c][P][4][2] (table ci = the caller view of the noise model run with C_value ci),
+ * d_calls [n_c][cap], d_n_calls [n_c] (zero them first).  The records are read once, the integer scan and its pre-screen
+ * run once (against the smallest threshold of all tables), and only the candidates -- a few per thousand records --
+ * are tested against every table.  List ci is what as_call_variants_dev returns for table ci (as a set; the lists are
+ * unordered).  1 <= n_c <= 8; AS_EOVERFLOW semantics per list are the caller's to check (d_n_calls[ci] > cap). */
+int as_call_variants_sweep_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t T, int64_t P, int64_t slot_begin,
+                               int64_t slot_end, const uint8_t* d_ref, const float* d_thr_views, int32_t n_c, int32_t cut,
+                               as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, void* stream);
 int as_call_variants_host(as_ctx* ctx, const uint32_t* counts, int32_t T, int64_t P, const uint8_t* ref,
                           const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls);
 

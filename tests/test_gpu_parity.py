@@ -7,6 +7,8 @@ quanta of 2^-53 below.
 """
 import numpy as np
 import pytest
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
 
 from oracle import pyoracle
 from tests import synth
@@ -283,6 +285,51 @@ def test_integer_prescreen_boundaries(ctx, variant):
     check_calls(got, want, [np.arange(P) for _ in range(T)])
 
 
+@pytest.mark.parametrize("variant", [13, 1])
+def test_critical_mean_screen(ctx, variant):
+    """The second exact screen of the caller (m >= AS_MCRIT[k-1] => the strand test cannot pass, k <= 64): records whose
+    mean m = depth * e straddles the critical mean m*(k) of every k = 1..64 by relative offsets from 1e-6 to 1e-1, on both
+    strands or on one (the other strand passing comfortably), against the straightforward kernel (no screens) and the
+    oracle.  e = 2^-20 makes depth * e exact, so the offsets are what they say."""
+    import sys
+    sys.path.insert(0, str(ROOT / "scripts"))
+    from critical_means import critical_means
+    mc = np.array(critical_means()) / (1 + 1e-9)
+    offs = np.array([-1e-1, -1e-2, -1e-4, -1e-6, 1e-6, 1e-4, 1e-2, 1e-1])
+    ks = np.arange(1, 65)
+    P, T = 64 * 2, len(offs)                      # slot = (k, both strands / one strand), sample = offset
+    e = np.float32(2.0 ** -20)
+    thr = np.full((P, 4, 2), e, np.float32)
+    ref = np.zeros(P, np.uint8)                   # reference base A, alt C carries the test
+    tumours = np.zeros((T, 2, P, 4), np.uint32)
+    for si, off in enumerate(offs):
+        depth = np.rint(mc * (1 + off) * 2.0 ** 20).astype(np.int64)      # m = depth * 2^-20
+        for mode in (0, 1):
+            slots = (ks - 1) * 2 + mode
+            tumours[si, 0, slots, 1] = ks
+            tumours[si, 0, slots, 0] = depth - ks
+            if mode == 0:
+                tumours[si, 1, slots, 1] = ks
+                tumours[si, 1, slots, 0] = depth - ks
+            else:                                  # reverse strand: same k at a tenth of the mean -> passes easily
+                tumours[si, 1, slots, 1] = ks
+                tumours[si, 1, slots, 0] = np.maximum(depth // 10, 200) - ks
+    ctx.set_call_kernel(0)
+    try:
+        plain = ctx.call_variants(tumours, ref, thr, 100)
+        ctx.set_call_kernel(variant)
+        got = ctx.call_variants(tumours, ref, thr, 100)
+    finally:
+        ctx.set_call_kernel(-1)
+    assert plain.tobytes() == got.tobytes()
+    # below the critical mean the pair is a call, above it is not -- for every k and both layouts
+    called = np.zeros((T, P), bool)
+    called[got["sample"], got["slot"]] = True
+    assert called[offs <= -1e-4].all() and not called[offs >= 1e-4].any()   # (the 1e-6 offsets are below the depth grid at small k)
+    want, _, _ = oracle_calls(tumours, np.arange(P, dtype=np.int32), P, ref, thr, 100)
+    check_calls(got, want, [np.arange(P) for _ in range(T)])
+
+
 @pytest.mark.parametrize("tile", [128, 512, 1024])
 def test_host_pipelines_across_tile_boundaries(ctx, tile):
     """The _host entry points tile over slots; twin groups that straddle a tile boundary take the gather path."""
@@ -377,6 +424,48 @@ def test_packed_host_entry_points_equal_the_32_bit_ones(ctx):
     assert len(we) == 0 and (pe == 0xFFFFFFFF).all()
     out = ctx.estimate_thresholds(pe, 0.002, 100)
     assert (out["nrec"] == 0).all() and np.isnan(out["thr"]).all()
+
+
+def test_noise_floor_sweep_equals_one_pass_per_c_value(ctx):
+    """as_call_variants_sweep_dev (BASELINE configs[3]: C_value 0.001 ... 0.005): one pass over the tumour tensor for all
+    threshold tables gives, per table, exactly the call set of the plain caller run with that table -- and that is the
+    oracle's for that C_value."""
+    import torch
+    from amplisolve_b200 import CALL_DTYPE
+    _, slots, pos_id, U = synth.make_panel(20, seed=91)
+    P = len(slots)
+    normals, ref = synth.make_counts(14, P, depth=2500, seed=91, pos_id=pos_id)
+    tumours, _ = synth.make_counts(37, P, depth=2500, seed=92, ref=ref, pos_id=pos_id, somatic_rate=0.02)
+    nxt, head = ctx_twins(pos_id)
+    c_values = [0.001, 0.002, 0.003, 0.004, 0.005]
+    views = [ctx.estimate_thresholds(normals, c, 100, nxt, head, with_view=True)["thr_view"] for c in c_values]
+    d_t = torch.from_numpy(tumours.view(np.int32)).cuda()
+    d_ref = torch.from_numpy(ref).cuda()
+    d_views = torch.from_numpy(np.stack(views)).cuda()
+    cap = 1 << 15
+    d_calls = torch.zeros(len(c_values) * cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device="cuda")
+    d_n = torch.zeros(len(c_values), dtype=torch.int64, device="cuda")
+    assert ctx.call_variants_sweep_dev(d_t, d_ref, d_views, 100, d_calls, d_n) == cap
+    torch.cuda.synchronize()
+    n = d_n.cpu().numpy()
+    lists = d_calls.cpu().numpy().view(CALL_DTYPE).reshape(len(c_values), cap)
+    ref_u = np.zeros(U, np.uint8)
+    ref_u[pos_id] = ref
+    sizes = []
+    for ci, c in enumerate(c_values):
+        got = np.sort(lists[ci, :n[ci]], order=["sample", "slot", "alt"])
+        want = ctx.call_variants(tumours, ref, views[ci], 100)          # sorted by (sample, slot, alt)
+        assert len(want) > 0 and got.tobytes() == want.tobytes(), c
+        sizes.append(len(want))
+    assert sizes[0] > sizes[-1]          # a higher noise floor calls less
+    # and the oracle, for the two ends of the sweep
+    for ci in (0, len(c_values) - 1):
+        nz = oracle_noise(normals, pos_id, U, np.float32(c_values[ci]), 100)
+        thr_u = pyoracle.thr_as_caller_sees(np.where(np.isnan(nz["thr"]), np.float32(0.01), nz["thr"]))
+        want, _, _ = oracle_calls(tumours, pos_id, U, ref_u, thr_u, 100)
+        got = np.sort(lists[ci, :n[ci]], order=["sample", "slot", "alt"])
+        present = tumours[:, 0, :, 0] != 0xFFFFFFFF
+        check_calls(got, want, [np.nonzero(present[s])[0] for s in range(tumours.shape[0])])
 
 
 def test_device_fisher_equals_host_and_boost(ctx):

@@ -94,6 +94,29 @@ def test_packed_wire_format_is_lossless():
     assert rc == -5 and n.value == len(wide)
 
 
+def test_critical_means_table_and_prescreen_bound():
+    """AS_MCRIT of as_kernels.cu is what scripts/critical_means.py computes (m*(k)(1 + 1e-9), P(X >= k | m*) = P*), the
+    reference's own p (oracle) is above P* at the table value and at most P* a hair below the critical mean, and the
+    scan's bound K - 9/16 >= AS_MCRIT[K-1] holds for K = 1..64."""
+    import sys
+    sys.path.insert(0, str(ROOT / "scripts"))
+    from critical_means import critical_means
+    want = critical_means()
+    src = (ROOT / "amplisolve_b200" / "csrc" / "as_kernels.cu").read_text()
+    body = src[src.index("AS_MCRIT[64] = {") + len("AS_MCRIT[64] = {"):]
+    body = body[:body.index("};")]
+    have = [float(x) for x in body.replace("\n", " ").split(",") if x.strip()]
+    assert have == want and len(have) == 64
+    p_star = np.frombuffer(np.uint64(0x3FD43D136248490E).tobytes(), dtype=np.float64)[0]
+    err = np.float32(2.0 ** -20)
+    for k in range(1, 65):
+        assert have[k - 1] <= k - 9 / 16
+        above = int(np.ceil(have[k - 1] * 2 ** 20))                   # the first depth whose mean is >= the table value
+        below = int(np.floor(have[k - 1] / (1 + 1e-9) * (1 - 3e-6) * 2 ** 20))
+        assert pyoracle.poisson_p(k, above, err) > p_star
+        assert pyoracle.poisson_p(k, below, err) <= p_star
+
+
 def test_twin_links():
     from amplisolve_b200 import twin_links
     nxt, head = twin_links([0, 1, 2, 1, 3, 0, 1])

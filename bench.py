@@ -269,14 +269,15 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(kernel, default_workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture of this workload."""
+def ncu_traffic(kernel, default_workload, key=None):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch (or another recorded figure) from the committed ncu capture
+    of this workload (profiles/ncu_traffic.json, written by scripts/ncu_summary.py --traffic)."""
     f = ROOT / "profiles" / "ncu_traffic.json"
     if not default_workload or not f.exists():
         return None
     try:
         k = json.loads(f.read_text())["kernels"][kernel]
-        return k["dram_bytes_read"] + k["dram_bytes_write"]
+        return k[key] if key else k["dram_bytes_read"] + k["dram_bytes_write"]
     except Exception:
         return None
 
@@ -520,10 +521,14 @@ def run_ours(args):
                          "achieved": call_bytes / (t_call * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": call_bytes / (t_call * 1e-3) / 1e9 / peak,
                          "traffic": ncu_traffic("call_staged_kernel", default_wl and args.call_kernel == 13), "peak_source": peak_src,
-                         "algorithmic_bytes": call_bytes},
+                         "algorithmic_bytes": call_bytes,
+                         "ncu_dram_pct_of_hw_peak": ncu_traffic("call_staged_kernel", default_wl and args.call_kernel == 13, "dram_pct_of_peak"),
+                         "note": "peak is the driver's copy measurement (read + write); a read-only stream can exceed it, hence frac > 1 is "
+                                 "possible -- ncu's own gpu__dram_throughput percentage of the hardware peak is given beside it"},
             "roofline_noise": {"bound": "hbm", "kernel": "noise_main_kernel" if args.noise_kernel == 0 else "noise_staged_kernel", "achieved": noise_bytes / (t_noise * 1e-3) / 1e9,
                                "peak": peak, "unit": "GB/s", "frac": noise_bytes / (t_noise * 1e-3) / 1e9 / peak,
                                "traffic": ncu_traffic("noise_staged_kernel", default_wl and args.noise_kernel == 1),
+                               "ncu_dram_pct_of_hw_peak": ncu_traffic("noise_staged_kernel", default_wl and args.noise_kernel == 1, "dram_pct_of_peak"),
                                "algorithmic_bytes": noise_bytes},
             "gpu_launches": int(launches * world), "clocks": clocks,
         }

@@ -48,8 +48,10 @@ def test_calls_from_cuda_match_reference_rows(ctx, name):
         assert gu.fmt_g(c["q_fw"]) == w[10] and gu.fmt_g(c["q_bw"]) == w[11]   # the device's own fp64 Q prints alike
 
 
-def run(prog, args, cwd):
-    r = subprocess.run([str(BIN / prog)] + args, cwd=cwd, capture_output=True, text=True)
+def run(prog, args, cwd, env=None):
+    import os
+    r = subprocess.run([str(BIN / prog)] + args, cwd=cwd, capture_output=True, text=True,
+                       env=None if env is None else dict(os.environ, **env))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
     return r.stdout
 
@@ -81,9 +83,63 @@ def test_programs_end_to_end_byte_identical(name, tmp_path):
     assert len(dummy) == len(slots) and dummy[0] == f"{slots[0][0]}\t{slots[0][1]}\t.\t.\t.\t.\t.\t."
 
 
+@pytest.mark.parametrize("wire", ["16", "packed"])
+def test_programs_byte_identical_in_either_wire_format(wire, tmp_path):
+    """The loaders write the packed wire format and fall back to the 16-bit one for ultra-deep data; AS_WIRE forces one.
+    Either way every output byte is the reference's (the Toy_data slice has 5000x rows: many records escape the packed
+    form, none the 16-bit one)."""
+    case = gu.load("toy_slice")
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    env = {"AS_WIRE": wire}
+    run("AmpliSolveErrorEstimation", ["panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N",
+                                      "C_value=%g" % float(case["c_value"]), f"coverage_cutoff={int(case['cutoff'])}",
+                                      "default_error=0.01", "output_dir=o"], tmp_path, env)
+    table = tmp_path / "o" / ("positionSpecificNoise_%.4f.txt" % float(case["c_value"]))
+    assert table.read_text() == case["noise_table"]
+    run("AmpliSolveVariantCalling", [f"errorFile=o/{table.name}", "tumour_dir=T", "output_dir=v",
+                                     f"coverage_cutoff={int(case['cutoff'])}", "p_value=0.05"], tmp_path, env)
+    assert (tmp_path / "v" / "Summary_Variant_Info.txt").read_text() == case["summary"]
+    for nm in case["tumour_names"]:
+        assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == case["vcfs"][nm], nm
+
+
+def test_program_falls_back_to_16_bit_on_ultra_deep_panels(tmp_path):
+    """At 50,000x (configs[4]) most records carry an error count above 15 and would escape the packed form: the loader
+    notices (more than 1 record in 16) and parses into the 16-bit format instead.  The table must equal the one the
+    forced formats give, and the oracle's."""
+    from tests import synth
+    bed, slots, pos_id, U = synth.make_panel(6, seed=71, chroms=("chr7",))
+    P = len(slots)
+    normals, ref = synth.make_counts(8, P, depth=50000, seed=71, pos_id=pos_id)
+    from amplisolve_b200 import pack_counts
+    _, wide = pack_counts(normals)
+    assert len(wide) * 16 > (normals[:, 0, :, 0] != 0xFFFFFFFF).sum()          # the fallback condition holds
+    ref_u = np.zeros(U, np.uint8)
+    ref_u[pos_id] = ref
+    case = {"bed": "".join(f"{c}\t{s}\t{e}\tA{i}\t.\tG\n" for i, (c, s, e) in enumerate(bed)),
+            "ref_letters": "".join("ACGT"[r] for r in ref_u[pos_id]), "normal_names": [f"DEEP{i}" for i in range(8)],
+            "normals": normals, "tumour_names": [], "tumours": np.zeros((0, 2, P, 4), np.uint32)}
+    slots2 = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots2, list(case["ref_letters"]))
+    args = ["panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N", "C_value=0.002", "coverage_cutoff=100",
+            "default_error=0.01"]
+    tables = {}
+    for tag, env in (("auto", None), ("w16", {"AS_WIRE": "16"}), ("packed", {"AS_WIRE": "packed"})):
+        run("AmpliSolveErrorEstimation", args + [f"output_dir=o_{tag}"], tmp_path, env)
+        tables[tag] = (tmp_path / f"o_{tag}" / "positionSpecificNoise_0.0020.txt").read_text()
+    assert tables["auto"] == tables["w16"] == tables["packed"]
+    order = pyoracle.hash_iteration_order([f"N/{n}.PILEUP.ASEQ" for n in case["normal_names"]])
+    rows, off = pyoracle.dense_to_rows(synth.to_oracle_layout(normals[order]), pos_id)
+    nz = pyoracle.noise_estimate(rows, off, U, np.float32(0.002), 100)
+    case.update(slots=slots2)
+    want = gu.noise_table_lines(case, nz["thr"][pos_id], nz["germ_val"][pos_id], nz["germ_present"][pos_id])
+    assert tables["auto"].splitlines() == want
+
+
 def test_program_escapes_counts_beyond_the_16_bit_wire_format(tmp_path):
-    """The loaders fill the uint16 wire format; a record with a count of 65534 or more is escaped into the side list of
-    wide records.  Checked end to end against the oracle's table on a panel with a few ultra-deep positions (incl.
+    """The loaders fill a wire format (packed, or 16-bit on ultra-deep data); a record that does not fit -- here counts of
+    65534 or more, which escape both -- goes to the side list of wide records.  Checked end to end against the oracle's table on a panel with a few ultra-deep positions (incl.
     depths beyond 2^24, where int -> float stops being exact)."""
     from tests import synth
     bed, slots, pos_id, U = synth.make_panel(14, seed=61, chroms=("chr5",))

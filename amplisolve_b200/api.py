@@ -29,7 +29,7 @@ EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
-    "as_call_variants_host16", "as_call_variants_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
+    "as_call_variants_host16", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
@@ -147,6 +147,7 @@ def lib():
     L.as_kernel_launches.argtypes = [vp]
     L.as_kernel_launches.restype = i64
     L.as_noise_estimate_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
+    L.as_noise_estimate_sweep_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]
     L.as_noise_estimate_host.argtypes = [vp, vp, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     L.as_noise_estimate_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
     L.as_thresholds_caller_view_dev.argtypes = [vp, vp, vp, i64, vp]
@@ -397,6 +398,19 @@ class Context:
             view = torch.empty_like(thr)
         _check(lib().as_thresholds_caller_view_dev(self._h, _dp(thr), _dp(view), thr.numel(), self._stream(stream)))
         return view
+
+    def estimate_thresholds_sweep_dev(self, counts, c_values, coverage_cutoff, thr, out, twin_next=None, twin_head=None,
+                                      slot_range=None, stream=None):
+        """Noise-floor sweep: thr torch float32 [n_c][P][4][2] receives one threshold table per C value; out (as from
+        alloc_noise_outputs) the outputs that do not depend on C (its "thr" entry is not written)."""
+        S, two, P, four = counts.shape
+        cv = _np(c_values, np.float32)
+        assert thr.shape == (len(cv), P, 4, 2) and thr.is_contiguous()
+        b, e = slot_range if slot_range is not None else (0, P)
+        _check(lib().as_noise_estimate_sweep_dev(self._h, _dp(counts), S, P, b, e, _dp(twin_next), _dp(twin_head), _hp(cv),
+                                                 len(cv), int(coverage_cutoff), _dp(thr), _dp(out["germ_val"]),
+                                                 _dp(out["germ_state"]), _dp(out["count"]), _dp(out["nrec"]),
+                                                 self._stream(stream)))
 
     def call_variants_dev(self, counts, ref, thr_view, coverage_cutoff, calls, n_calls, slot_range=None, stream=None):
         """calls: torch uint8 CUDA tensor of cap*48 bytes; n_calls: torch int64 CUDA tensor [1] (added to)."""

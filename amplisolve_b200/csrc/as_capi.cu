@@ -240,6 +240,36 @@ int as_noise_estimate_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_
     return AS_OK;
 }
 
+int as_noise_estimate_sweep_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, int64_t P, int64_t b, int64_t e,
+                                const int32_t* d_twin_next, const int32_t* d_twin_head, const float* c_values, int32_t n_c,
+                                int32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count,
+                                uint32_t* d_nrec, void* stream) {
+    if (!c_values || n_c < 1 || n_c > 8) return fail(AS_EINVAL, "a sweep takes 1..8 values of C");
+    // the first value: every output, twin groups on the side stream, joined before control returns to `stream`
+    int rc = as_noise_estimate_dev(c, d_counts, S, P, b, e, d_twin_next, d_twin_head, c_values[0], cut, d_thr, d_germ_val,
+                                   d_germ_state, d_count, d_nrec, stream);
+    if (rc != AS_OK || n_c == 1) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t stride = P * 8;
+    for (int32_t i = 1; i < n_c; i += 4) {  // up to four further values per pass over the normals
+        const int32_t m = std::min<int32_t>(4, n_c - i);
+        CU(as_launch_noise_sweep(d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, c_values + i, m, (uint32_t)cut,
+                                 d_thr + (int64_t)i * stride, stride, st));
+        c->launches += 1;
+    }
+    if (d_twin_next) {
+        // twin groups the streaming kernels leave out (pairs cut by a CTA tile, longer chains): a few slots, value by value.
+        // They rewrite Germ_Max / count / nrec of those slots with the same values.
+        for (int32_t i = 1; i < n_c; ++i) {
+            CU(as_launch_noise_twins(AS_DEFAULT_NOISE_KERNEL, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
+                                     (uint32_t*)c->nheads.p, c_values[i], (uint32_t)cut, d_thr + (int64_t)i * stride, d_germ_val,
+                                     d_germ_state, d_count, d_nrec, st));
+            c->launches += 3;
+        }
+    }
+    return AS_OK;
+}
+
 int as_thresholds_caller_view_dev(as_ctx* c, const float* d_thr, float* d_view, int64_t n, void* stream) {
     if (!c || !d_thr || !d_view || n < 0) return fail(AS_EINVAL, "bad argument");
     CU(cudaSetDevice(c->device));

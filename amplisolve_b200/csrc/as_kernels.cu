@@ -206,6 +206,229 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
 }
 
 // ------------------------------------------------------------------------------------------------
+// noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): thresholds for NC further C values in ONE pass
+// over the normals.  Only the sum of float(depth) * float(C) (EE:1617) depends on C; the filter, the alt-read and depth
+// sums and the counts are shared.  Germ_Max, count and nrec do not depend on C at all and come from the plain kernel
+// run with the first value.  Same ring, same fast-path arithmetic, same handling of twin pairs inside the tile (sums
+// simply add here); slots of other twin groups are left to noise_pair_kernel / noise_twin_kernel, per value.
+// ------------------------------------------------------------------------------------------------
+#define AS_SWEEP_NC 4
+struct SweepC {
+    float c[AS_SWEEP_NC];
+};
+struct SweepBase {
+    uint32_t s_b_fw, s_b_bw;                      // 32-bit partial sums of alt reads (folded like FastBase)
+    double s_d_fw, s_d_bw;                        // strand depth
+    double s_p_fw[AS_SWEEP_NC], s_p_bw[AS_SWEEP_NC];  // float(depth) * float(C) per value, plus the folded alt-read sums
+    uint32_t count;
+};
+struct SweepAcc {
+    SweepBase b[4];
+    uint32_t nrec, big;
+};
+struct SweepXfer {  // what the second slot of a twin pair hands to the first (after the fold: s_b is zero)
+    double d[4][2], p[4][2][AS_SWEEP_NC];
+    uint32_t count[4], nrec, big;
+};
+
+__device__ __forceinline__ void sweep_fold(SweepAcc& a) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double bf = u32_to_double(a.b[i].s_b_fw), bb = u32_to_double(a.b[i].s_b_bw);
+#pragma unroll
+        for (int c = 0; c < AS_SWEEP_NC; ++c) {
+            a.b[i].s_p_fw[c] = __dadd_rn(a.b[i].s_p_fw[c], bf);
+            a.b[i].s_p_bw[c] = __dadd_rn(a.b[i].s_p_bw[c], bb);
+        }
+        a.b[i].s_b_fw = a.b[i].s_b_bw = 0u;
+    }
+}
+
+__device__ __forceinline__ void sweep_store(const SweepBase (&b)[4], uint32_t n_records, int n_c, int64_t slot,
+                                            float* __restrict__ thr, int64_t thr_stride) {
+#pragma unroll  // (a run-time index into s_p would put the whole accumulator into local memory)
+    for (int c = 0; c < AS_SWEEP_NC; ++c) {
+        if (c >= n_c) break;
+        float t[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            NoiseBase nb;
+            nb.s_b_fw = nb.s_b_bw = 0ull;  // folded into s_p
+            nb.s_d_fw = (unsigned long long)__double2ll_rn(b[i].s_d_fw);
+            nb.s_d_bw = (unsigned long long)__double2ll_rn(b[i].s_d_bw);
+            nb.s_p_fw = b[i].s_p_fw[c]; nb.s_p_bw = b[i].s_p_bw[c];
+            nb.count = b[i].count;
+            nb.g_n = 0; nb.g_x = 0; nb.g_rd = 1; nb.g_first_x = 0; nb.g_first_rd = 1;
+            float g;
+            uint32_t st;
+            noise_final_base(nb, n_records, i, t[2 * i], t[2 * i + 1], g, st);
+        }
+        float4* t4 = reinterpret_cast<float4*>(thr + c * thr_stride + slot * 8);
+        t4[0] = make_float4(t[0], t[1], t[2], t[3]);
+        t4[1] = make_float4(t[4], t[5], t[6], t[7]);
+    }
+}
+
+template <int K, int STAGES>
+__global__ void __launch_bounds__(AS_CTA_THREADS, 3)
+noise_sweep_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t p0, int64_t p1,
+                   const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head, int64_t twin_base,
+                   SweepC cs, int n_c, uint32_t cut, float* __restrict__ thr, int64_t thr_stride) {
+    static_assert(StageRing<K, STAGES>::kStageBytes * STAGES >= AS_TILE_SLOTS * (int)sizeof(SweepXfer), "hand-over block of twin pairs");
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES];
+    StageRing<K, STAGES> ring;
+    ring.init(smem_raw, bars);
+    const int64_t tile0 = p0 + (int64_t)blockIdx.x * AS_TILE_SLOTS;
+    const int n_slots = (int)min((int64_t)AS_TILE_SLOTS, p1 - tile0);
+    const int tid = threadIdx.x;
+    if (tid >= AS_TILE_SLOTS) {  // producer warp
+        if (tid == AS_TILE_SLOTS) ring.produce(counts + tile0, 2 * P, P, 0, S, n_slots);
+        return;
+    }
+    const int64_t p = tile0 + tid;
+    bool active = tid < n_slots;
+    int role = 0, twin_d = 0;  // as in noise_staged_kernel
+    if (active && twin_next != nullptr) {
+        const int64_t gid = p + twin_base;
+        if (twin_next[p] >= 0 || twin_head[p] != (int32_t)gid) role = 3;
+        twin_d = intile_twin_distance(twin_next, twin_head, p, gid, tid, n_slots);
+        if (twin_d > 0) {
+            role = 1;
+        } else if (role == 3) {
+            const int64_t back = gid - (int64_t)twin_head[p];
+            if (back > 0 && back <= tid && intile_twin_distance(twin_next, twin_head, p - back, gid - back, tid - (int)back, n_slots) == (int)back)
+                role = 2;
+        }
+        if (role == 3) active = false;
+    }
+
+    SweepAcc f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f.b[i].s_b_fw = f.b[i].s_b_bw = 0u;
+        f.b[i].s_d_fw = f.b[i].s_d_bw = 0.0;
+        f.b[i].count = 0u;
+#pragma unroll
+        for (int c = 0; c < AS_SWEEP_NC; ++c) f.b[i].s_p_fw[c] = f.b[i].s_p_bw[c] = 0.0;
+    }
+    f.nrec = 0; f.big = 0;
+    int it = 0, since_fold = 0;
+    for (int t = 0; t < S; t += K, ++it) {
+        const uint4* st = ring.consumer_wait(it);
+        const int k = min(K, S - t);
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                if (j < k) {
+                    const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid];
+                    const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid];
+                    if ((int32_t)fw.x >= 0) {  // not AS_ABSENT
+                        f.nrec += 1;
+                        FastRecord r;
+                        fast_record(r, fw, bw, cs.c[0], cut);
+                        f.big |= r.RD;
+                        const float Ff = __uint2float_rn(fw.x + fw.y + fw.z + fw.w), Bf = __uint2float_rn(bw.x + bw.y + bw.z + bw.w);
+                        double pf[AS_SWEEP_NC], pb[AS_SWEEP_NC];
+#pragma unroll
+                        for (int c = 0; c < AS_SWEEP_NC; ++c) {  // EE:1617: fp32 product, then widened
+                            pf[c] = (double)__fmul_rn(Ff, cs.c[c]);
+                            pb[c] = (double)__fmul_rn(Bf, cs.c[c]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            SweepBase& sb = f.b[i];
+                            const uint32_t bf = comp(fw, i), bb = comp(bw, i);
+                            if (((int32_t)bf <= r.lim_fw) & ((int32_t)bb <= r.lim_bw)) {  // EE:1613-1615
+                                sb.s_b_fw += bf; sb.s_b_bw += bb;
+                                sb.s_d_fw = __dadd_rn(sb.s_d_fw, r.d_fw); sb.s_d_bw = __dadd_rn(sb.s_d_bw, r.d_bw);
+#pragma unroll
+                                for (int c = 0; c < AS_SWEEP_NC; ++c) {
+                                    sb.s_p_fw[c] = __dadd_rn(sb.s_p_fw[c], pf[c]);
+                                    sb.s_p_bw[c] = __dadd_rn(sb.s_p_bw[c], pb[c]);
+                                }
+                                sb.count += 1;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        ring.consumer_release(it);
+        since_fold += K;
+        if (since_fold >= AS_FOLD_EVERY) { sweep_fold(f); since_fold = 0; }
+    }
+    sweep_fold(f);
+
+    if (twin_next != nullptr) {  // twin pairs inside the tile: the second slot's sums join the first slot's
+        SweepXfer* xfer = reinterpret_cast<SweepXfer*>(smem_raw);
+        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");  // every consumer warp is done with the ring
+        if (role == 2) {
+            SweepXfer& o = xfer[tid];
+            o.nrec = f.nrec; o.big = f.big;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                o.d[i][0] = f.b[i].s_d_fw; o.d[i][1] = f.b[i].s_d_bw;
+                o.count[i] = f.b[i].count;
+#pragma unroll
+                for (int c = 0; c < AS_SWEEP_NC; ++c) { o.p[i][0][c] = f.b[i].s_p_fw[c]; o.p[i][1][c] = f.b[i].s_p_bw[c]; }
+            }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");
+        if (role == 1) {
+            const SweepXfer& o = xfer[tid + twin_d];
+            f.nrec += o.nrec;
+            f.big |= o.big;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f.b[i].s_d_fw = __dadd_rn(f.b[i].s_d_fw, o.d[i][0]); f.b[i].s_d_bw = __dadd_rn(f.b[i].s_d_bw, o.d[i][1]);
+                f.b[i].count += o.count[i];
+#pragma unroll
+                for (int c = 0; c < AS_SWEEP_NC; ++c) {
+                    f.b[i].s_p_fw[c] = __dadd_rn(f.b[i].s_p_fw[c], o.p[i][0][c]);
+                    f.b[i].s_p_bw[c] = __dadd_rn(f.b[i].s_p_bw[c], o.p[i][1][c]);
+                }
+            }
+        }
+        if (role == 2) active = false;  // stored by the first slot's thread
+    }
+    if (!active) return;
+    const int tw = role == 1 ? twin_d : 0;
+    if (f.big < (1u << 24)) {
+        sweep_store(f.b, f.nrec, n_c, p, thr, thr_stride);
+        if (tw > 0) sweep_store(f.b, f.nrec, n_c, p + tw, thr, thr_stride);
+    } else {
+        // a depth of 2^24 or more: int -> float is inexact, redo the slot with the general code, value by value
+        const uint4* q = counts + p;
+        for (int c = 0; c < n_c; ++c) {
+            NoiseAcc acc;
+            noise_init(acc);
+#pragma unroll 1
+            for (int s = 0; s < S; ++s) {
+#pragma unroll 1
+                for (int r = 0; r <= (tw > 0 ? 1 : 0); ++r) {
+                    const uint4 fw = ld_stream(q + (int64_t)s * 2 * P + r * tw);
+                    const uint4 bw = ld_stream(q + (int64_t)s * 2 * P + P + r * tw);
+                    noise_accumulate<false>(acc, fw, bw, cs.c[c], cut);
+                }
+            }
+            float t[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float g;
+                uint32_t st;
+                noise_final_base(acc.b[i], acc.nrec, i, t[2 * i], t[2 * i + 1], g, st);
+            }
+            for (int r = 0; r <= (tw > 0 ? 1 : 0); ++r) {
+                float4* t4 = reinterpret_cast<float4*>(thr + c * thr_stride + (p + r * tw) * 8);
+                t4[0] = make_float4(t[0], t[1], t[2], t[3]);
+                t4[1] = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // noise model, twin groups: the reference keys records by "chrom_pos" text, so every row of every
 // slot of a duplicated position feeds ONE estimate (EE:1241-1245), in the order file, then row.
 // ------------------------------------------------------------------------------------------------
@@ -1107,6 +1330,28 @@ cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64
         default: return launch_noise_staged<4, 3>(AS_NOISE_ARGS, st);
     }
 #undef AS_NOISE_ARGS
+}
+
+// thresholds of n_c (<= AS_SWEEP_NC) further C values in one pass: table c at d_thr + c * thr_stride floats
+cudaError_t as_launch_noise_sweep(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1, const int32_t* d_twin_next,
+                                  const int32_t* d_twin_head, int64_t twin_base, const float* c_values, int n_c, uint32_t cut,
+                                  float* d_thr, int64_t thr_stride, cudaStream_t st) {
+    if (p1 <= p0 || n_c <= 0) return cudaSuccess;
+    if (n_c > AS_SWEEP_NC) return cudaErrorInvalidValue;
+    static bool configured[AS_MAX_DEVICES] = {};
+    const int smem = StageRing<4, 3>::kStageBytes * 3;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(noise_sweep_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
+    }
+    SweepC cs;
+    for (int c = 0; c < AS_SWEEP_NC; ++c) cs.c[c] = c_values[c < n_c ? c : n_c - 1];
+    noise_sweep_kernel<4, 3><<<cdiv64(p1 - p0, AS_TILE_SLOTS), AS_CTA_THREADS, smem, st>>>(
+        reinterpret_cast<const uint4*>(d_counts), S, P, p0, p1, d_twin_next, d_twin_head, twin_base, cs, n_c, cut, d_thr, thr_stride);
+    return cudaGetLastError();
 }
 
 // 4 launches (memset node + 3 kernels).  d_heads_scratch holds n slots of int32 (pairs in the first half, longer

@@ -26,6 +26,9 @@ cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int6
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
                                   uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
+cudaError_t as_launch_noise_sweep(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1, const int32_t* d_twin_next,
+                                  const int32_t* d_twin_head, int64_t twin_base, const float* c_values, int n_c, uint32_t cut,
+                                  float* d_thr, int64_t thr_stride, cudaStream_t st);
 cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_unpack(const uint32_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32_t* d_tile, int64_t n, int64_t p0,

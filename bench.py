@@ -445,10 +445,16 @@ def run_ours(args):
         s_calls = torch.empty(len(c_values) * cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         s_n = torch.zeros(len(c_values), dtype=torch.int64, device=dev)
 
-        def sweep_noise():
+        thr_tables = torch.empty_like(views)
+
+        def sweep_noise_separate():
             for ci, cv in enumerate(c_values):
                 ctx.estimate_thresholds_dev(normals, cv, cut, out, twin_next, twin_head)
                 ctx.thresholds_caller_view_dev(out["thr"], views[ci])
+
+        def sweep_noise():   # shared passes over the normals: the first value alone, the other four together
+            ctx.estimate_thresholds_sweep_dev(normals, c_values, cut, thr_tables, out, twin_next, twin_head)
+            ctx.thresholds_caller_view_dev(thr_tables, views)
 
         def sweep_fused():
             s_n.zero_()
@@ -471,20 +477,26 @@ def run_ours(args):
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
 
+        t_sns = timed(sweep_noise_separate)
+        views_separate = views.clone()
         t_sn = timed(sweep_noise)
+        if not torch.equal(views.view(torch.int32), views_separate.view(torch.int32)):
+            raise RuntimeError("the fused noise sweep and the per-value passes disagree")
+        del views_separate
         t_sf = timed(sweep_fused)
         found_fused = [int(x) for x in s_n.tolist()]
         t_ss = timed(sweep_separate)
-        tt = torch.tensor([t_sn, t_sf, t_ss], dtype=torch.float64, device=dev)
+        tt = torch.tensor([t_sn, t_sf, t_ss, t_sns], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_sn, t_sf, t_ss = [float(x) for x in tt.tolist()]
-        sweep = {"C_values": c_values, "noise_ms_all_values": t_sn, "caller_ms_fused_one_pass": t_sf,
-                 "caller_ms_one_pass_per_value": t_ss, "calls_per_value_rank0": found_fused,
+        t_sn, t_sf, t_ss, t_sns = [float(x) for x in tt.tolist()]
+        sweep = {"C_values": c_values, "noise_ms_fused": t_sn, "noise_ms_one_pass_per_value": t_sns,
+                 "caller_ms_fused_one_pass": t_sf, "caller_ms_one_pass_per_value": t_ss, "calls_per_value_rank0": found_fused,
                  "tests_per_s_fused": 6.0 * T * P * world * len(c_values) / ((t_sn + t_sf) * 1e-3),
-                 "tests_per_s_separate": 6.0 * T * P * world * len(c_values) / ((t_sn + t_ss) * 1e-3),
-                 "api": "as_call_variants_sweep_dev (tumour tensor read once for all threshold tables)"}
-        del views, s_calls
+                 "tests_per_s_separate": 6.0 * T * P * world * len(c_values) / ((t_sns + t_ss) * 1e-3),
+                 "api": "as_noise_estimate_sweep_dev (normals read twice for five values) + as_call_variants_sweep_dev (tumour "
+                        "tensor read once for all threshold tables)"}
+        del views, s_calls, thr_tables
 
     # ---- end to end through the host-buffer C ABI ----------------------------------------------------
     e2e = None

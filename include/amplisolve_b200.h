@@ -110,6 +110,15 @@ int as_noise_estimate_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int6
                           uint32_t* d_nrec, void* stream);
 /* The _host forms also fill thr_view [P][4][2] when it is not NULL: the thresholds as the caller will parse them
  * (as_thresholds_caller_view_dev applied while the tile is still on the device). */
+/* Noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): the noise model for n_c values of C.  Only the sum of
+ * float(depth) * float(C) (EE:1617) depends on C, so the first value runs the plain kernels (all outputs; Germ_Max, count
+ * and nrec do not depend on C) and the others share passes over the normals, four values per pass.  c_values is a HOST
+ * array [n_c], 1 <= n_c <= 8; d_thr [n_c][P][4][2], table i = the thresholds as_noise_estimate_dev gives for c_values[i]
+ * (bit-identical; tested).  The other outputs as in as_noise_estimate_dev. */
+int as_noise_estimate_sweep_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int64_t P, int64_t slot_begin,
+                                int64_t slot_end, const int32_t* d_twin_next, const int32_t* d_twin_head,
+                                const float* c_values, int32_t n_c, int32_t cut, float* d_thr, float* d_germ_val,
+                                uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, void* stream);
 int as_noise_estimate_host(as_ctx* ctx, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,
                            const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
                            uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view);

@@ -426,6 +426,37 @@ def test_packed_host_entry_points_equal_the_32_bit_ones(ctx):
     assert (out["nrec"] == 0).all() and np.isnan(out["thr"]).all()
 
 
+@pytest.mark.parametrize("n_c", [2, 5, 8])
+@pytest.mark.parametrize("seed,big_rate,ragged", [(101, 0.0, False), (102, 0.01, True)])
+def test_noise_sweep_equals_one_pass_per_c_value(ctx, n_c, seed, big_rate, ragged):
+    """as_noise_estimate_sweep_dev: the threshold table of every C value from shared passes over the normals is bit-identical
+    to the plain noise model run with that value (twin pairs inside and across CTA tiles, longer chains, absent rows, counts
+    beyond 2^24), and so are the outputs that do not depend on C."""
+    import torch
+    _, slots, pos_id, U = synth.make_panel(60, seed=seed, overlap_frac=0.6, amp_len=(20, 70))
+    pos_id = pos_id.copy()
+    pos_id[-3] = pos_id[5]          # a position enumerated three times (general twin kernel)
+    P = len(slots)
+    normals, _ = synth.make_counts(21, P, depth=3000, seed=seed, pos_id=pos_id, big_rate=big_rate, ragged_twins=ragged)
+    nxt, head = ctx_twins(pos_id)
+    d_n = torch.from_numpy(normals.view(np.int32)).cuda()
+    d_nxt, d_head = torch.from_numpy(nxt).cuda(), torch.from_numpy(head).cuda()
+    c_values = [0.001, 0.0015, 0.002, 0.003, 0.004, 0.005, 0.0075, 0.01][:n_c]
+    thr = torch.full((n_c, P, 4, 2), -7.0, dtype=torch.float32, device="cuda")
+    out = ctx.alloc_noise_outputs(P)
+    ctx.estimate_thresholds_sweep_dev(d_n, c_values, 100, thr, out, d_nxt, d_head)
+    torch.cuda.synchronize()
+    thr = thr.cpu().numpy()
+    for ci, c in enumerate(c_values):
+        one = ctx.alloc_noise_outputs(P)
+        ctx.estimate_thresholds_dev(d_n, c, 100, one, d_nxt, d_head)
+        torch.cuda.synchronize()
+        assert np.array_equal(bits(thr[ci]), bits(one["thr"].cpu().numpy())), c
+        for k in ("germ_val", "germ_state", "count", "nrec"):
+            assert np.array_equal(out[k].cpu().numpy().view(np.uint8), one[k].cpu().numpy().view(np.uint8)), (c, k)
+    assert not np.array_equal(bits(thr[0]), bits(thr[-1]))
+
+
 def test_noise_floor_sweep_equals_one_pass_per_c_value(ctx):
     """as_call_variants_sweep_dev (BASELINE configs[3]: C_value 0.001 ... 0.005): one pass over the tumour tensor for all
     threshold tables gives, per table, exactly the call set of the plain caller run with that table -- and that is the

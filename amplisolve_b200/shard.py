@@ -61,5 +61,20 @@ def gather_calls(calls: np.ndarray, slot_offset: int, group=None, device=None) -
     dist.all_gather(out, buf, group=group)
     if rank != 0:
         return None
+    if dev.type == "cuda":   # merge on the device: one radix sort of 64-bit keys, one row gather, one download
+        rows = torch.cat([o[: s * CALL_DTYPE.itemsize] for o, s in zip(out, sizes)]).view(-1, CALL_DTYPE.itemsize)
+        return sort_calls_device(rows)
     parts = [o.cpu().numpy()[: s * CALL_DTYPE.itemsize].view(CALL_DTYPE) for o, s in zip(out, sizes)]
     return sort_calls(np.concatenate(parts))
+
+
+def sort_calls_device(rows) -> np.ndarray:
+    """rows: torch uint8 CUDA tensor [n][48] of as_call records -> numpy array in the reference's row order
+    (sample, slot, alt).  The key of a call is unique, so the order is total."""
+    import torch
+    if rows.shape[0] == 0:
+        return np.zeros(0, dtype=CALL_DTYPE)
+    head = rows[:, :12].contiguous().view(torch.int32).to(torch.int64)     # sample, slot, alt
+    key = (head[:, 0] << 33) | (head[:, 1] << 2) | (head[:, 2] & 3)
+    order = torch.argsort(key)
+    return rows.index_select(0, order).cpu().numpy().reshape(-1).view(CALL_DTYPE)

@@ -499,6 +499,23 @@ def test_noise_floor_sweep_equals_one_pass_per_c_value(ctx):
         check_calls(got, want, [np.nonzero(present[s])[0] for s in range(tumours.shape[0])])
 
 
+def test_device_merge_of_gathered_calls_equals_numpy_sort(ctx):
+    """shard.sort_calls_device (the NCCL path of gather_calls merges the ranks' lists on the device) == the numpy lexsort."""
+    import torch
+    from amplisolve_b200 import CALL_DTYPE
+    from amplisolve_b200.api import sort_calls
+    from amplisolve_b200.shard import sort_calls_device
+    rng = np.random.default_rng(4)
+    n = 50_000
+    calls = np.zeros(n, CALL_DTYPE)
+    keys = rng.choice(400 * 100_000 * 4, n, replace=False)
+    calls["sample"], calls["slot"], calls["alt"] = keys // 400_000, (keys // 4) % 100_000, keys % 4
+    calls["p_fw"], calls["q_bw"], calls["ref"] = rng.random(n), rng.random(n), rng.integers(0, 4, n)
+    rows = torch.from_numpy(calls.view(np.uint8).reshape(n, CALL_DTYPE.itemsize)).cuda()
+    assert sort_calls_device(rows).tobytes() == sort_calls(calls).tobytes()
+    assert len(sort_calls_device(rows[:0])) == 0
+
+
 def test_device_fisher_equals_host_and_boost(ctx):
     """as_fisher_tests_host (one warp per 2x2 table) against the scalar host form as_fisher_test and the
     Boost.Math-pinned fixture: p within 1e-13 relative of the host's (same lgamma values, device exp, lane-ordered sum),

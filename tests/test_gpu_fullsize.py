@@ -107,3 +107,32 @@ def test_random_slots_match_the_oracle_exactly(ctx, big):
     sub = np.sort(sub, order=["sample", "slot", "alt"])
     present = h_tum[:, 0, :, 0] != 0xFFFFFFFF
     check_calls(sub, wcalls, [np.nonzero(present[s])[0] for s in range(T)])
+
+
+@pytest.mark.parametrize("depth,c_value,n_slots,n_tumours", [(2000.0, 0.002, 2_000_000, 24), (2000.0, 0.001, 500_000, 24),
+                                                             (50000.0, 0.002, 100_000, 400)])
+def test_screened_caller_equals_the_straightforward_kernel_at_full_size(ctx, depth, c_value, n_slots, n_tumours):
+    """The default caller (integer pre-screen in the scan, continued-fraction and critical-mean screens in the revisit)
+    against call_naive_kernel, which evaluates every strand test with the full arithmetic: identical call lists, byte for
+    byte, over whole shards at the c3 depth (two noise floors: at 0.001 most means are of order 1, the regime of the
+    critical-mean screen) and at the c5 depth."""
+    import torch
+    gen = dict(seed=20199, mean_depth=depth, twin_period=6, absent_rate=0.01)
+    normals, ref = ctx.synth_counts_dev(40, n_slots, **gen)
+    tumours, _ = ctx.synth_counts_dev(n_tumours, n_slots, somatic_rate=5e-4, vaf=(0.005, 0.2), sample_offset=1 << 20,
+                                      want_ref=False, **gen)
+    nxt, head = ctx.synth_twin_links_dev(n_slots, seed=20199, twin_period=6)
+    out = ctx.alloc_noise_outputs(n_slots)
+    ctx.estimate_thresholds_dev(normals, c_value, 100, out, nxt, head)
+    view = ctx.thresholds_caller_view_dev(out["thr"])
+    torch.cuda.synchronize()
+    del normals
+    lists = {}
+    for variant in (-1, 0):
+        ctx.set_call_kernel(variant)
+        try:
+            lists[variant] = run_calls(ctx, tumours, ref, view, cap=4_000_000)
+        finally:
+            ctx.set_call_kernel(-1)
+    assert len(lists[0]) > 1000
+    assert lists[-1].tobytes() == lists[0].tobytes()

@@ -101,7 +101,7 @@ __device__ __forceinline__ double q_from_p(double p) {
 // The reference compares the x87 long double Q = -10*log10l(p) with 5 (VC:898).  As a predicate on the
 // double p that is a threshold: Q >= 5 <=> p <= AS_P_STAR, where AS_P_STAR = 0x3FD43D136248490E is the
 // largest double for which glibc's x87 evaluation gives Q >= 5 (found by bisection over the doubles,
-// tests/test_oracle_vs_ref.py pins it against the compiled reference; plain fp64 log10 would accept one
+// tests/test_oracle_golden.py pins it against the compiled reference; plain fp64 log10 would accept one
 // more double).  p < 1e-10 gives Q = 100, NaN gives NaN >= 5 = false.
 #define AS_P_STAR_BITS 0x3FD43D136248490Eull
 __device__ __forceinline__ bool q_at_least_5(double p) { return p <= __longlong_as_double(AS_P_STAR_BITS); }

@@ -687,7 +687,7 @@ __device__ __forceinline__ void load_slot_const(CallSlotConst& c, const float* _
 // exact screen of SURVEY.md B.6(3): on the continued-fraction branch of VC:3728 (m >= k and m > 1) the
 // reference's Q never reaches 5 (p = P(X >= k) >= 1/2 for a Poisson mean m >= k; validated against the
 // compiled reference including the region where its 99-step cap leaves the fraction unconverged,
-// tests/test_screens.py), so such a strand test can only veto the call.
+// tests/test_oracle_golden.py::test_screen_continued_fraction_branch_never_calls), so such a strand test can only veto the call.
 //
 // Second exact screen, for small k: p = P(X >= k | m) grows with m, so there is a critical mean m*(k) with
 // p(k, m*) = P* (the largest p whose Q reaches 5, as_device.cuh) and a strand test with m above it cannot pass.

@@ -200,3 +200,37 @@ def test_toy_data_end_to_end_against_reference(tmp_path):
     lines = gu.noise_table_lines(case, nz["thr"][pos_id], nz["germ_val"][pos_id], nz["germ_present"][pos_id])
     assert lines == want
     assert len(want) == 41487
+
+
+@needs_ref
+def test_screen_critical_mean_never_calls():
+    """The second exact screen of the caller (AS_MCRIT, scripts/critical_means.py): for k = 1..64 and every mean from the
+    table value m*(k)(1 + 1e-9) up to 3k, the compiled reference's Q stays below 5 -- on the series branch (m < k), at
+    m <= 1 (k = 1) and on the continued-fraction branch alike; a hair below m*(k) it reaches 5.  e = 2^-20 makes
+    m = depth * e exact."""
+    import sys
+    sys.path.insert(0, str(ROOT / "scripts"))
+    from critical_means import critical_means
+    L = C.CDLL(str(ROOT / "oracle" / "_ref" / "libvc_ref_funcs.so"))
+    mc = np.array(critical_means())
+    ks, depths = [], []
+    for k in range(1, 65):
+        lo = int(np.ceil(mc[k - 1] * 2 ** 20))
+        grid = np.unique(np.concatenate([lo + np.arange(0, 200), np.geomspace(lo, 3 * k * 2 ** 20 + lo, 400).astype(np.int64)]))
+        ks.append(np.full(len(grid), k))
+        depths.append(grid)
+    k = np.concatenate(ks).astype(np.int32)
+    rd = np.concatenate(depths).astype(np.int32)
+    err = np.full(len(k), 2.0 ** -20, np.float32)
+    q = np.empty(len(k), np.float64)
+    L.ref_poisson_q_vec(k.ctypes.data_as(C.c_void_p), rd.ctypes.data_as(C.c_void_p), err.ctypes.data_as(C.c_void_p),
+                        q.ctypes.data_as(C.c_void_p), C.c_long(len(k)))
+    assert len(k) > 30000 and (q < 5).all(), (k[q >= 5][:5], rd[q >= 5][:5])
+    # just below the critical mean the strand test passes: the table is tight, not merely safe
+    kb = np.arange(1, 65, dtype=np.int32)
+    rb = np.floor(mc / (1 + 1e-9) * (1 - 3e-6) * 2 ** 20).astype(np.int32)
+    qb = np.empty(64, np.float64)
+    eb = np.full(64, 2.0 ** -20, np.float32)
+    L.ref_poisson_q_vec(kb.ctypes.data_as(C.c_void_p), rb.ctypes.data_as(C.c_void_p), eb.ctypes.data_as(C.c_void_p),
+                        qb.ctypes.data_as(C.c_void_p), C.c_long(64))
+    assert (qb >= 5).all()

@@ -27,7 +27,7 @@ assert CALL_DTYPE.itemsize == 48
 
 EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
-    "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
+    "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_set_option", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
     "as_call_variants_host16", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
@@ -144,6 +144,7 @@ def lib():
     L.as_set_call_kernel.argtypes = [vp, C.c_int]
     L.as_set_noise_kernel.argtypes = [vp, C.c_int]
     L.as_set_host_tile_slots.argtypes = [vp, i64]
+    L.as_set_option.argtypes = [vp, C.c_char_p, i64]
     L.as_kernel_launches.argtypes = [vp]
     L.as_kernel_launches.restype = i64
     L.as_noise_estimate_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
@@ -269,6 +270,9 @@ class Context:
 
     def set_host_tile_slots(self, slots: int):
         _check(lib().as_set_host_tile_slots(self._h, slots))
+
+    def set_option(self, name: str, value: int):
+        _check(lib().as_set_option(self._h, name.encode(), int(value)))
 
     # ---- host-buffer entry points --------------------------------------------------------------
     def _pinned_array(self, name, shape, dtype):

@@ -18,11 +18,17 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libamplisolve_b200.so"
 BIN = PKG / "bin"
-CU_SOURCES = ["as_kernels.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu"]
+OBJ = PKG / "lib" / "obj"
+CU_SOURCES = ["as_kernels.cu", "as_noise_pattern.cu", "as_call_deferred.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu"]
 CXX_SOURCES = ["as_host.cpp"]
-HEADERS = ["as_device.cuh", "as_noise.cuh", "as_pipeline.cuh", "as_kernels.h", "as_wire.h", "../../include/amplisolve_b200.h"]
+HEADERS = ["as_device.cuh", "as_noise.cuh", "as_pipeline.cuh", "as_call.cuh", "as_kernels.h", "as_wire.h",
+           "../../include/amplisolve_b200.h"]
+# -cudart shared: the CUDA runtime is NOT linked into the product library (a static runtime would carry every runtime entry
+# point, used or not, into libamplisolve_b200.so); libcudart.so.12 comes from the toolkit (rpath) or from the process
+# (torch loads its own copy first in bench.py / the tests -- every runtime symbol this library imports exists there).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-cudart", "static"]
+              "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-cudart", "shared"]
+CUDA_LIB_DIRS = ["/usr/local/cuda/lib64"]
 
 
 def nvcc() -> str:
@@ -39,19 +45,51 @@ def _stale(target: Path, deps) -> bool:
     return any(Path(d).stat().st_mtime > t for d in deps)
 
 
+def _compile(src: Path, obj: Path, verbose: bool):
+    cmd = [nvcc(), *NVCC_FLAGS, "-c", "-o", str(obj), str(src), "-I", str(ROOT / "include")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    return src, r
+
+
+def check_no_batch_memcpy(paths) -> None:
+    """The shipped binaries must not carry the batched-memcpy entry points of the CUDA runtime (they would only be there
+    through a statically linked runtime: this library copies with plain cudaMemcpyAsync / cudaMemcpy2DAsync)."""
+    import re
+    pat = re.compile(rb"Memcpy(3D)?BatchAsync")
+    for p in paths:
+        if Path(p).exists() and pat.search(Path(p).read_bytes()):
+            raise RuntimeError(f"{p} contains a batched-memcpy runtime symbol: link the CUDA runtime dynamically (-cudart shared)")
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    from concurrent.futures import ThreadPoolExecutor
     srcs = [CSRC / s for s in CU_SOURCES + CXX_SOURCES]
-    deps = srcs + [CSRC / h for h in HEADERS] + [Path(__file__)]
-    if force or _stale(LIB, deps):
-        LIB.parent.mkdir(parents=True, exist_ok=True)
-        cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, srcs), "-I", str(ROOT / "include")]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
+    hdrs = [CSRC / h for h in HEADERS] + [Path(__file__)]
+    OBJ.mkdir(parents=True, exist_ok=True)
+    jobs = []
+    for src in srcs:
+        obj = OBJ / (src.stem + ".o")
+        if force or _stale(obj, [src] + hdrs):
+            jobs.append((src, obj))
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for src, r in pool.map(lambda j: _compile(j[0], j[1], verbose), jobs):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(f"== {src.name}\n" + r.stdout + r.stderr)
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed compiling {src.name}")
+    objs = [OBJ / (src.stem + ".o") for src in srcs]
+    if force or jobs or _stale(LIB, objs):
+        cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, objs)]
+        for d in CUDA_LIB_DIRS:
+            cmd += ["-Xlinker", f"-rpath={d}"]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        if verbose or r.returncode != 0:
-            sys.stderr.write(r.stdout + r.stderr)
         if r.returncode != 0:
-            raise RuntimeError("nvcc failed building libamplisolve_b200.so")
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed linking libamplisolve_b200.so")
+    check_no_batch_memcpy([LIB])
     mains = CSRC / "as_main.cpp"
     if mains.exists():
         BIN.mkdir(exist_ok=True)

@@ -91,11 +91,13 @@ struct as_ctx {
     int noise_cfg = AS_DEFAULT_NOISE_KERNEL;      // 0 direct loads, >= 1 TMA-staged (K, stages) variants
     int64_t launches = 0;
     int64_t host_tile_slots = 0;  // 0 = automatic
+    int64_t defer_cap_override = 0;  // > 0: capacity of the deferred caller's candidate list (tests of the overflow path)
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
     DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls, sortbuf;  // _host pipelines
+    DevBuf defer;                                                              // candidate / survivor lists of the deferred caller
     DevBuf lgtab;                                                              // lgamma(i + 1), i < lg_n (as_fisher_tests_host)
     int64_t lg_n = 0;
     PinnedGrow h_links, h_small;                                              // _host pipelines, host side
@@ -155,7 +157,7 @@ void as_destroy(as_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release(); c->sortbuf.release();
-    c->h_links.release(); c->h_small.release(); c->lgtab.release();
+    c->h_links.release(); c->h_small.release(); c->lgtab.release(); c->defer.release();
     for (int i = 0; i < 2; ++i) {
         c->tile[i].release(); c->tile16[i].release(); c->wide[i].release(); c->out[i].release(); c->aux[i].release();
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
@@ -179,17 +181,30 @@ int as_host_free(void* p) {
     return AS_OK;
 }
 
+int as_set_host_tile_slots(as_ctx* c, int64_t slots);
 int as_set_call_kernel(as_ctx* c, int variant) {
-    if (!c || variant < -1 || variant > 16) return fail(AS_EINVAL, "bad call kernel variant");
+    if (!c || variant < -1 || variant > 20) return fail(AS_EINVAL, "bad call kernel variant");
     c->call_variant = variant < 0 ? AS_DEFAULT_CALL_KERNEL : variant;
     return AS_OK;
 }
 int as_set_noise_kernel(as_ctx* c, int variant) {
-    if (!c || variant < -1 || variant > 6) return fail(AS_EINVAL, "bad noise kernel variant");
+    if (!c || variant < -1 || variant > 11) return fail(AS_EINVAL, "bad noise kernel variant");
     c->noise_cfg = variant < 0 ? AS_DEFAULT_NOISE_KERNEL : variant;
     return AS_OK;
 }
 int64_t as_kernel_launches(const as_ctx* c) { return c ? c->launches : 0; }
+int as_set_option(as_ctx* c, const char* name, int64_t value) {
+    if (!c || !name) return fail(AS_EINVAL, "bad argument");
+    if (!strcmp(name, "call_kernel")) return as_set_call_kernel(c, (int)value);
+    if (!strcmp(name, "noise_kernel")) return as_set_noise_kernel(c, (int)value);
+    if (!strcmp(name, "host_tile_slots")) return as_set_host_tile_slots(c, value);
+    if (!strcmp(name, "deferred_capacity")) {
+        if (value < 0) return fail(AS_EINVAL, "deferred_capacity must be >= 0 (0 = automatic)");
+        c->defer_cap_override = value;
+        return AS_OK;
+    }
+    return fail(AS_EINVAL, "unknown option %s", name);
+}
 int as_set_host_tile_slots(as_ctx* c, int64_t slots) {
     if (!c || slots < 0 || (slots % 128) != 0) return fail(AS_EINVAL, "host tile size must be 0 (automatic) or a multiple of 128 slots");
     c->host_tile_slots = slots;
@@ -245,27 +260,37 @@ int as_noise_estimate_sweep_dev(as_ctx* c, const uint32_t* d_counts, int32_t S, 
                                 int32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count,
                                 uint32_t* d_nrec, void* stream) {
     if (!c_values || n_c < 1 || n_c > 8) return fail(AS_EINVAL, "a sweep takes 1..8 values of C");
-    // the first value: every output, twin groups on the side stream, joined before control returns to `stream`
-    int rc = as_noise_estimate_dev(c, d_counts, S, P, b, e, d_twin_next, d_twin_head, c_values[0], cut, d_thr, d_germ_val,
-                                   d_germ_state, d_count, d_nrec, stream);
-    if (rc != AS_OK || n_c == 1) return rc;
+    int rc = check_common(c, d_counts, S, P, b, e, cut);
+    if (rc) return rc;
+    if (!d_thr || !d_germ_val || !d_germ_state || !d_count || !d_nrec) return fail(AS_EINVAL, "output pointer is NULL");
+    if ((d_twin_next == nullptr) != (d_twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
+    CU(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t stride = P * 8;
-    for (int32_t i = 1; i < n_c; i += 4) {  // up to four further values per pass over the normals
-        const int32_t m = std::min<int32_t>(4, n_c - i);
-        CU(as_launch_noise_sweep(d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, c_values + i, m, (uint32_t)cut,
-                                 d_thr + (int64_t)i * stride, stride, st));
-        c->launches += 1;
-    }
     if (d_twin_next) {
-        // twin groups the streaming kernels leave out (pairs cut by a CTA tile, longer chains): a few slots, value by value.
-        // They rewrite Germ_Max / count / nrec of those slots with the same values.
-        for (int32_t i = 1; i < n_c; ++i) {
-            CU(as_launch_noise_twins(AS_DEFAULT_NOISE_KERNEL, d_counts, S, P, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p,
-                                     (uint32_t*)c->nheads.p, c_values[i], (uint32_t)cut, d_thr + (int64_t)i * stride, d_germ_val,
-                                     d_germ_state, d_count, d_nrec, st));
-            c->launches += 3;
+        CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((e - b + 1) / 2 + 1)));
+        CU(c->nheads.need(2 * sizeof(uint32_t)));
+        CU(cudaEventRecord(c->ev_fork, st));
+    }
+    // ONE pass over the normals for all values (noise_pattern_kernel): every output, in-tile twin pairs included
+    const int geom = c->noise_cfg >= 7 ? c->noise_cfg - 7 : 0;
+    CU(as_launch_noise_pattern(geom, d_counts, S, P, b, e, d_twin_next, d_twin_head, 0, c_values, n_c, (uint32_t)cut, d_thr, stride,
+                               d_germ_val, d_germ_state, d_count, d_nrec, st));
+    c->launches += 1;
+    if (d_twin_next) {
+        // the twin groups it leaves out (pairs cut by a CTA tile, longer chains: a few slots, scattered reads) run beside it
+        // on the side stream, value by value; they rewrite Germ_Max / count / nrec of those slots with the same values
+        CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        CU(as_launch_twin_heads(7, b, e, d_twin_next, d_twin_head, (int32_t*)c->heads.p, (uint32_t*)c->nheads.p, c->aux_stream));
+        c->launches += 1;
+        for (int32_t i = 0; i < n_c; ++i) {
+            CU(as_launch_noise_twin_groups(d_counts, S, P, b, e, d_twin_next, (const int32_t*)c->heads.p, (const uint32_t*)c->nheads.p,
+                                           c_values[i], (uint32_t)cut, d_thr + (int64_t)i * stride, d_germ_val, d_germ_state, d_count,
+                                           d_nrec, c->aux_stream));
+            c->launches += 2;
         }
+        CU(cudaEventRecord(c->ev_join, c->aux_stream));
+        CU(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
     return AS_OK;
 }
@@ -603,6 +628,20 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
 }
 
 // ---- caller ----------------------------------------------------------------------------------------
+// the caller as scan -> resolve -> series kernels (as_call_deferred.cu), lists in scratch owned by the context
+static int call_deferred(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t P, int64_t b, int64_t e, const uint8_t* d_ref,
+                         const float* d_thr_views, int32_t n_c, int32_t cut, as_call* d_calls, int64_t cap,
+                         unsigned long long* d_n_calls, cudaStream_t st) {
+    int64_t cap_cand = 0, cap_surv = 0;
+    const size_t bytes = as_deferred_scratch_bytes(T, e - b, &cap_cand, &cap_surv) + 256;
+    if (c->defer_cap_override > 0) { cap_cand = c->defer_cap_override; cap_surv = std::max<int64_t>(1, cap_cand / 4); }
+    CU(c->defer.need(bytes));
+    CU(as_launch_call_deferred(d_counts, T, P, b, e, d_ref, d_thr_views, n_c, P * 8, (uint32_t)cut, d_calls, cap, d_n_calls, c->defer.p,
+                               cap_cand, cap_surv, st));
+    c->launches += 3;
+    return AS_OK;
+}
+
 int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t P, int64_t b, int64_t e,
                          const uint8_t* d_ref, const float* d_thr_view, int32_t cut, as_call* d_calls, int64_t cap,
                          unsigned long long* d_n_calls, void* stream) {
@@ -611,6 +650,8 @@ int as_call_variants_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t
     if (!d_ref || !d_thr_view || !d_n_calls || (!d_calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
     if (T >= (1 << 27)) return fail(AS_EINVAL, "at most 2^27-1 samples per call");
     CU(cudaSetDevice(c->device));
+    if (c->call_variant == AS_DEFERRED_CALL_KERNEL)
+        return call_deferred(c, d_counts, T, P, b, e, d_ref, d_thr_view, 1, cut, d_calls, cap, d_n_calls, (cudaStream_t)stream);
     CU(as_launch_call(c->call_variant, d_counts, T, P, b, e, d_ref, d_thr_view, (uint32_t)cut, d_calls, cap, d_n_calls,
                       (cudaStream_t)stream));
     c->launches += 1;
@@ -627,6 +668,9 @@ int as_call_variants_sweep_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, i
     if (T >= (1 << 27)) return fail(AS_EINVAL, "at most 2^27-1 samples per call");
     if (c->call_variant < 2 && n_c > 1) return fail(AS_EINVAL, "the sweep needs a TMA-staged caller variant (>= 2)");
     CU(cudaSetDevice(c->device));
+    // default: the deferred pipeline; a staged variant selected by hand runs the in-stage sweep kernel (cross-check)
+    if (c->call_variant == AS_DEFERRED_CALL_KERNEL || (c->call_variant == AS_DEFAULT_CALL_KERNEL && n_c > 1))
+        return call_deferred(c, d_counts, T, P, b, e, d_ref, d_thr_views, n_c, cut, d_calls, cap, d_n_calls, (cudaStream_t)stream);
     CU(as_launch_call_sweep(c->call_variant, d_counts, T, P, b, e, d_ref, d_thr_views, n_c, P * 8, (uint32_t)cut, d_calls, cap,
                             d_n_calls, (cudaStream_t)stream));
     c->launches += 1;

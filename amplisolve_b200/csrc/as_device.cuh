@@ -14,6 +14,19 @@
 
 namespace asdev {
 
+// 128-bit streaming load: read-only path, do not allocate in L1 (every record is read exactly once).
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4& v, int i) {
+    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
+}
+
 #define AS_KF_EPS 1e-14   /* VC:149 */
 #define AS_KF_TINY 1e-290 /* VC:150 */
 

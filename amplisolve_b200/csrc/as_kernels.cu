@@ -15,17 +15,9 @@
 #include "as_device.cuh"
 #include "as_noise.cuh"
 #include "as_pipeline.cuh"
+#include "as_call.cuh"
 
 namespace asdev {
-
-// 128-bit streaming load: read-only path, do not allocate in L1 (every record is read exactly once).
-__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
 
 // ------------------------------------------------------------------------------------------------
 // noise model, singleton slots: one thread per slot, all normals in sequence
@@ -203,229 +195,6 @@ noise_staged_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t 
         if (role == 2) active = false;  // stored by the first slot's thread
     }
     if (active) noise_finish_slot(f, counts + p, S, P, C, cut, p, role == 1 ? twin_d : 0, thr, germ_val, germ_state, count, nrec);
-}
-
-// ------------------------------------------------------------------------------------------------
-// noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): thresholds for NC further C values in ONE pass
-// over the normals.  Only the sum of float(depth) * float(C) (EE:1617) depends on C; the filter, the alt-read and depth
-// sums and the counts are shared.  Germ_Max, count and nrec do not depend on C at all and come from the plain kernel
-// run with the first value.  Same ring, same fast-path arithmetic, same handling of twin pairs inside the tile (sums
-// simply add here); slots of other twin groups are left to noise_pair_kernel / noise_twin_kernel, per value.
-// ------------------------------------------------------------------------------------------------
-#define AS_SWEEP_NC 4
-struct SweepC {
-    float c[AS_SWEEP_NC];
-};
-struct SweepBase {
-    uint32_t s_b_fw, s_b_bw;                      // 32-bit partial sums of alt reads (folded like FastBase)
-    double s_d_fw, s_d_bw;                        // strand depth
-    double s_p_fw[AS_SWEEP_NC], s_p_bw[AS_SWEEP_NC];  // float(depth) * float(C) per value, plus the folded alt-read sums
-    uint32_t count;
-};
-struct SweepAcc {
-    SweepBase b[4];
-    uint32_t nrec, big;
-};
-struct SweepXfer {  // what the second slot of a twin pair hands to the first (after the fold: s_b is zero)
-    double d[4][2], p[4][2][AS_SWEEP_NC];
-    uint32_t count[4], nrec, big;
-};
-
-__device__ __forceinline__ void sweep_fold(SweepAcc& a) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const double bf = u32_to_double(a.b[i].s_b_fw), bb = u32_to_double(a.b[i].s_b_bw);
-#pragma unroll
-        for (int c = 0; c < AS_SWEEP_NC; ++c) {
-            a.b[i].s_p_fw[c] = __dadd_rn(a.b[i].s_p_fw[c], bf);
-            a.b[i].s_p_bw[c] = __dadd_rn(a.b[i].s_p_bw[c], bb);
-        }
-        a.b[i].s_b_fw = a.b[i].s_b_bw = 0u;
-    }
-}
-
-__device__ __forceinline__ void sweep_store(const SweepBase (&b)[4], uint32_t n_records, int n_c, int64_t slot,
-                                            float* __restrict__ thr, int64_t thr_stride) {
-#pragma unroll  // (a run-time index into s_p would put the whole accumulator into local memory)
-    for (int c = 0; c < AS_SWEEP_NC; ++c) {
-        if (c >= n_c) break;
-        float t[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            NoiseBase nb;
-            nb.s_b_fw = nb.s_b_bw = 0ull;  // folded into s_p
-            nb.s_d_fw = (unsigned long long)__double2ll_rn(b[i].s_d_fw);
-            nb.s_d_bw = (unsigned long long)__double2ll_rn(b[i].s_d_bw);
-            nb.s_p_fw = b[i].s_p_fw[c]; nb.s_p_bw = b[i].s_p_bw[c];
-            nb.count = b[i].count;
-            nb.g_n = 0; nb.g_x = 0; nb.g_rd = 1; nb.g_first_x = 0; nb.g_first_rd = 1;
-            float g;
-            uint32_t st;
-            noise_final_base(nb, n_records, i, t[2 * i], t[2 * i + 1], g, st);
-        }
-        float4* t4 = reinterpret_cast<float4*>(thr + c * thr_stride + slot * 8);
-        t4[0] = make_float4(t[0], t[1], t[2], t[3]);
-        t4[1] = make_float4(t[4], t[5], t[6], t[7]);
-    }
-}
-
-template <int K, int STAGES>
-__global__ void __launch_bounds__(AS_CTA_THREADS, 3)
-noise_sweep_kernel(const uint4* __restrict__ counts, int S, int64_t P, int64_t p0, int64_t p1,
-                   const int32_t* __restrict__ twin_next, const int32_t* __restrict__ twin_head, int64_t twin_base,
-                   SweepC cs, int n_c, uint32_t cut, float* __restrict__ thr, int64_t thr_stride) {
-    static_assert(StageRing<K, STAGES>::kStageBytes * STAGES >= AS_TILE_SLOTS * (int)sizeof(SweepXfer), "hand-over block of twin pairs");
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * STAGES];
-    StageRing<K, STAGES> ring;
-    ring.init(smem_raw, bars);
-    const int64_t tile0 = p0 + (int64_t)blockIdx.x * AS_TILE_SLOTS;
-    const int n_slots = (int)min((int64_t)AS_TILE_SLOTS, p1 - tile0);
-    const int tid = threadIdx.x;
-    if (tid >= AS_TILE_SLOTS) {  // producer warp
-        if (tid == AS_TILE_SLOTS) ring.produce(counts + tile0, 2 * P, P, 0, S, n_slots);
-        return;
-    }
-    const int64_t p = tile0 + tid;
-    bool active = tid < n_slots;
-    int role = 0, twin_d = 0;  // as in noise_staged_kernel
-    if (active && twin_next != nullptr) {
-        const int64_t gid = p + twin_base;
-        if (twin_next[p] >= 0 || twin_head[p] != (int32_t)gid) role = 3;
-        twin_d = intile_twin_distance(twin_next, twin_head, p, gid, tid, n_slots);
-        if (twin_d > 0) {
-            role = 1;
-        } else if (role == 3) {
-            const int64_t back = gid - (int64_t)twin_head[p];
-            if (back > 0 && back <= tid && intile_twin_distance(twin_next, twin_head, p - back, gid - back, tid - (int)back, n_slots) == (int)back)
-                role = 2;
-        }
-        if (role == 3) active = false;
-    }
-
-    SweepAcc f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f.b[i].s_b_fw = f.b[i].s_b_bw = 0u;
-        f.b[i].s_d_fw = f.b[i].s_d_bw = 0.0;
-        f.b[i].count = 0u;
-#pragma unroll
-        for (int c = 0; c < AS_SWEEP_NC; ++c) f.b[i].s_p_fw[c] = f.b[i].s_p_bw[c] = 0.0;
-    }
-    f.nrec = 0; f.big = 0;
-    int it = 0, since_fold = 0;
-    for (int t = 0; t < S; t += K, ++it) {
-        const uint4* st = ring.consumer_wait(it);
-        const int k = min(K, S - t);
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                if (j < k) {
-                    const uint4 fw = st[(j * 2 + 0) * AS_TILE_SLOTS + tid];
-                    const uint4 bw = st[(j * 2 + 1) * AS_TILE_SLOTS + tid];
-                    if ((int32_t)fw.x >= 0) {  // not AS_ABSENT
-                        f.nrec += 1;
-                        FastRecord r;
-                        fast_record(r, fw, bw, cs.c[0], cut);
-                        f.big |= r.RD;
-                        const float Ff = __uint2float_rn(fw.x + fw.y + fw.z + fw.w), Bf = __uint2float_rn(bw.x + bw.y + bw.z + bw.w);
-                        double pf[AS_SWEEP_NC], pb[AS_SWEEP_NC];
-#pragma unroll
-                        for (int c = 0; c < AS_SWEEP_NC; ++c) {  // EE:1617: fp32 product, then widened
-                            pf[c] = (double)__fmul_rn(Ff, cs.c[c]);
-                            pb[c] = (double)__fmul_rn(Bf, cs.c[c]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            SweepBase& sb = f.b[i];
-                            const uint32_t bf = comp(fw, i), bb = comp(bw, i);
-                            if (((int32_t)bf <= r.lim_fw) & ((int32_t)bb <= r.lim_bw)) {  // EE:1613-1615
-                                sb.s_b_fw += bf; sb.s_b_bw += bb;
-                                sb.s_d_fw = __dadd_rn(sb.s_d_fw, r.d_fw); sb.s_d_bw = __dadd_rn(sb.s_d_bw, r.d_bw);
-#pragma unroll
-                                for (int c = 0; c < AS_SWEEP_NC; ++c) {
-                                    sb.s_p_fw[c] = __dadd_rn(sb.s_p_fw[c], pf[c]);
-                                    sb.s_p_bw[c] = __dadd_rn(sb.s_p_bw[c], pb[c]);
-                                }
-                                sb.count += 1;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        ring.consumer_release(it);
-        since_fold += K;
-        if (since_fold >= AS_FOLD_EVERY) { sweep_fold(f); since_fold = 0; }
-    }
-    sweep_fold(f);
-
-    if (twin_next != nullptr) {  // twin pairs inside the tile: the second slot's sums join the first slot's
-        SweepXfer* xfer = reinterpret_cast<SweepXfer*>(smem_raw);
-        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");  // every consumer warp is done with the ring
-        if (role == 2) {
-            SweepXfer& o = xfer[tid];
-            o.nrec = f.nrec; o.big = f.big;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                o.d[i][0] = f.b[i].s_d_fw; o.d[i][1] = f.b[i].s_d_bw;
-                o.count[i] = f.b[i].count;
-#pragma unroll
-                for (int c = 0; c < AS_SWEEP_NC; ++c) { o.p[i][0][c] = f.b[i].s_p_fw[c]; o.p[i][1][c] = f.b[i].s_p_bw[c]; }
-            }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(AS_TILE_SLOTS) : "memory");
-        if (role == 1) {
-            const SweepXfer& o = xfer[tid + twin_d];
-            f.nrec += o.nrec;
-            f.big |= o.big;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                f.b[i].s_d_fw = __dadd_rn(f.b[i].s_d_fw, o.d[i][0]); f.b[i].s_d_bw = __dadd_rn(f.b[i].s_d_bw, o.d[i][1]);
-                f.b[i].count += o.count[i];
-#pragma unroll
-                for (int c = 0; c < AS_SWEEP_NC; ++c) {
-                    f.b[i].s_p_fw[c] = __dadd_rn(f.b[i].s_p_fw[c], o.p[i][0][c]);
-                    f.b[i].s_p_bw[c] = __dadd_rn(f.b[i].s_p_bw[c], o.p[i][1][c]);
-                }
-            }
-        }
-        if (role == 2) active = false;  // stored by the first slot's thread
-    }
-    if (!active) return;
-    const int tw = role == 1 ? twin_d : 0;
-    if (f.big < (1u << 24)) {
-        sweep_store(f.b, f.nrec, n_c, p, thr, thr_stride);
-        if (tw > 0) sweep_store(f.b, f.nrec, n_c, p + tw, thr, thr_stride);
-    } else {
-        // a depth of 2^24 or more: int -> float is inexact, redo the slot with the general code, value by value
-        const uint4* q = counts + p;
-        for (int c = 0; c < n_c; ++c) {
-            NoiseAcc acc;
-            noise_init(acc);
-#pragma unroll 1
-            for (int s = 0; s < S; ++s) {
-#pragma unroll 1
-                for (int r = 0; r <= (tw > 0 ? 1 : 0); ++r) {
-                    const uint4 fw = ld_stream(q + (int64_t)s * 2 * P + r * tw);
-                    const uint4 bw = ld_stream(q + (int64_t)s * 2 * P + P + r * tw);
-                    noise_accumulate<false>(acc, fw, bw, cs.c[c], cut);
-                }
-            }
-            float t[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float g;
-                uint32_t st;
-                noise_final_base(acc.b[i], acc.nrec, i, t[2 * i], t[2 * i + 1], g, st);
-            }
-            for (int r = 0; r <= (tw > 0 ? 1 : 0); ++r) {
-                float4* t4 = reinterpret_cast<float4*>(thr + c * thr_stride + (p + r * tw) * 8);
-                t4[0] = make_float4(t[0], t[1], t[2], t[3]);
-                t4[1] = make_float4(t[4], t[5], t[6], t[7]);
-            }
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -684,59 +453,6 @@ __device__ __forceinline__ void load_slot_const(CallSlotConst& c, const float* _
     c.ref = ref[p];
 }
 
-// exact screen of SURVEY.md B.6(3): on the continued-fraction branch of VC:3728 (m >= k and m > 1) the
-// reference's Q never reaches 5 (p = P(X >= k) >= 1/2 for a Poisson mean m >= k; validated against the
-// compiled reference including the region where its 99-step cap leaves the fraction unconverged,
-// tests/test_oracle_golden.py::test_screen_continued_fraction_branch_never_calls), so such a strand test can only veto the call.
-//
-// Second exact screen, for small k: p = P(X >= k | m) grows with m, so there is a critical mean m*(k) with
-// p(k, m*) = P* (the largest p whose Q reaches 5, as_device.cuh) and a strand test with m above it cannot pass.
-// AS_MCRIT[k-1] = m*(k) * (1 + 1e-9), k = 1..64, m* solved to 40 digits (mpmath; scripts/critical_means.py).  Between
-// m*(k) and k the reference evaluates the series of VC:3785-3794 (z < s), whose p is within 1.5e-13 relative of the exact
-// value there (measured against mpmath over k = 1..64); the 1e-9 margin in m is a margin of >= 5e-10 relative in p, so
-// m >= AS_MCRIT[k-1] implies that the reference's own p exceeds P*.  Pairs inside the margin go to the series as before.
-// This matters where depth * e is of order 1 (low noise floors, shallow positions): there "m >= k" never fires and
-// every candidate with one or two alt reads would otherwise cost a full fp64 series only to be rejected.
-__device__ const double AS_MCRIT[64] = {
-    0.3801304084463019, 1.1417568666028408, 1.9737827925528142, 2.836655303617698,
-    3.717842035557975, 4.6115129863431354, 5.514398678438836, 6.4244483020565735,
-    7.340275226714001, 8.26088993116463, 9.185556927304383, 10.113711843311759,
-    11.044910368246212, 11.978795260900911, 12.915074175299806, 13.853504259954532,
-    14.793881161100241, 15.736030981805042, 16.679804280096405, 17.62507150754917,
-    18.571719486996063, 19.519648653852276, 20.468770867935323, 21.419007657863915,
-    22.370288797876483, 23.322551143218725, 24.275737668892344, 25.229796669971126,
-    26.184681091478662, 27.14034796305633, 28.096757919060714, 29.05387478882073,
-    30.01166524490941, 30.97009849969475, 31.929146042307917, 32.888781409637,
-    33.84897998611586, 34.80971882800224, 35.77097650858012, 36.73273298131915,
-    37.694969458508524, 38.657668303278726, 39.62081293324896, 40.58438773430595,
-    41.548377983241544, 42.51276977816144, 43.4775499757315, 44.44270613445805,
-    45.40822646330781, 46.37409977506551, 47.34031544390594, 48.30686336672417,
-    49.273733927824765, 50.240917966620174, 51.208406748030676, 52.17619193531465,
-    53.14426556508969, 54.11262002433242, 55.08124802916871, 56.05014260528682,
-    57.019297069824276, 57.988705014595105, 58.95836029053817, 59.92825699327966,
-};
-
-__device__ __forceinline__ bool strand_can_pass(uint32_t k, uint32_t depth, float err) {
-    if (err == -1.0f) return false;  // VC:3844-3849: Q = -888
-    const double m = __dmul_rn((double)depth, (double)effective_err(err));
-    if (m >= (double)k && m > 1.0) return false;
-    if (k >= 1u && k <= 64u && m >= AS_MCRIT[k - 1u]) return false;
-    return true;
-}
-
-// Integer pre-screen of the staged caller's scan.  R = floor(e_min * 2^32) for the smallest threshold e_min of the strand;
-// m16 = floor(16 * depth * e_min) in sixteenths (depth saturates at 2^28: a smaller product is still a lower bound).
-// Returns K such that a strand test with 1 <= k <= K cannot pass for any alt base (real mean m >= m16 / 16):
-//   K = floor(m16/16 + 9/16) when that is <= 64: m >= K - 9/16 >= m*(K)(1 + 1e-9) = AS_MCRIT[K-1] (checked for K = 1..64 in
-//       tests/test_host_cpu.py), the critical-mean screen of strand_can_pass;
-//   K = floor(m16/16) otherwise: m >= k and m > 1, the continued-fraction screen.
-__device__ __forceinline__ uint32_t prescreen_k(uint32_t depth, uint32_t R) {
-    const uint32_t d16 = depth > 0x0FFFFFFFu ? 0xFFFFFFFFu : depth << 4;
-    const uint32_t m16 = __umulhi(d16, R);
-    const uint32_t lo = m16 >> 4, hi = lo + (((m16 & 15u) + 9u) >> 4);
-    return hi <= 64u ? hi : lo;
-}
-
 __device__ __forceinline__ void emit_call(as_call* __restrict__ calls, unsigned long long* __restrict__ n_calls,
                                           int64_t cap, bool is_call, int32_t sample, int32_t slot, int32_t alt,
                                           int32_t ref, double p_fw, double p_bw) {
@@ -933,15 +649,6 @@ call_queued_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p
     if (n1 > 0) stage1_batch(q1, n1, q2, n2, ref, calls, cap, n_calls);
     if (n2 > 0) stage2_batch(q2, n2, ref, calls, cap, n_calls);
 }
-
-// Survivor entry of the staged kernel: 24 bytes (the thresholds are read again from thr_view when the series is
-// evaluated -- survivors are a few per ten thousand records -- so that five CTAs fit one SM).
-struct StagedCand {
-    uint32_t k_fw, d_fw, k_bw, d_bw;
-    uint32_t sample_alt;  // sample | threshold table (noise-floor sweep) << 27 | alt << 30
-    int32_t slot;
-};
-static_assert(sizeof(StagedCand) == 24, "StagedCand is three 8-byte words");
 
 // n_c threshold tables (noise-floor sweep), c_stride floats apart; table ci owns the list calls + ci * cap and the
 // counter n_calls[ci].  n_c == 1 is the plain caller.
@@ -1318,69 +1025,64 @@ cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64
     if (p1 <= p0) return cudaSuccess;
     const uint4* c = reinterpret_cast<const uint4*>(d_counts);
 #define AS_NOISE_ARGS c, S, P, p0, p1, d_twin_next, d_twin_head, twin_base, C, cut, d_thr, d_germ_val, d_germ_state, d_count, d_nrec
+    if (cfg >= 7)  // register-lean pattern kernel (as_noise_pattern.cu), one value of C
+        return as_launch_noise_pattern(cfg - 7, d_counts, S, P, p0, p1, d_twin_next, d_twin_head, twin_base, &C, 1, cut, d_thr, 0,
+                                       d_germ_val, d_germ_state, d_count, d_nrec, st);
     switch (cfg) {
         case 0:
             noise_main_kernel<AS_NOISE_UNROLL><<<cdiv64(p1 - p0, AS_NOISE_THREADS), AS_NOISE_THREADS, 0, st>>>(AS_NOISE_ARGS);
             return cudaGetLastError();
-        case 2: return launch_noise_staged<4, 4>(AS_NOISE_ARGS, st);
-        case 3: return launch_noise_staged<2, 4>(AS_NOISE_ARGS, st);
         case 4: return launch_noise_staged<8, 2>(AS_NOISE_ARGS, st);
-        case 5: return launch_noise_staged<8, 3>(AS_NOISE_ARGS, st);
         case 6: return launch_noise_staged<4, 2>(AS_NOISE_ARGS, st);
         default: return launch_noise_staged<4, 3>(AS_NOISE_ARGS, st);
     }
 #undef AS_NOISE_ARGS
 }
 
-// thresholds of n_c (<= AS_SWEEP_NC) further C values in one pass: table c at d_thr + c * thr_stride floats
-cudaError_t as_launch_noise_sweep(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1, const int32_t* d_twin_next,
-                                  const int32_t* d_twin_head, int64_t twin_base, const float* c_values, int n_c, uint32_t cut,
-                                  float* d_thr, int64_t thr_stride, cudaStream_t st) {
-    if (p1 <= p0 || n_c <= 0) return cudaSuccess;
-    if (n_c > AS_SWEEP_NC) return cudaErrorInvalidValue;
-    static bool configured[AS_MAX_DEVICES] = {};
-    const int smem = StageRing<4, 3>::kStageBytes * 3;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(noise_sweep_kernel<4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
-    }
-    SweepC cs;
-    for (int c = 0; c < AS_SWEEP_NC; ++c) cs.c[c] = c_values[c < n_c ? c : n_c - 1];
-    noise_sweep_kernel<4, 3><<<cdiv64(p1 - p0, AS_TILE_SLOTS), AS_CTA_THREADS, smem, st>>>(
-        reinterpret_cast<const uint4*>(d_counts), S, P, p0, p1, d_twin_next, d_twin_head, twin_base, cs, n_c, cut, d_thr, thr_stride);
+// Twin groups the streaming kernel leaves out.  as_launch_twin_heads (memset + 1 kernel) lists them -- pairs in the first
+// half of d_heads_scratch, longer groups in the second, d_counters two uint32 -- and as_launch_noise_twin_groups (2
+// kernels) reduces them for one value of C.  cfg = the streaming kernel's variant (decides who owns in-tile pairs).
+cudaError_t as_launch_twin_heads(int cfg, int64_t p0, int64_t p1, const int32_t* d_twin_next, const int32_t* d_twin_head,
+                                 int32_t* d_heads_scratch, uint32_t* d_counters, cudaStream_t st) {
+    if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
+    const int64_t half = (p1 - p0 + 1) / 2 + 1;
+    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), st);
+    // in-tile pairs are reduced by the staged kernel when its ring can hold the hand-over block (see kPairsInTile)
+    int ring_kb = 0;
+    switch (cfg) { case 0: ring_kb = 0; break; case 4: ring_kb = 64; break; case 6: ring_kb = 32; break; default: ring_kb = 48; }
+    // cfg >= 7: noise_pattern_kernel, which always merges in-tile pairs itself
+    const int skip_intile = cfg >= 7 ? 1 : ((AS_INTILE_TWINS && ring_kb * 1024 >= AS_TILE_SLOTS * (int)sizeof(PairXfer)) ? 1 : 0);
+    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, skip_intile, d_heads_scratch,
+                                                           d_heads_scratch + half, d_counters);
     return cudaGetLastError();
 }
 
-// 4 launches (memset node + 3 kernels).  d_heads_scratch holds n slots of int32 (pairs in the first half, longer
-// groups in the second), d_counters two uint32.
+cudaError_t as_launch_noise_twin_groups(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                        const int32_t* d_twin_next, const int32_t* d_heads_scratch, const uint32_t* d_counters,
+                                        float C, uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
+                                        uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
+    if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
+    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
+    const int64_t half = (p1 - p0 + 1) / 2 + 1;
+    // pairs: at most (p1-p0)/2 quads; enough CTAs to cover a typical panel (~1 % of the slots) in one pass
+    const unsigned pair_grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (p1 - p0) / 64 / 32 + 1));  // 32 pairs per CTA
+    noise_pair_kernel<<<pair_grid, 128, 0, st>>>(c, S, P, d_twin_next, d_heads_scratch, d_counters, C, cut, d_thr, d_germ_val,
+                                                 d_germ_state, d_count, d_nrec);
+    const unsigned grid = (unsigned)std::min<int64_t>(148 * 2, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
+    noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_heads_scratch + half, d_counters, C, cut, d_thr, d_germ_val,
+                                            d_germ_state, d_count, d_nrec);
+    return cudaGetLastError();
+}
+
+// 4 launches (memset node + 3 kernels): heads, then the groups for one value of C
 cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
                                   uint32_t* d_counters, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
-    if (p1 <= p0 || d_twin_next == nullptr) return cudaSuccess;
-    const uint4* c = reinterpret_cast<const uint4*>(d_counts);
-    const int64_t half = (p1 - p0 + 1) / 2 + 1;
-    int32_t* d_pairs = d_heads_scratch;
-    int32_t* d_groups = d_heads_scratch + half;
-    cudaMemsetAsync(d_counters, 0, 2 * sizeof(uint32_t), st);
-    // in-tile pairs are reduced by the staged kernel when its ring can hold the hand-over block (see kPairsInTile)
-    int ring_kb = 0;
-    switch (cfg) { case 0: ring_kb = 0; break; case 2: ring_kb = 64; break; case 3: ring_kb = 32; break; case 4: ring_kb = 64; break;
-                   case 5: ring_kb = 96; break; case 6: ring_kb = 32; break; default: ring_kb = 48; }
-    const int skip_intile = (AS_INTILE_TWINS && ring_kb * 1024 >= AS_TILE_SLOTS * (int)sizeof(PairXfer)) ? 1 : 0;
-    twin_heads_kernel<<<cdiv64(p1 - p0, 256), 256, 0, st>>>(d_twin_next, d_twin_head, p0, p1, skip_intile,
-                                                           d_pairs, d_groups, d_counters);
-    // pairs: at most (p1-p0)/2 quads; enough CTAs to cover a typical panel (~1 % of the slots) in one pass
-    const unsigned pair_grid = (unsigned)std::min<int64_t>(148 * 16, std::max<int64_t>(1, (p1 - p0) / 64 / 32 + 1));  // 32 pairs per CTA
-    noise_pair_kernel<<<pair_grid, 128, 0, st>>>(c, S, P, d_twin_next, d_pairs, d_counters, C, cut, d_thr, d_germ_val,
-                                                 d_germ_state, d_count, d_nrec);
-    const unsigned grid = (unsigned)std::min<int64_t>(148 * 2, std::max<int64_t>(1, (p1 - p0 + 7) / 8));
-    noise_twin_kernel<<<grid, 128, 0, st>>>(c, S, P, d_twin_next, d_groups, d_counters, C, cut, d_thr, d_germ_val,
-                                            d_germ_state, d_count, d_nrec);
-    return cudaGetLastError();
+    cudaError_t e = as_launch_twin_heads(cfg, p0, p1, d_twin_next, d_twin_head, d_heads_scratch, d_counters, st);
+    if (e != cudaSuccess) return e;
+    return as_launch_noise_twin_groups(d_counts, S, P, p0, p1, d_twin_next, d_heads_scratch, d_counters, C, cut, d_thr, d_germ_val,
+                                       d_germ_state, d_count, d_nrec, st);
 }
 
 cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st) {
@@ -1462,20 +1164,9 @@ cudaError_t as_launch_call_sweep(int variant, const uint32_t* d_counts, int T, i
         case 0: if (n_c != 1) return cudaErrorInvalidValue; call_naive_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
         case 1: if (n_c != 1) return cudaErrorInvalidValue; call_queued_kernel<<<grid, AS_CALL_THREADS, 0, st>>>(AS_CALL_ARGS); return cudaGetLastError();
         case 3: return launch_call_staged<4, 2>(grid, AS_SWEEP_ARGS, st);
-        case 4: return launch_call_staged<4, 4>(grid, AS_SWEEP_ARGS, st);
-        case 5: return launch_call_staged<8, 2>(grid, AS_SWEEP_ARGS, st);
-        case 6: return launch_call_staged<8, 3>(grid, AS_SWEEP_ARGS, st);
-        case 7: return launch_call_staged<2, 2>(grid, AS_SWEEP_ARGS, st);
-        case 8: return launch_call_staged<2, 3>(grid, AS_SWEEP_ARGS, st);
-        case 9: return launch_call_staged<2, 4>(grid, AS_SWEEP_ARGS, st);
-        case 10: return launch_call_staged<3, 3>(grid, AS_SWEEP_ARGS, st);
         case 11: return launch_call_staged<3, 2>(grid, AS_SWEEP_ARGS, st);
-        case 12: return launch_call_staged<6, 2>(grid, AS_SWEEP_ARGS, st);
-        case 13: return launch_call_staged<3, 2, true>(grid, AS_SWEEP_ARGS, st);
         case 14: return launch_call_staged<4, 2, true>(grid, AS_SWEEP_ARGS, st);
-        case 15: return launch_call_staged<2, 2, true>(grid, AS_SWEEP_ARGS, st);
-        case 16: return launch_call_staged<4, 3, true>(grid, AS_SWEEP_ARGS, st);
-        default: return launch_call_staged<4, 3>(grid, AS_SWEEP_ARGS, st);
+        default: return launch_call_staged<3, 2, true>(grid, AS_SWEEP_ARGS, st);
     }
 #undef AS_CALL_ARGS
 #undef AS_SWEEP_ARGS

@@ -17,6 +17,7 @@
 #define AS_INTILE_TWINS 1
 #define AS_DEFAULT_CALL_KERNEL 13 /* TMA-staged, 3 samples per stage, 2 stages (7 CTAs/SM), integer pre-screen in the scan: best of the measured sweeps on the c3 and the c5 shape */
 #define AS_DEFAULT_NOISE_KERNEL 1 /* TMA-staged, 4 samples per stage, 3 stages */
+#define AS_DEFERRED_CALL_KERNEL 20 /* scan -> resolve -> series (as_call_deferred.cu); what a sweep runs by default */
 
 cudaError_t as_launch_noise_main(int cfg, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
                                  const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base, float C,
@@ -26,9 +27,24 @@ cudaError_t as_launch_noise_twins(int cfg, const uint32_t* d_counts, int S, int6
                                   const int32_t* d_twin_next, const int32_t* d_twin_head, int32_t* d_heads_scratch,
                                   uint32_t* d_nheads_scratch, float C, uint32_t cut, float* d_thr, float* d_germ_val,
                                   uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
-cudaError_t as_launch_noise_sweep(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1, const int32_t* d_twin_next,
-                                  const int32_t* d_twin_head, int64_t twin_base, const float* c_values, int n_c, uint32_t cut,
-                                  float* d_thr, int64_t thr_stride, cudaStream_t st);
+cudaError_t as_launch_twin_heads(int cfg, int64_t p0, int64_t p1, const int32_t* d_twin_next, const int32_t* d_twin_head,
+                                 int32_t* d_heads_scratch, uint32_t* d_counters, cudaStream_t st);
+cudaError_t as_launch_noise_twin_groups(const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                        const int32_t* d_twin_next, const int32_t* d_heads_scratch, const uint32_t* d_counters,
+                                        float C, uint32_t cut, float* d_thr, float* d_germ_val, uint8_t* d_germ_state,
+                                        uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
+// as_noise_pattern.cu: every output of the noise model for n_c (1..8) values of C in ONE pass over the normals; table c at
+// d_thr + c * thr_stride floats.  geom selects the ring: 0 = (4 samples, 3 stages), 1 = (3, 3), 2 = (4, 2).
+cudaError_t as_launch_noise_pattern(int geom, const uint32_t* d_counts, int S, int64_t P, int64_t p0, int64_t p1,
+                                    const int32_t* d_twin_next, const int32_t* d_twin_head, int64_t twin_base,
+                                    const float* c_values, int n_c, uint32_t cut, float* d_thr, int64_t thr_stride,
+                                    float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
+// as_call_deferred.cu: the caller as scan -> resolve -> series kernels over candidate / survivor lists in d_scratch
+size_t as_deferred_scratch_bytes(int T, int64_t n_slots, int64_t* cap_cand, int64_t* cap_surv);
+cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1, const uint8_t* d_ref,
+                                    const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut, as_call* d_calls,
+                                    int64_t cap, unsigned long long* d_n_calls, void* d_scratch, int64_t cap_cand,
+                                    int64_t cap_surv, cudaStream_t st);
 cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_unpack(const uint32_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32_t* d_tile, int64_t n, int64_t p0,

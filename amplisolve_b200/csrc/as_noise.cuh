@@ -21,6 +21,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "as_device.cuh"
+
 namespace asdev {
 
 #define AS_AF_LIMIT_NUM 26843545ull /* 0.05 as the float-rounding boundary, times 2^29 */
@@ -58,10 +60,6 @@ __device__ __forceinline__ void noise_init(NoiseAcc& a) {
         a.b[i].g_x = 0; a.b[i].g_rd = 1;
     }
     a.nrec = 0;
-}
-
-__device__ __forceinline__ uint32_t comp(const uint4& v, int i) {
-    return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w;
 }
 
 // One (sample, slot) record.  TRACK_FIRST keeps the first qualifying Germ_Max record so that partial

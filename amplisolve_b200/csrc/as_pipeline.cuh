@@ -32,16 +32,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Blocking wait: try_wait parks the warp until the phase completes or the suspend-time hint (ns) runs out, so a waiting
+// warp issues one instruction per AS_MBAR_SUSPEND_NS instead of spinning (ncu of round 1: the producer's and the
+// consumers' polling loops were 58 % of the warp instructions the sweep caller executed).
+#define AS_MBAR_SUSPEND_NS 20000
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(AS_MBAR_SUSPEND_NS)
         : "memory");
 }
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier.  bytes % 16 == 0, both 16-B aligned.

@@ -79,15 +79,19 @@ void as_destroy(as_ctx* ctx);
 int as_host_alloc(void** out, size_t bytes);
 int as_host_free(void* p);
 /* Kernel variants (the tests cross-check them against each other and the oracle; -1 = default):
- *   caller: 0 = straightforward, 1 = per-warp queues over direct loads, 2..12 = TMA-staged with
- *           (samples per stage, stages) = (4,3), (4,2), (4,4), (8,2), (8,3), (2,2), (2,3), (2,4), (3,3), (3,2), (6,2)
- *           13..16 = TMA-staged with the integer pre-screen in the scan: (3,2) default, (4,2), (2,2), (4,3)
- *   noise : 0 = direct loads, 1..6 = TMA-staged with (4,3) default, (4,4), (2,4), (8,2), (8,3), (4,2) */
+ *   caller: 0 = straightforward, 1 = per-warp queues over direct loads, TMA-staged with (samples per stage, stages):
+ *           3 = (4,2), 11 = (3,2); with the integer pre-screen in the scan: 13 = (3,2) default, 14 = (4,2);
+ *           20 = deferred: scan -> resolve -> series kernels over candidate lists (what a sweep of several tables runs)
+ *   noise : 0 = direct loads; TMA-staged 1 = (4,3) default, 4 = (8,2), 6 = (4,2); 7..9 = shared-pattern accumulators
+ *           (the kernel of as_noise_estimate_sweep_dev) with rings (4,3), (3,3), (4,2) */
 int as_set_call_kernel(as_ctx* ctx, int variant);
 int as_set_noise_kernel(as_ctx* ctx, int variant);
 /* Slots per tile of the _host pipelines: 0 = automatic (~256 MiB of counts per buffer), else a multiple of 128.
  * Small values are for tests (tile-boundary handling). */
 int as_set_host_tile_slots(as_ctx* ctx, int64_t slots);
+/* Generic form of the setters above plus "deferred_capacity" (entries of the deferred caller's candidate list; 0 =
+ * automatic; the kernels resolve what does not fit on the spot, so results never depend on it -- tests use tiny values). */
+int as_set_option(as_ctx* ctx, const char* name, int64_t value);
 /* Number of kernel launches this context has enqueued so far (bench.py's gpu_launches). */
 int64_t as_kernel_launches(const as_ctx* ctx);
 
@@ -110,10 +114,11 @@ int as_noise_estimate_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int6
                           uint32_t* d_nrec, void* stream);
 /* The _host forms also fill thr_view [P][4][2] when it is not NULL: the thresholds as the caller will parse them
  * (as_thresholds_caller_view_dev applied while the tile is still on the device). */
-/* Noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): the noise model for n_c values of C.  Only the sum of
- * float(depth) * float(C) (EE:1617) depends on C, so the first value runs the plain kernels (all outputs; Germ_Max, count
- * and nrec do not depend on C) and the others share passes over the normals, four values per pass.  c_values is a HOST
- * array [n_c], 1 <= n_c <= 8; d_thr [n_c][P][4][2], table i = the thresholds as_noise_estimate_dev gives for c_values[i]
+/* Noise-floor sweep (BASELINE configs[3]: C_value 0.001 ... 0.005): the noise model for n_c values of C in ONE pass over
+ * the normals.  Only the sum of float(depth) * float(C) (EE:1617) depends on C; the filter, the depth and alt-read sums,
+ * Germ_Max, count and nrec are shared, and the per-C sums are kept once per slot (not per base) for the records that carry
+ * the slot's usual keep pattern (noise_pattern_kernel, as_noise_pattern.cu).  c_values is a HOST array [n_c],
+ * 1 <= n_c <= 8; d_thr [n_c][P][4][2], table i = the thresholds as_noise_estimate_dev gives for c_values[i]
  * (bit-identical; tested).  The other outputs as in as_noise_estimate_dev. */
 int as_noise_estimate_sweep_dev(as_ctx* ctx, const uint32_t* d_counts, int32_t S, int64_t P, int64_t slot_begin,
                                 int64_t slot_end, const int32_t* d_twin_next, const int32_t* d_twin_head,

@@ -95,14 +95,14 @@ def test_packed_wire_format_is_lossless():
 
 
 def test_critical_means_table_and_prescreen_bound():
-    """AS_MCRIT of as_kernels.cu is what scripts/critical_means.py computes (m*(k)(1 + 1e-9), P(X >= k | m*) = P*), the
+    """AS_MCRIT of as_call.cuh is what scripts/critical_means.py computes (m*(k)(1 + 1e-9), P(X >= k | m*) = P*), the
     reference's own p (oracle) is above P* at the table value and at most P* a hair below the critical mean, and the
     scan's bound K - 9/16 >= AS_MCRIT[K-1] holds for K = 1..64."""
     import sys
     sys.path.insert(0, str(ROOT / "scripts"))
     from critical_means import critical_means
     want = critical_means()
-    src = (ROOT / "amplisolve_b200" / "csrc" / "as_kernels.cu").read_text()
+    src = (ROOT / "amplisolve_b200" / "csrc" / "as_call.cuh").read_text()
     body = src[src.index("AS_MCRIT[64] = {") + len("AS_MCRIT[64] = {"):]
     body = body[:body.index("};")]
     have = [float(x) for x in body.replace("\n", " ").split(",") if x.strip()]

@@ -5,4 +5,4 @@ two drop-in programs under amplisolve_b200/bin; this package is the thin Python 
 tests and the benchmark.
 """
 from .api import (ABSENT, CALL_DTYPE, AmpliSolveError, Context, calls_from_device, fisher_test, hash_iteration_order, lib,  # noqa: F401
-                  pack_counts, to_wire16, to_wire_packed, twin_links)
+                  pack_counts, shard_bounds, to_wire16, to_wire_packed, twin_links)

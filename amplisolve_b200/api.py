@@ -26,7 +26,7 @@ CALL_DTYPE = np.dtype([("sample", "<i4"), ("slot", "<i4"), ("alt", "<i4"), ("ref
 assert CALL_DTYPE.itemsize == 48
 
 EXPORTS = [
-    "as_last_error", "as_version", "as_device_count", "as_create", "as_destroy", "as_host_alloc", "as_host_free",
+    "as_last_error", "as_version", "as_device_count", "as_create", "as_create_multi", "as_context_devices", "as_shard_bounds", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_set_option", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
     "as_call_variants_host16", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
@@ -137,6 +137,9 @@ def lib():
     L.as_version.restype = C.c_char_p
     L.as_device_count.argtypes = [C.POINTER(C.c_int)]
     L.as_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.as_create_multi.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.as_context_devices.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+    L.as_shard_bounds.argtypes = [i64, i32, vp, vp, vp]
     L.as_destroy.argtypes = [vp]
     L.as_destroy.restype = None
     L.as_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
@@ -208,6 +211,15 @@ def fisher_test(fw: int, bw: int, alt_fw: int, alt_bw: int) -> float:
     return float(lib().as_fisher_test(int(fw), int(bw), int(alt_fw), int(alt_bw)))
 
 
+def shard_bounds(n_slots: int, n_shards: int, twin_next=None, twin_head=None) -> list:
+    """as_shard_bounds: the slot ranges a multi-device context splits a panel into (twin groups kept whole)."""
+    out = np.zeros(n_shards + 1, dtype=np.int64)
+    tn = None if twin_next is None else _np(twin_next, np.int32)
+    th = None if twin_head is None else _np(twin_head, np.int32)
+    _check(lib().as_shard_bounds(int(n_slots), int(n_shards), None if tn is None else _hp(tn), None if th is None else _hp(th), _hp(out)))
+    return [int(x) for x in out]
+
+
 def twin_links(pos_id) -> tuple[np.ndarray, np.ndarray]:
     """twin_next / twin_head arrays from a slot -> unique-position map (slots in panel order)."""
     pos_id = np.asarray(pos_id)
@@ -234,10 +246,17 @@ def _host_format(counts) -> str:
 class Context:
     """One per device (as_ctx)."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one ordinal (as_create) or a list of ordinals (as_create_multi: the host entry points shard the panel's
+        slots over them; device-resident entry points use the first)."""
         self._h = C.c_void_p()
-        self.device = device
-        _check(lib().as_create(device, C.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            arr = (C.c_int * len(device))(*device)
+            self.device = int(device[0])
+            _check(lib().as_create_multi(arr, len(device), C.byref(self._h)))
+        else:
+            self.device = device
+            _check(lib().as_create(device, C.byref(self._h)))
 
     def close(self):
         if self._h:

@@ -320,24 +320,33 @@ size_t as_deferred_scratch_bytes(int T, int64_t n_slots, int64_t* cap_cand, int6
     cc = std::max<int64_t>(1 << 20, std::min<int64_t>(cc, 64ll << 20));
     *cap_cand = cc;
     *cap_surv = std::max<int64_t>(1 << 18, cc / 4);
-    return 256 + (size_t)cc * sizeof(StagedCand) + (size_t)*cap_surv * sizeof(Survivor);
+    return 4096 + (size_t)cc * sizeof(StagedCand) + (size_t)*cap_surv * sizeof(Survivor) + 512 * AS_DEFER_MAX_CHUNKS;
 }
 
-// d_scratch: as_deferred_scratch_bytes() bytes, 256-byte aligned: counters | candidates | survivors.  3 kernels + 1 memset.
+// pieces a range is cut into: at most `want`, and at least two full waves of scan CTAs (148 SMs x 7) per piece
+int as_deferred_chunks(int64_t n_slots, int want) {
+    const int64_t tiles = (n_slots + AS_TILE_SLOTS - 1) / AS_TILE_SLOTS;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(want, AS_DEFER_MAX_CHUNKS), tiles / (148 * 7 * 2)));
+}
+
+// d_scratch: as_deferred_scratch_bytes() bytes, 256-byte aligned: counters | candidates | survivors.
+// The slot range is cut into n_chunks pieces (each with its share of the two lists): the scan of piece i+1 runs on `st`
+// while the resolve and series kernels of piece i run on `aux` (a high-priority stream; ev[i] orders them) -- the scan is
+// bound by HBM, the series by the fp64 pipe, so the two overlap almost for free.  n_chunks == 1: everything on `st`.
+// Launches: 1 memset + 3 kernels per piece.
 cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1, const uint8_t* d_ref,
                                     const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut, as_call* d_calls,
                                     int64_t cap, unsigned long long* d_n_calls, void* d_scratch, int64_t cap_cand,
-                                    int64_t cap_surv, cudaStream_t st) {
+                                    int64_t cap_surv, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, int n_chunks) {
     if (p1 <= p0 || T <= 0 || n_c <= 0) return cudaSuccess;
     if (n_c > 8) return cudaErrorInvalidValue;
-    DeferredLists L;
-    L.counters = (unsigned long long*)d_scratch;
-    L.cand = (StagedCand*)((char*)d_scratch + 256);
-    L.cap_cand = (unsigned long long)cap_cand;
-    L.surv = (Survivor*)((char*)d_scratch + 256 + (((size_t)cap_cand * sizeof(StagedCand) + 255) & ~(size_t)255));
-    L.cap_surv = (unsigned long long)cap_surv;
+    const int64_t tiles = (p1 - p0 + AS_TILE_SLOTS - 1) / AS_TILE_SLOTS;
+    n_chunks = (aux == nullptr || ev == nullptr) ? 1 : as_deferred_chunks(p1 - p0, n_chunks);
     CallSink sink{d_ref, d_thr_views, n_c, c_stride, d_calls, cap, d_n_calls};
-    cudaError_t e = cudaMemsetAsync(L.counters, 0, 16, st);
+    unsigned long long* counters = (unsigned long long*)d_scratch;  // two per piece
+    StagedCand* cand0 = (StagedCand*)((char*)d_scratch + 4096);
+    Survivor* surv0 = (Survivor*)((char*)d_scratch + 4096 + (((size_t)cap_cand * sizeof(StagedCand) + 255) & ~(size_t)255));
+    cudaError_t e = cudaMemsetAsync(counters, 0, 16 * AS_DEFER_MAX_CHUNKS, st);
     if (e != cudaSuccess) return e;
     constexpr int K = 3, STAGES = 2;
     static bool configured[AS_MAX_DEVICES] = {};
@@ -350,10 +359,32 @@ cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, 
         if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
     }
     const int chunk = as_call_chunk(T, p1 - p0);
-    dim3 grid((unsigned)((p1 - p0 + AS_TILE_SLOTS - 1) / AS_TILE_SLOTS), (unsigned)((T + chunk - 1) / chunk));
-    call_scan_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(d_counts), T, P, p0, p1, chunk,
-                                                                      cut, L, sink);
-    call_resolve_kernel<<<148 * 8, 256, 0, st>>>(L, sink);
-    call_series_kernel<<<dim3(148 * 4, (unsigned)n_c), 128, 0, st>>>(L, sink);
+    const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        const int64_t t_lo = tiles * ch / n_chunks, t_hi = tiles * (ch + 1) / n_chunks;
+        const int64_t q0 = p0 + t_lo * AS_TILE_SLOTS, q1 = std::min(p1, p0 + t_hi * AS_TILE_SLOTS);
+        if (q1 <= q0) continue;
+        DeferredLists L;
+        L.counters = counters + 2 * ch;
+        L.cap_cand = (unsigned long long)(cap_cand / n_chunks);
+        L.cap_surv = (unsigned long long)(cap_surv / n_chunks);
+        L.cand = cand0 + (size_t)ch * L.cap_cand;
+        L.surv = surv0 + (size_t)ch * L.cap_surv;
+        dim3 grid((unsigned)(t_hi - t_lo), gy);
+        call_scan_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(d_counts), T, P, q0, q1, chunk,
+                                                                          cut, L, sink);
+        cudaStream_t post = st;
+        if (n_chunks > 1) {
+            if ((e = cudaEventRecord(ev[ch], st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(aux, ev[ch], 0)) != cudaSuccess) return e;
+            post = aux;
+        }
+        call_resolve_kernel<<<148 * 8, 256, 0, post>>>(L, sink);
+        call_series_kernel<<<dim3(148 * 4, (unsigned)n_c), 128, 0, post>>>(L, sink);
+    }
+    if (n_chunks > 1) {  // join: control returns to `st` when the last series kernel is done
+        if ((e = cudaEventRecord(ev[n_chunks], aux)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(st, ev[n_chunks], 0)) != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }

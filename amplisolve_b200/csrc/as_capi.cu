@@ -87,6 +87,7 @@ struct PinnedGrow {  // grow-only pinned host scratch owned by the context (cuda
 
 struct as_ctx {
     int device = 0;
+    std::vector<as_ctx*> subs;  // as_create_multi: one single-device context per GPU; the _host entry points shard over them
     int call_variant = AS_DEFAULT_CALL_KERNEL;   // 0 straightforward, 1 queued (direct loads), >= 2 TMA-staged (K, stages) variants
     int noise_cfg = AS_DEFAULT_NOISE_KERNEL;      // 0 direct loads, >= 1 TMA-staged (K, stages) variants
     int64_t launches = 0;
@@ -95,6 +96,8 @@ struct as_ctx {
     cudaStream_t copy_stream = nullptr, exec_stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    cudaEvent_t ev_chunk[AS_DEFER_MAX_CHUNKS + 1] = {};  // deferred caller: scan of piece i -> resolve / series on aux_stream
+    int defer_chunks = 6;
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
     DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls, sortbuf;  // _host pipelines
     DevBuf defer;                                                              // candidate / survivor lists of the deferred caller
@@ -148,12 +151,55 @@ int as_create(int device, as_ctx** out) {
         CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i <= AS_DEFER_MAX_CHUNKS; ++i) CU(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     *out = c;
     return AS_OK;
 }
 
+// One context over several GPUs of the box: the _host entry points shard the panel's slots over them (contiguous ranges
+// that keep twin groups whole, one host thread per device, no data-path exchange between devices) and merge the call
+// lists.  _dev entry points and the element-wise evaluators run on the first device.
+int as_create_multi(const int* devices, int ndev, as_ctx** out) {
+    if (!out) return fail(AS_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (!devices || ndev < 1 || ndev > AS_MAX_DEVICES) return fail(AS_EINVAL, "as_create_multi takes 1..%d devices", AS_MAX_DEVICES);
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(AS_EINVAL, "device %d listed twice", devices[i]);
+    as_ctx* head = nullptr;
+    int rc = as_create(devices[0], &head);
+    if (rc != AS_OK) return rc;
+    if (ndev > 1) {
+        head->subs.push_back(nullptr);  // slot 0 = the head itself (filled below)
+        for (int i = 1; i < ndev; ++i) {
+            as_ctx* sub = nullptr;
+            rc = as_create(devices[i], &sub);
+            if (rc != AS_OK) {
+                for (size_t k = 1; k < head->subs.size(); ++k) as_destroy(head->subs[k]);
+                head->subs.clear();
+                as_destroy(head);
+                return rc;
+            }
+            head->subs.push_back(sub);
+        }
+        head->subs[0] = head;
+        cudaSetDevice(head->device);
+    }
+    *out = head;
+    return AS_OK;
+}
+
+int as_context_devices(const as_ctx* c, int* devices, int cap) {
+    if (!c) return 0;
+    const int n = c->subs.empty() ? 1 : (int)c->subs.size();
+    for (int i = 0; i < n && i < cap && devices; ++i) devices[i] = c->subs.empty() ? c->device : c->subs[(size_t)i]->device;
+    return n;
+}
+
 void as_destroy(as_ctx* c) {
     if (!c) return;
+    for (size_t k = 1; k < c->subs.size(); ++k) as_destroy(c->subs[k]);
+    c->subs.clear();
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release(); c->sortbuf.release();
@@ -163,6 +209,8 @@ void as_destroy(as_ctx* c) {
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
         if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
     }
+    for (int i = 0; i <= AS_DEFER_MAX_CHUNKS; ++i)
+        if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
@@ -185,19 +233,31 @@ int as_set_host_tile_slots(as_ctx* c, int64_t slots);
 int as_set_call_kernel(as_ctx* c, int variant) {
     if (!c || variant < -1 || variant > 20) return fail(AS_EINVAL, "bad call kernel variant");
     c->call_variant = variant < 0 ? AS_DEFAULT_CALL_KERNEL : variant;
+    for (size_t k = 1; k < c->subs.size(); ++k) c->subs[k]->call_variant = c->call_variant;
     return AS_OK;
 }
 int as_set_noise_kernel(as_ctx* c, int variant) {
     if (!c || variant < -1 || variant > 11) return fail(AS_EINVAL, "bad noise kernel variant");
     c->noise_cfg = variant < 0 ? AS_DEFAULT_NOISE_KERNEL : variant;
+    for (size_t k = 1; k < c->subs.size(); ++k) c->subs[k]->noise_cfg = c->noise_cfg;
     return AS_OK;
 }
-int64_t as_kernel_launches(const as_ctx* c) { return c ? c->launches : 0; }
+int64_t as_kernel_launches(const as_ctx* c) {
+    if (!c) return 0;
+    int64_t n = c->launches;
+    for (size_t k = 1; k < c->subs.size(); ++k) n += c->subs[k]->launches;
+    return n;
+}
 int as_set_option(as_ctx* c, const char* name, int64_t value) {
     if (!c || !name) return fail(AS_EINVAL, "bad argument");
     if (!strcmp(name, "call_kernel")) return as_set_call_kernel(c, (int)value);
     if (!strcmp(name, "noise_kernel")) return as_set_noise_kernel(c, (int)value);
     if (!strcmp(name, "host_tile_slots")) return as_set_host_tile_slots(c, value);
+    if (!strcmp(name, "deferred_chunks")) {
+        if (value < 1 || value > AS_DEFER_MAX_CHUNKS) return fail(AS_EINVAL, "deferred_chunks must be 1..%d", AS_DEFER_MAX_CHUNKS);
+        c->defer_chunks = (int)value;
+        return AS_OK;
+    }
     if (!strcmp(name, "deferred_capacity")) {
         if (value < 0) return fail(AS_EINVAL, "deferred_capacity must be >= 0 (0 = automatic)");
         c->defer_cap_override = value;
@@ -208,6 +268,7 @@ int as_set_option(as_ctx* c, const char* name, int64_t value) {
 int as_set_host_tile_slots(as_ctx* c, int64_t slots) {
     if (!c || slots < 0 || (slots % 128) != 0) return fail(AS_EINVAL, "host tile size must be 0 (automatic) or a multiple of 128 slots");
     c->host_tile_slots = slots;
+    for (size_t k = 1; k < c->subs.size(); ++k) c->subs[k]->host_tile_slots = slots;
     return AS_OK;
 }
 
@@ -439,19 +500,15 @@ struct NoiseOutLayout {  // one device block per tile: thr | germ_val | count | 
     }
 };
 
-static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, int64_t P, const int32_t* twin_next,
-                                    const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
-                                    uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view) {
+// Slots [B, E) of the panel on ONE device (c is a single-device context).  Twin groups must not straddle B or E.
+static int noise_estimate_host_range(as_ctx* c, const HostSrc& src, int32_t S, int64_t P, int64_t B, int64_t E,
+                                     const int32_t* twin_next, const int32_t* twin_head, float C, int32_t cut, float* thr,
+                                     float* germ_val, uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view) {
     const int elem = src.elem;
     PhaseClock clk;
-    int rc = check_common(c, src.counts, S, P, 0, P, cut);
-    if (rc) return rc;
-    if ((rc = check_wide(src, S, P)) != AS_OK) return rc;
-    if (!thr || !germ_val || !germ_state || !count || !nrec) return fail(AS_EINVAL, "output pointer is NULL");
-    if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
-    if (P == 0) return AS_OK;
+    if (E <= B) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(c, S, P, elem);
+    const int64_t TP = tile_slots(c, S, E - B, elem);
     const NoiseOutLayout lay(TP);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)std::max(1, S)));
@@ -462,22 +519,22 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
     // pass 1, tile by tile (the copy of tile i+1 overlaps the kernels of tile i): singleton slots by the streaming
     // kernel, twin groups that lie completely inside the tile by the twin kernels on tile-local links.  A group that
     // straddles a tile boundary is excluded here (all its members get head = -1) and done in pass 2.
-    int64_t ntiles = (P + TP - 1) / TP;
-    int32_t* h_links = nullptr;     // pinned: the tile-local links of every tile, tile t at [2 * p0, 2 * (p0 + n)): next[n] | head[n]
+    int64_t ntiles = (E - B + TP - 1) / TP;
+    int32_t* h_links = nullptr;     // pinned: the tile-local links of every tile, tile at p0 at [2 * (p0 - B), ...): next[n] | head[n]
     std::vector<int32_t> crossing;  // heads of the groups that straddle tiles
     if (twin_next) {
-        CU(c->h_links.need((size_t)P * 8));
+        CU(c->h_links.need((size_t)(E - B) * 8));
         h_links = (int32_t*)c->h_links.p;
         CU(c->heads.need(sizeof(int32_t) * 2 * (size_t)((TP + 1) / 2 + 1)));
         CU(c->nheads.need(2 * sizeof(uint32_t)));
         // every slot's verdict depends on its own chain only (does the whole group lie inside the slot's tile?), so
         // the links of all tiles are written by a few threads before the first upload
-        const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 16u), P / 65536));
+        const int nth = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(std::thread::hardware_concurrency(), 16u), (E - B) / 65536));
         std::vector<std::vector<int32_t>> cross_t((size_t)nth);
         auto work = [&](int k) {
-            for (int64_t g = P * k / nth, ge = P * (k + 1) / nth; g < ge; ++g) {
-                const int64_t p0 = (g / TP) * TP, n = std::min(TP, P - p0), i = g - p0;
-                int32_t* ln = h_links + p0 * 2;
+            for (int64_t g = B + (E - B) * k / nth, ge = B + (E - B) * (k + 1) / nth; g < ge; ++g) {
+                const int64_t p0 = B + ((g - B) / TP) * TP, n = std::min(TP, E - p0), i = g - p0;
+                int32_t* ln = h_links + (p0 - B) * 2;
                 int32_t* lh = ln + n;
                 const int64_t h = twin_head[g], nx = twin_next[g];
                 if (h == g && nx < 0) { ln[i] = -1; lh[i] = (int32_t)i; continue; }  // singleton
@@ -510,14 +567,14 @@ static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, in
 #define CUT(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret1 = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
     for (int64_t t = 0; t < ntiles; ++t) {
         const int bsel = (int)(t & 1);
-        const int64_t p0 = t * TP, n = std::min(TP, P - p0);
+        const int64_t p0 = B + t * TP, n = std::min(TP, E - p0);
         if (t >= 2) CUT(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));  // buffer free again
         CUT(upload_tile(c, bsel, src, S, P, p0, n, c->copy_stream));
         int32_t *d_tn = nullptr, *d_th = nullptr;
         if (twin_next) {
             d_tn = (int32_t*)c->aux[bsel].p;
             d_th = d_tn + n;
-            CUT(cudaMemcpyAsync(d_tn, h_links + p0 * 2, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+            CUT(cudaMemcpyAsync(d_tn, h_links + (p0 - B) * 2, (size_t)n * 8, cudaMemcpyHostToDevice, c->copy_stream));
         }
         CUT(cudaEventRecord(c->ev_up[bsel], c->copy_stream));
         CUT(cudaStreamWaitEvent(c->exec_stream, c->ev_up[bsel], 0));
@@ -637,8 +694,8 @@ static int call_deferred(as_ctx* c, const uint32_t* d_counts, int32_t T, int64_t
     if (c->defer_cap_override > 0) { cap_cand = c->defer_cap_override; cap_surv = std::max<int64_t>(1, cap_cand / 4); }
     CU(c->defer.need(bytes));
     CU(as_launch_call_deferred(d_counts, T, P, b, e, d_ref, d_thr_views, n_c, P * 8, (uint32_t)cut, d_calls, cap, d_n_calls, c->defer.p,
-                               cap_cand, cap_surv, st));
-    c->launches += 3;
+                               cap_cand, cap_surv, st, c->aux_stream, c->ev_chunk, c->defer_chunks));
+    c->launches += 3 * as_deferred_chunks(e - b, c->defer_chunks);
     return AS_OK;
 }
 
@@ -677,43 +734,41 @@ int as_call_variants_sweep_dev(as_ctx* c, const uint32_t* d_counts, int32_t T, i
     return AS_OK;
 }
 
-static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int64_t P, const uint8_t* ref,
-                                   const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
+// Slots [B, E) of the panel on ONE device (c is a single-device context).  The calls stay on the device, unsorted, with
+// panel slot ids, in c->calls (capacity cap); *found = the number found (may exceed cap).
+static int call_variants_host_range(as_ctx* c, const HostSrc& src, int32_t T, int64_t P, int64_t B, int64_t E, const uint8_t* ref,
+                                    const float* thr_view, int32_t cut, int64_t cap, int64_t* found) {
     const int elem = src.elem;
     PhaseClock clk;
-    int rc = check_common(c, src.counts, T, P, 0, P, cut);
-    if (rc) return rc;
-    if ((rc = check_wide(src, T, P)) != AS_OK) return rc;
-    if (!ref || !thr_view || !n_calls || (!calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
-    *n_calls = 0;
-    if (P == 0 || T == 0) return AS_OK;
+    *found = 0;
+    if (E <= B || T == 0) return AS_OK;
     CU(cudaSetDevice(c->device));
-    const int64_t TP = tile_slots(c, T, P, elem);
+    const int64_t TP = tile_slots(c, T, E - B, elem);
     for (int i = 0; i < 2; ++i) {
         CU(c->tile[i].need((size_t)TP * 32 * (size_t)T));
         if (elem != 4) CU(c->tile16[i].need((size_t)TP * 8 * (size_t)elem * (size_t)T));
     }
-    // thresholds (32 B/slot) and reference bases (1 B/slot) of the whole panel go up once, ahead of the first tile: a
+    // thresholds (32 B/slot) and reference bases (1 B/slot) of the range go up once, ahead of the first tile: a
     // per-tile copy from pageable memory would stall the upload queue at every tile
-    CU(c->aux[0].need((size_t)P * 33 + 64));
+    CU(c->aux[0].need((size_t)(E - B) * 33 + 64));
     float* d_tv_all = (float*)c->aux[0].p;
-    uint8_t* d_rf_all = (uint8_t*)c->aux[0].p + (size_t)P * 32;
-    CU(cudaMemcpyAsync(d_tv_all, thr_view, (size_t)P * 32, cudaMemcpyHostToDevice, c->copy_stream));
-    CU(cudaMemcpyAsync(d_rf_all, ref, (size_t)P, cudaMemcpyHostToDevice, c->copy_stream));
+    uint8_t* d_rf_all = (uint8_t*)c->aux[0].p + (size_t)(E - B) * 32;
+    CU(cudaMemcpyAsync(d_tv_all, thr_view + B * 8, (size_t)(E - B) * 32, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d_rf_all, ref + B, (size_t)(E - B), cudaMemcpyHostToDevice, c->copy_stream));
     CU(c->calls.need(sizeof(as_call) * (size_t)std::max<int64_t>(cap, 1)));
     CU(c->misc.need(32));
     CU(c->h_small.need(64));
     unsigned long long* d_n = (unsigned long long*)c->misc.p;  // calls found so far; d_n[1] = the count before the current tile
     unsigned long long* h_total = (unsigned long long*)c->h_small.p;
     CU(cudaMemsetAsync(d_n, 0, 16, c->exec_stream));
-    const int64_t ntiles = (P + TP - 1) / TP;
+    const int64_t ntiles = (E - B + TP - 1) / TP;
     clk.lap("call.checks_alloc");
     CU(stage_wide(c, src, c->copy_stream));
     clk.lap("call.stage_wide");
     int ret = AS_OK;
     for (int64_t t = 0; t < ntiles && ret == AS_OK; ++t) {
         const int bsel = (int)(t & 1);
-        const int64_t p0 = t * TP, n = std::min(TP, P - p0);
+        const int64_t p0 = B + t * TP, n = std::min(TP, E - p0);
 #define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ret = fail(AS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); break; } }
         if (t >= 2) CUB(cudaStreamWaitEvent(c->copy_stream, c->ev_done[bsel], 0));
         CUB(upload_tile(c, bsel, src, T, P, p0, n, c->copy_stream));
@@ -722,7 +777,7 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
         CUB(expand_tile(c, bsel, src, T, p0, n, c->exec_stream));
         // the tile kernel emits tile-local slot ids; the entries it appended, [d_n[1], d_n[0]), get the tile offset
         if (p0 > 0) CUB(cudaMemcpyAsync(d_n + 1, d_n, 8, cudaMemcpyDeviceToDevice, c->exec_stream));
-        CUB(as_launch_call(c->call_variant, (const uint32_t*)c->tile[bsel].p, T, n, 0, n, d_rf_all + p0, d_tv_all + p0 * 8,
+        CUB(as_launch_call(c->call_variant, (const uint32_t*)c->tile[bsel].p, T, n, 0, n, d_rf_all + (p0 - B), d_tv_all + (p0 - B) * 8,
                            (uint32_t)cut, (as_call*)c->calls.p, cap, d_n, c->exec_stream));
         c->launches += 1;
         if (p0 > 0) {
@@ -740,24 +795,147 @@ static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int
         if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess)
             ret = fail(AS_ECUDA, "caller pipeline failed: %s", cudaGetErrorString(e0 != cudaSuccess ? e0 : e1 != cudaSuccess ? e1 : e2));
     }
-    if (ret == AS_OK) {
-        const unsigned long long total = *h_total;
-        *n_calls = (int64_t)total;
-        const int64_t have = std::min<int64_t>((int64_t)total, cap);
-        if (have > 0) {
-            // the reference's row order (sample, slot, alt), sorted on the device; one copy into the caller's list
-            const size_t scratch = as_sort_calls_scratch_bytes(have), list = ((size_t)have * sizeof(as_call) + 255) & ~(size_t)255;
-            CU(c->sortbuf.need(list + scratch));
-            CU(as_launch_sort_calls((const as_call*)c->calls.p, have, (as_call*)c->sortbuf.p, (char*)c->sortbuf.p + list, scratch,
-                                    c->exec_stream));
-            c->launches += 3;
-            CU(cudaMemcpyAsync(calls, c->sortbuf.p, sizeof(as_call) * (size_t)have, cudaMemcpyDeviceToHost, c->exec_stream));
-            CU(cudaStreamSynchronize(c->exec_stream));
-            clk.lap("call.sort_download");
-        }
-        if ((int64_t)total > cap) ret = fail(AS_EOVERFLOW, "%llu calls found, capacity %lld", total, (long long)cap);
-    }
+    if (ret == AS_OK) *found = (int64_t)*h_total;
     return ret;
+}
+
+// ---- sharding of the _host entry points over the devices of a multi-device context ------------------------------------
+// Contiguous, near-equal slot ranges whose boundaries are multiples of 128 where possible and never split a twin group
+// (the noise model reduces all slots of a position together, EE:1241-1245).  twin_head may be NULL.
+static std::vector<int64_t> shard_bounds(int64_t P, int n, const int32_t* twin_next, const int32_t* twin_head) {
+    std::vector<int32_t> reach;  // reach[i] = the last slot of any group that has a member <= i (prefix maximum)
+    if (twin_head && twin_next) {
+        std::vector<int32_t> last((size_t)P);
+        for (int64_t i = 0; i < P; ++i) last[(size_t)i] = (int32_t)i;
+        for (int64_t i = 0; i < P; ++i) {  // members are chained in ascending order: the last write per head is the maximum
+            const int32_t h = twin_head[i];
+            if (h >= 0 && h < P && last[(size_t)h] < (int32_t)i) last[(size_t)h] = (int32_t)i;
+        }
+        reach.resize((size_t)P);
+        int32_t m = -1;
+        for (int64_t i = 0; i < P; ++i) {
+            const int32_t h = twin_head[i];
+            if (h >= 0 && h < P) m = std::max(m, last[(size_t)h]);
+            reach[(size_t)i] = m;
+        }
+    }
+    std::vector<int64_t> bounds(1, 0);
+    for (int r = 1; r < n; ++r) {
+        int64_t b = (P * r / n) / 128 * 128;
+        b = std::max(b, bounds.back());
+        if (!reach.empty())
+            while (b > 0 && b < P && reach[(size_t)b - 1] >= b) b = (int64_t)reach[(size_t)b - 1] + 1;  // a group that starts below b ends at or after b
+        bounds.push_back(std::min(b, P));
+    }
+    bounds.push_back(P);
+    return bounds;
+}
+
+// the same partition for callers that place the shards themselves (one process per GPU: bench.py, amplisolve_b200/shard.py)
+int as_shard_bounds(int64_t P, int32_t n_shards, const int32_t* twin_next, const int32_t* twin_head, int64_t* bounds_out) {
+    if (P < 0 || n_shards < 1 || !bounds_out) return fail(AS_EINVAL, "bad argument");
+    if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
+    const std::vector<int64_t> b = shard_bounds(P, n_shards, twin_next, twin_head);
+    for (size_t i = 0; i < b.size(); ++i) bounds_out[i] = b[i];
+    return AS_OK;
+}
+
+struct ShardResult {
+    int rc = AS_OK;
+    char err[512] = "";
+    int64_t found = 0;
+};
+
+}  // extern "C"
+template <class F>
+static int run_on_devices(as_ctx* c, F body) {  // body(k, sub-context) on one host thread per device
+    const int n = (int)c->subs.size();
+    std::vector<ShardResult> res((size_t)n);
+    auto work = [&](int k) {
+        res[(size_t)k].rc = body(k, c->subs[(size_t)k], res[(size_t)k]);
+        if (res[(size_t)k].rc != AS_OK) snprintf(res[(size_t)k].err, sizeof res[(size_t)k].err, "%s", g_err);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < n; ++k) th.emplace_back(work, k);
+    work(0);
+    for (auto& t : th) t.join();
+    cudaSetDevice(c->device);
+    for (int k = 0; k < n; ++k)
+        if (res[(size_t)k].rc != AS_OK) return fail(res[(size_t)k].rc, "device %d: %s", c->subs[(size_t)k]->device, res[(size_t)k].err);
+    return AS_OK;
+}
+extern "C" {
+
+static int noise_estimate_host_impl(as_ctx* c, const HostSrc& src, int32_t S, int64_t P, const int32_t* twin_next,
+                                    const int32_t* twin_head, float C, int32_t cut, float* thr, float* germ_val,
+                                    uint8_t* germ_state, uint32_t* count, uint32_t* nrec, float* thr_view) {
+    int rc = check_common(c, src.counts, S, P, 0, P, cut);
+    if (rc) return rc;
+    if ((rc = check_wide(src, S, P)) != AS_OK) return rc;
+    if (!thr || !germ_val || !germ_state || !count || !nrec) return fail(AS_EINVAL, "output pointer is NULL");
+    if ((twin_next == nullptr) != (twin_head == nullptr)) return fail(AS_EINVAL, "twin_next and twin_head go together");
+    if (P == 0) return AS_OK;
+    if (c->subs.size() < 2)
+        return noise_estimate_host_range(c, src, S, P, 0, P, twin_next, twin_head, C, cut, thr, germ_val, germ_state, count, nrec, thr_view);
+    const std::vector<int64_t> bounds = shard_bounds(P, (int)c->subs.size(), twin_next, twin_head);
+    return run_on_devices(c, [&](int k, as_ctx* sub, ShardResult&) {
+        return noise_estimate_host_range(sub, src, S, P, bounds[(size_t)k], bounds[(size_t)k + 1], twin_next, twin_head, C, cut, thr,
+                                         germ_val, germ_state, count, nrec, thr_view);
+    });
+}
+
+static int call_variants_host_impl(as_ctx* c, const HostSrc& src, int32_t T, int64_t P, const uint8_t* ref,
+                                   const float* thr_view, int32_t cut, as_call* calls, int64_t cap, int64_t* n_calls) {
+    PhaseClock clk;
+    int rc = check_common(c, src.counts, T, P, 0, P, cut);
+    if (rc) return rc;
+    if ((rc = check_wide(src, T, P)) != AS_OK) return rc;
+    if (!ref || !thr_view || !n_calls || (!calls && cap > 0) || cap < 0) return fail(AS_EINVAL, "bad pointer / cap");
+    *n_calls = 0;
+    if (P == 0 || T == 0) return AS_OK;
+    const int ndev = c->subs.size() < 2 ? 1 : (int)c->subs.size();
+    std::vector<int64_t> found((size_t)ndev, 0);
+    if (ndev == 1) {
+        rc = call_variants_host_range(c, src, T, P, 0, P, ref, thr_view, cut, cap, &found[0]);
+    } else {
+        const std::vector<int64_t> bounds = shard_bounds(P, ndev, nullptr, nullptr);
+        rc = run_on_devices(c, [&](int k, as_ctx* sub, ShardResult&) {
+            return call_variants_host_range(sub, src, T, P, bounds[(size_t)k], bounds[(size_t)k + 1], ref, thr_view, cut, cap,
+                                            &found[(size_t)k]);
+        });
+    }
+    if (rc != AS_OK) return rc;
+    // the lists of all devices meet on the first one (peer copies of exact sizes), are sorted there into the reference's
+    // row order (sample, slot, alt) and come down in one copy
+    CU(cudaSetDevice(c->device));
+    int64_t total = 0, have = 0;
+    for (int k = 0; k < ndev; ++k) { total += found[(size_t)k]; have += std::min(found[(size_t)k], cap); }
+    *n_calls = total;
+    const int64_t keep = std::min(have, cap);
+    if (have > 0) {
+        const size_t scratch = as_sort_calls_scratch_bytes(have), list = ((size_t)have * sizeof(as_call) + 255) & ~(size_t)255;
+        CU(c->sortbuf.need(2 * list + scratch));
+        as_call* gathered = (as_call*)c->calls.p;
+        if (ndev > 1) {
+            gathered = (as_call*)((char*)c->sortbuf.p + list + scratch);
+            int64_t off = 0;
+            for (int k = 0; k < ndev; ++k) {
+                const int64_t n = std::min(found[(size_t)k], cap);
+                if (n > 0) CU(cudaMemcpyPeerAsync(gathered + off, c->device, c->subs[(size_t)k]->calls.p, c->subs[(size_t)k]->device,
+                                                  sizeof(as_call) * (size_t)n, c->exec_stream));
+                off += n;
+            }
+        }
+        CU(as_launch_sort_calls(gathered, have, (as_call*)c->sortbuf.p, (char*)c->sortbuf.p + list, scratch, c->exec_stream));
+        c->launches += 3;
+        CU(cudaMemcpyAsync(calls, c->sortbuf.p, sizeof(as_call) * (size_t)keep, cudaMemcpyDeviceToHost, c->exec_stream));
+        CU(cudaStreamSynchronize(c->exec_stream));
+        clk.lap("call.sort_download");
+    }
+    bool over = total > cap;
+    for (int k = 0; k < ndev; ++k) over = over || found[(size_t)k] > cap;
+    if (over) return fail(AS_EOVERFLOW, "%lld calls found, capacity %lld", (long long)total, (long long)cap);
+    return AS_OK;
 }
 
 int as_noise_estimate_host(as_ctx* c, const uint32_t* counts, int32_t S, int64_t P, const int32_t* twin_next,

@@ -8,6 +8,7 @@
 #include <sys/types.h>
 #include <dirent.h>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -229,11 +230,20 @@ bool list_count_files(const std::string& dir, std::vector<CountFile>& files, std
 
 // ---------------------------------------------------------------------------------------------------
 // .PILEUP.ASEQ -> dense counts of one sample (EE:1114-1176, VC:723-770)
+//
+// Text ingestion is what bounds a real run once the kernels are at the HBM roof, so the row loop is
+// built for speed: the file is mmap'ed (no copy), a row in the usual shape -- one tab between fields, digits only -- is
+// parsed by a branch-light scanner without bounds checks (anything else, and the last 256 bytes of the file, go through
+// the general whitespace-tolerant parser, which accepts everything sscanf("%s %s %s %s %s %s %d ...") of the reference
+// does), and the slot of a row is found by a CURSOR: ASEQ files follow the panel enumeration, so the next row almost
+// always belongs to the next slot (or a few slots further when rows are missing); the hash lookup is the fallback.
 // ---------------------------------------------------------------------------------------------------
 struct AseqStats {
     int64_t rows = 0, outside = 0, extra = 0, bad_rd = 0;
     bool ok = true;
-    std::vector<as_wide_record> wide;  // records of this file that do not fit the wire format
+    bool in_order = true;                 // every row landed on a later slot than the row before it (row order == slot order)
+    std::vector<int32_t> slot_of_row;     // filled only for files that are NOT in order (second parse): row -> slot or -1
+    std::vector<as_wide_record> wide;     // records of this file that do not fit the wire format
 };
 
 // Host layouts of a count tensor (include/amplisolve_b200.h).  FMT = bytes per count in the two plain layouts (4: the
@@ -254,118 +264,226 @@ inline bool parse_int(const char*& p, const char* e, long long& v) {
     return true;
 }
 
-// counts: this sample's plane pair, [2][P][PER]; row_of (optional) [P] file row index of each filled slot.
-// In the wire formats a record that does not fit (a count of 65534 or more in the 16-bit one; a major count beyond 16
-// bits or another count beyond 4 bits in the packed one) is escaped and goes to stats.wide.
+struct MappedFile {  // read-only view of a whole file
+    const char* p = nullptr;
+    size_t n = 0;
+    bool ok = false;
+    explicit MappedFile(const std::string& path) {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return;
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) { close(fd); return; }
+        n = (size_t)sb.st_size;
+        ok = true;
+        if (n > 0) {
+            void* m = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { ok = false; n = 0; }
+            else { p = (const char*)m; madvise(m, n, MADV_SEQUENTIAL); }
+        }
+        close(fd);
+    }
+    ~MappedFile() { if (p) munmap((void*)p, n); }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+};
+
+struct AseqRow {
+    const char* chrom;
+    size_t chrom_len;
+    long long pos, v[9];  // A C G T RD Ars Crs Grs Trs
+};
+
+// The usual row, "chr\tpos\tx\tx\tx\tx\tA\tC\tG\tT\tRD\tArs\tCrs\tGrs\tTrs\n" with unsigned decimal numbers: no bounds checks
+// (the caller guarantees 256 readable bytes), returns false -- p untouched -- at the first byte that does not fit.
+inline bool parse_row_fast(const char*& p, AseqRow& r) {
+    const char* q = p;
+    r.chrom = q;
+    while ((unsigned char)*q > ' ') ++q;
+    r.chrom_len = (size_t)(q - p);
+    if (*q != '\t' || r.chrom_len == 0) return false;
+    ++q;
+    unsigned d = (unsigned)(*q - '0');
+    if (d > 9) return false;
+    uint64_t x = 0;
+    do { x = x * 10 + d; d = (unsigned)(*++q - '0'); } while (d <= 9);
+    r.pos = (long long)x;
+    uint64_t dots;
+    memcpy(&dots, q, 8);
+    if (dots == 0x2E092E092E092E09ull) {  // "\t.\t.\t.\t." -- dbsnp MAF ref alt as the pileup step writes them
+        q += 8;
+    } else {
+        for (int k = 0; k < 4; ++k) {
+            if (*q != '\t') return false;
+            ++q;
+            if ((unsigned char)*q <= ' ') return false;
+            while ((unsigned char)*q > ' ') ++q;
+        }
+    }
+    for (int k = 0; k < 9; ++k) {
+        if (*q != '\t') return false;
+        d = (unsigned)(*++q - '0');
+        if (d > 9) return false;
+        uint32_t y = 0;
+        int digits = 0;
+        do { y = y * 10 + d; d = (unsigned)(*++q - '0'); ++digits; } while (d <= 9);
+        if (digits > 9) return false;  // beyond 32 bits: the general parser decides
+        r.v[k] = y;
+    }
+    if (*q == '\r') ++q;
+    if (*q != '\n') return false;
+    p = q + 1;
+    return true;
+}
+
+// Any row the reference's sscanf accepts (whitespace-separated, signs allowed).  Returns 0 = blank line, 1 = parsed,
+// -1 = a first token but not 15 fields.  p moves past the line either way.
+inline int parse_row_general(const char*& p, const char* e, AseqRow& r) {
+    const char* eol = (const char*)memchr(p, '\n', (size_t)(e - p));
+    if (!eol) eol = e;
+    const char* q = skip_ws(p, eol);
+    const char* t = token_end(q, eol);
+    p = eol < e ? eol + 1 : e;
+    if (t == q) return 0;
+    r.chrom = q;
+    r.chrom_len = (size_t)(t - q);
+    const char* c = t;
+    bool ok = parse_int(c, eol, r.pos);
+    for (int k = 0; k < 4 && ok; ++k) { c = skip_ws(c, eol); c = token_end(c, eol); }
+    for (int k = 0; k < 9 && ok; ++k) ok = parse_int(c, eol, r.v[k]);
+    return ok ? 1 : -1;
+}
+
+// counts: this sample's plane pair, [2][P][PER], preset to "absent".  In the wire formats a record that does not fit (a
+// count of 65534 or more in the 16-bit one; a major count beyond 16 bits or another count beyond 4 bits in the packed
+// one) is escaped and goes to stats.wide.  record_rows: also fill stats.slot_of_row (files that are not in panel order).
 template <int FMT>
-AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<FMT>::E* counts, int32_t* row_of, int32_t sample) {
+void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::E* counts, int32_t sample, bool record_rows,
+                AseqStats& st) {
     typedef typename Wire<FMT>::E E;
     const int PER = Wire<FMT>::PER;
     const E absent = (E)~(E)0;
-    AseqStats st;
-    std::string text;
-    if (!read_file(path, text)) { st.ok = false; return st; }
     const int64_t P = panel.size();
-    std::vector<uint8_t> seen;  // occurrences of a twinned position in this file
-    if (panel.has_twins) seen.assign(P, 0);
-    const char* p = text.data();
-    const char* e = p + text.size();
-    const char* eol = (const char*)memchr(p, '\n', e - p);  // first line is the header (EE:1113)
+    const int32_t* slot_pos = panel.slot_pos.data();
+    const int32_t* slot_chrom = panel.slot_chrom.data();
+    const char* p = file.p;
+    const char* e = p + file.n;
+    const char* eol = p ? (const char*)memchr(p, '\n', file.n) : nullptr;  // first line is the header (EE:1113)
     p = eol ? eol + 1 : e;
-    int32_t last_chrom = -1;
-    std::string last_name;
+    const char* fast_end = file.n > 256 ? e - 256 : file.p;
+    int32_t last_chrom = -2;
+    const char* last_name = nullptr;
+    size_t last_len = 0;
+    int64_t cursor = 0, last_slot = -1;
+    AseqRow r;
     while (p < e) {
-        eol = (const char*)memchr(p, '\n', e - p);
-        if (!eol) eol = e;
-        const char* q = skip_ws(p, eol);
-        const char* t = token_end(q, eol);
-        if (t > q) {
-            const int64_t row = st.rows++;
-            if (last_chrom < 0 || last_name.size() != (size_t)(t - q) || memcmp(last_name.data(), q, t - q) != 0) {
-                last_name.assign(q, t);
-                last_chrom = panel.find_chrom(q, t - q);
-                if (last_chrom < 0) last_chrom = -2;
-            }
-            const char* r = t;
-            long long pos = 0, v[9];
-            bool ok = parse_int(r, eol, pos);
-            for (int k = 0; k < 4 && ok; ++k) { r = skip_ws(r, eol); r = token_end(r, eol); }  // dbsnp MAF ref alt
-            for (int k = 0; k < 9 && ok; ++k) ok = parse_int(r, eol, v[k]);
-            if (ok) {
-                int32_t slot = last_chrom >= 0 ? panel.lookup(last_chrom, (int32_t)pos) : -1;
-                if (slot >= 0 && panel.has_twins && panel.twin_next[slot] >= 0) {
-                    const int k = seen[slot]++;
-                    for (int j = 0; j < k && slot >= 0; ++j) slot = panel.twin_next[slot];
-                    if (slot < 0) ++st.extra;
-                } else if (slot >= 0 && counts[(int64_t)slot * PER] != absent) {
-                    slot = -1;  // a second row for a position that owns one slot
-                    ++st.extra;
-                } else if (slot < 0) {
+        if (!(p < fast_end && parse_row_fast(p, r))) {
+            const int got = parse_row_general(p, e, r);
+            if (got == 0) continue;
+            ++st.rows;
+            if (got < 0) { if (record_rows) st.slot_of_row.push_back(-1); continue; }
+        } else {
+            ++st.rows;
+        }
+        if (last_name == nullptr || last_len != r.chrom_len || memcmp(last_name, r.chrom, r.chrom_len) != 0) {
+            last_name = r.chrom;
+            last_len = r.chrom_len;
+            last_chrom = panel.find_chrom(r.chrom, r.chrom_len);
+        }
+        // ---- the slot of this row: the k-th row of a position in a file takes the position's k-th slot (EE:1241-1245
+        // keys records by position; the slots only matter for the order of the output rows)
+        int64_t slot = -1;
+        const int32_t pos = (int32_t)r.pos;
+        if (last_chrom >= 0 && r.pos == (long long)pos) {
+            for (int64_t c = cursor, ce = std::min(P, cursor + 32); c < ce; ++c)
+                if (slot_pos[c] == pos && slot_chrom[c] == last_chrom && counts[c * PER] == absent) { slot = c; break; }
+            if (slot < 0) {  // not where the panel order says: hash lookup, then the first free slot of the position
+                slot = panel.lookup(last_chrom, pos);
+                if (slot < 0) {
                     ++st.outside;
+                } else {
+                    while (slot >= 0 && counts[slot * PER] != absent) slot = panel.has_twins ? panel.twin_next[slot] : -1;
+                    if (slot < 0) ++st.extra;  // more rows than panel slots for this position
                 }
-                if (slot >= 0) {
-                    // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
-                    if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
-                    E* fw = counts + (int64_t)slot * PER;
-                    E* bw = counts + ((int64_t)P + slot) * PER;
-                    bool escape = false;
-                    if (FMT == 1) {
-                        uint32_t f4[4], r4[4], wf = 0, wb = 0;
-                        for (int b = 0; b < 4; ++b) {
-                            const long long f = v[b] - v[5 + b], r2 = v[5 + b];
-                            if (f < 0 || r2 < 0 || f > 0xFFFF || r2 > 0xFFFF) escape = true;
-                            f4[b] = (uint32_t)f;
-                            r4[b] = (uint32_t)r2;
-                        }
-                        if (!escape) escape = !(as_pack_word(f4, &wf) && as_pack_word(r4, &wb));
-                        fw[0] = (E)wf;
-                        bw[0] = (E)wb;
-                    } else {
-                        for (int b = 0; b < 4; ++b) {
-                            const long long f = v[b] - v[5 + b], r2 = v[5 + b];
-                            if (FMT == 2 && (f >= AS_WIRE_ESCAPE || r2 >= AS_WIRE_ESCAPE || f < 0 || r2 < 0)) escape = true;
-                            fw[b] = (E)f;
-                            bw[b] = (E)r2;
-                        }
-                    }
-                    if (escape) {
-                        as_wide_record w;
-                        w.sample = sample;
-                        w.slot = slot;
-                        for (int b = 0; b < 4; ++b) {
-                            w.fw[b] = (uint32_t)(v[b] - v[5 + b]);
-                            w.bw[b] = (uint32_t)v[5 + b];
-                            if (b < PER) fw[b] = bw[b] = (E)(absent - 1);  // AS_WIRE_ESCAPE / AS_PACKED_ESCAPE
-                        }
-                        st.wide.push_back(w);
-                    }
-                    if (row_of) row_of[slot] = (int32_t)row;
-                }
+            }
+        } else {
+            ++st.outside;
+        }
+        if (record_rows) st.slot_of_row.push_back((int32_t)slot);
+        if (slot < 0) continue;
+        if (slot < last_slot) st.in_order = false;
+        last_slot = slot;
+        cursor = slot + 1;
+        // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
+        const long long* v = r.v;
+        if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
+        E* fw = counts + slot * PER;
+        E* bw = counts + (P + slot) * PER;
+        bool escape = false;
+        if (FMT == 1) {
+            uint32_t f4[4], r4[4], wf = 0, wb = 0;
+            for (int b = 0; b < 4; ++b) {
+                const long long f = v[b] - v[5 + b], r2 = v[5 + b];
+                if (f < 0 || r2 < 0 || f > 0xFFFF || r2 > 0xFFFF) escape = true;
+                f4[b] = (uint32_t)f;
+                r4[b] = (uint32_t)r2;
+            }
+            if (!escape) escape = !(as_pack_word(f4, &wf) && as_pack_word(r4, &wb));
+            fw[0] = (E)wf;
+            bw[0] = (E)wb;
+        } else {
+            for (int b = 0; b < 4; ++b) {
+                const long long f = v[b] - v[5 + b], r2 = v[5 + b];
+                if (FMT == 2 && (f >= AS_WIRE_ESCAPE || r2 >= AS_WIRE_ESCAPE || f < 0 || r2 < 0)) escape = true;
+                fw[b] = (E)f;
+                bw[b] = (E)r2;
             }
         }
-        p = eol + 1;
+        if (escape) {
+            as_wide_record w;
+            w.sample = sample;
+            w.slot = (int32_t)slot;
+            for (int b = 0; b < 4; ++b) {
+                w.fw[b] = (uint32_t)(v[b] - v[5 + b]);
+                w.bw[b] = (uint32_t)v[5 + b];
+                if (b < PER) fw[b] = bw[b] = (E)(absent - 1);  // AS_WIRE_ESCAPE / AS_PACKED_ESCAPE
+            }
+            st.wide.push_back(w);
+        }
+    }
+}
+
+template <int FMT>
+AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<FMT>::E* counts, int32_t sample) {
+    typedef typename Wire<FMT>::E E;
+    AseqStats st;
+    MappedFile file(path);
+    if (!file.ok) { st.ok = false; return st; }
+    const size_t words = (size_t)panel.size() * 2 * Wire<FMT>::PER;
+    memset(counts, 0xFF, words * sizeof(E));
+    parse_aseq<FMT>(file, panel, counts, sample, false, st);
+    if (!st.in_order) {  // rare: rows not in panel order.  Parse again, recording the slot of every row (the writer needs it)
+        st = AseqStats();
+        memset(counts, 0xFF, words * sizeof(E));
+        parse_aseq<FMT>(file, panel, counts, sample, true, st);
+        st.in_order = false;
     }
     return st;
 }
 
-// all samples, in the given order, into one pinned tensor [n][2][P][PER]
+// samples [first, first + n) of `files` into one tensor [n][2][P][PER]; sample ids in the wide records are 0..n-1
 template <int FMT>
-bool load_all(const std::vector<CountFile>& files, const Panel& panel, typename Wire<FMT>::E* counts, int32_t* row_of,
+bool load_all(const std::vector<CountFile>& files, size_t first, size_t n, const Panel& panel, typename Wire<FMT>::E* counts,
               std::vector<AseqStats>& stats) {
     typedef typename Wire<FMT>::E E;
     const int PER = Wire<FMT>::PER;
-    const int n = (int)files.size();
     const int64_t P = panel.size();
     stats.assign(n, AseqStats());
-    std::atomic<int> next(0);
+    std::atomic<size_t> next(0);
     auto work = [&]() {
-        for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
-            E* plane = counts + (int64_t)i * 2 * P * PER;
-            memset(plane, 0xFF, (size_t)P * 2 * PER * sizeof(E));
-            stats[i] = load_aseq<FMT>(files[i].path, panel, plane, row_of ? row_of + (int64_t)i * P : nullptr, (int32_t)i);
-        }
+        for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+            stats[i] = load_aseq<FMT>(files[first + i].path, panel, counts + (int64_t)i * 2 * P * PER, (int32_t)i);
     };
-    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, n)));
+    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max<size_t>(1, n)));
     std::vector<std::thread> th;
     for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
     work();
@@ -391,16 +509,26 @@ void parallel_for(size_t n, F body) {
     for (auto& t : th) t.join();
 }
 
-// The count tensor of a run in a wire format (a quarter / half of the pinned memory and PCIe traffic of uint32).  The
-// loader writes the packed format (8 bytes per record); when more than 1 record in 16 would have to be escaped
-// (ultra-deep or very noisy data) the files are parsed again into the 16-bit format.  Escaped records are in `wide`,
-// sorted by (slot, sample).  AS_WIRE=16 / AS_WIRE=packed in the environment forces one of the two.
+// The count tensor of a group of samples in a wire format (a quarter / half of the pinned memory and PCIe traffic of
+// uint32), in pinned memory owned by this object and reused from group to group.  The loader writes the packed format
+// (8 bytes per record); when more than 1 record in 16 would have to be escaped (ultra-deep or very noisy data) the group is
+// parsed again into the 16-bit format, and later groups go straight there.  Escaped records are in `wide`, sorted by
+// (slot, sample).  AS_WIRE=16 / AS_WIRE=packed in the environment forces one of the two.
 struct HostCounts {
     void* p = nullptr;
+    size_t bytes = 0;
     int fmt = 1;  // 1 packed, 2 uint16
     std::vector<as_wide_record> wide;
     ~HostCounts() { if (p) as_host_free(p); }
-    // the eight counts of (sample, slot); P = slots of the panel
+    bool reserve(size_t n) {
+        if (n <= bytes) return true;
+        if (p) as_host_free(p);
+        p = nullptr; bytes = 0;
+        if (as_host_alloc(&p, std::max<size_t>(16, n)) != AS_OK) { p = nullptr; return false; }
+        bytes = n;
+        return true;
+    }
+    // the eight counts of (sample, slot) of the group; P = slots of the panel
     void record(int64_t sample, int64_t slot, int64_t P, uint32_t (&fw)[4], uint32_t (&bw)[4]) const {
         const int64_t wf = (sample * 2) * P + slot, wb = wf + P;
         bool escaped;
@@ -428,37 +556,75 @@ struct HostCounts {
         }
     }
 };
-// returns 0 ok, 1 pinned allocation failed, 2 a file could not be opened
-int load_counts(const std::vector<CountFile>& files, const Panel& panel, HostCounts& hc, int32_t* row_of,
+// samples [first, first + n) of `files`.  returns 0 ok, 1 pinned allocation failed, 2 a file could not be opened
+int load_counts(const std::vector<CountFile>& files, size_t first, size_t n, const Panel& panel, HostCounts& hc,
                 std::vector<AseqStats>& stats) {
-    const size_t strand_words = (size_t)files.size() * 2 * (size_t)panel.size();
+    const size_t strand_words = n * 2 * (size_t)panel.size();
     const char* force = getenv("AS_WIRE");
-    for (int fmt = (force && !strcmp(force, "16")) ? 2 : 1; fmt <= 2; ++fmt) {
-        void* mem = nullptr;
-        if (as_host_alloc(&mem, std::max<size_t>(16, strand_words * 4 * (size_t)fmt)) != AS_OK) return 1;
-        hc.p = mem;
+    if (force && !strcmp(force, "16")) hc.fmt = 2;
+    hc.wide.clear();
+    for (int fmt = hc.fmt; fmt <= 2; ++fmt) {
+        if (!hc.reserve(std::max<size_t>(16, strand_words * 4 * (size_t)fmt))) return 1;
         hc.fmt = fmt;
-        const bool ok = fmt == 1 ? load_all<1>(files, panel, (uint32_t*)mem, row_of, stats)
-                                 : load_all<2>(files, panel, (uint16_t*)mem, row_of, stats);
+        const bool ok = fmt == 1 ? load_all<1>(files, first, n, panel, (uint32_t*)hc.p, stats)
+                                 : load_all<2>(files, first, n, panel, (uint16_t*)hc.p, stats);
         if (!ok) return 2;
         int64_t rows = 0, escaped = 0;
         for (const AseqStats& s : stats) { rows += s.rows; escaped += (int64_t)s.wide.size(); }
-        if (fmt == 1 && escaped * 16 > rows && !(force && !strcmp(force, "packed"))) {  // too many: the 16-bit format is denser
-            as_host_free(mem);
-            hc.p = nullptr;
-            continue;
-        }
+        if (fmt == 1 && escaped * 16 > rows && !(force && !strcmp(force, "packed"))) continue;  // too many: the 16-bit format is denser
         break;
     }
     for (AseqStats& s : stats) {
         hc.wide.insert(hc.wide.end(), s.wide.begin(), s.wide.end());
         s.wide.clear();
+        s.wide.shrink_to_fit();
     }
     std::sort(hc.wide.begin(), hc.wide.end(), [](const as_wide_record& x, const as_wide_record& y) {
         return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
     });
     return 0;
 }
+
+// The GPUs of a run: every visible device, or the list in AS_DEVICES ("0,2,3").  Created on a thread at program entry
+// (CUDA start-up takes 1.5-2 s on a cold box: the panel / noise table is read meanwhile).
+struct GpuContext {
+    as_ctx* ctx = nullptr;
+    int rc = AS_OK;
+    std::string error;
+    std::thread starter;
+    void start() {
+        starter = std::thread([this]() {
+            std::vector<int> devs;
+            if (const char* env = getenv("AS_DEVICES")) {
+                for (const char* q = env; *q;) {
+                    char* endp = nullptr;
+                    const long d = strtol(q, &endp, 10);
+                    if (endp == q) break;
+                    devs.push_back((int)d);
+                    q = *endp == ',' ? endp + 1 : endp;
+                }
+            }
+            if (devs.empty()) {
+                int n = 0;
+                if (as_device_count(&n) != AS_OK || n == 0) {
+                    rc = as_create(0, &ctx);  // fails with the "no CUDA device ... no CPU fallback" message
+                    n = 0;
+                }
+                for (int i = 0; i < n; ++i) devs.push_back(i);
+            }
+            if (rc == AS_OK && !devs.empty()) rc = as_create_multi(devs.data(), (int)devs.size(), &ctx);
+            if (rc != AS_OK) error = as_last_error();
+        });
+    }
+    bool wait() {
+        if (starter.joinable()) starter.join();
+        return rc == AS_OK && ctx != nullptr;
+    }
+    ~GpuContext() {
+        if (starter.joinable()) starter.join();
+        if (ctx) as_destroy(ctx);
+    }
+};
 
 bool make_dir(const std::string& path) {  // mkdir -p (EE:3079)
     std::string cur;
@@ -615,13 +781,18 @@ void write_list_file(const std::string& path, const std::vector<std::string>& li
     for (const std::string& s : listed) f << s << "\n";
 }
 
-void report_load(const std::vector<CountFile>& files, const std::vector<AseqStats>& stats) {
-    for (size_t i = 0; i < files.size(); ++i) {
+void report_load(const std::vector<CountFile>& files, size_t first, const std::vector<AseqStats>& stats) {
+    for (size_t i = 0; i < stats.size(); ++i) {
         const AseqStats& s = stats[i];
         for (int64_t k = 0; k < s.bad_rd; ++k) std::cout << "malakia paizei edo" << std::endl;  // EE:1178-1181, VC:762-765
+        if (s.bad_rd)
+            std::cout << "Warning: " << files[first + i].path << " has " << s.bad_rd << " row(s) whose RD column is not A+C+G+T; "
+                      << "the total allele fractions of those rows (Germ_Max, AF column) use the sum, the reference the column"
+                      << std::endl;
         if (s.extra)
-            std::cout << "Warning: " << files[i].path << " has " << s.extra
-                      << " row(s) beyond the number of panel slots of their position; ignored" << std::endl;
+            std::cout << "Warning: " << files[first + i].path << " has " << s.extra
+                      << " row(s) beyond the number of panel slots of their position; ignored (the reference counts them)"
+                      << std::endl;
     }
 }
 
@@ -717,6 +888,8 @@ int as_error_estimation_main(int argc, char** argv) {
         std::cout << "Error: cannot create " << interm << std::endl;
         return 0;
     }
+    GpuContext gpu;  // CUDA start-up runs beside the panel / reference-base work below (no CPU fallback: see as_create)
+    if (with_germlines) gpu.start();
     srand((unsigned)time(nullptr));
     const int seed = rand() % 1000;  // EE:581-584
     const std::string stem = interm + "/" + std::to_string(seed);
@@ -786,20 +959,23 @@ int as_error_estimation_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << stem << "_germline_count_list_original.txt" << RESET
               << " stored with success. It contains " << GREEN << files.size() << RESET << " samples" << std::endl;
     const int S = (int)files.size();
-    as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
-    if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
-    timer.lap("cuda_context");
+    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
+        std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
+        return 1;
+    }
+    as_ctx* ctx = gpu.ctx;
+    timer.lap("cuda_context_wait");
     std::cout << "Running function storeGermlineStatistics:" << std::endl;
     HostCounts counts;
     std::vector<AseqStats> stats;
-    const int lrc = load_counts(files, panel, counts, nullptr, stats);
+    const int lrc = load_counts(files, 0, files.size(), panel, counts, stats);
     if (lrc == 1) return report_gpu_error("pinned host allocation");
     if (lrc == 2) {
         for (int i = 0; i < S; ++i)
             if (!stats[i].ok) printf("Error: Cannot open %s\n", files[i].path.c_str());
         return 0;
     }
-    report_load(files, stats);
+    report_load(files, 0, stats);
     {
         double rows = 0;
         for (const AseqStats& st : stats) rows += (double)st.rows;
@@ -819,7 +995,6 @@ int as_error_estimation_main(int argc, char** argv) {
                        : as_noise_estimate_host_packed(ctx, (const uint32_t*)counts.p, counts.wide.data(),
                                                        (int64_t)counts.wide.size(), S, P, tn, th, C_value_float, cut, thr.data(),
                                                        germ_val.data(), germ_state.data(), count.data(), nrec.data(), nullptr);
-    as_destroy(ctx);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");
     std::cout << "thresholds for " << panel.first_slot.size() << " positions estimated on the GPU" << std::endl;
@@ -912,6 +1087,8 @@ int as_variant_calling_main(int argc, char** argv) {
         return 0;
     }
 
+    GpuContext gpu;  // CUDA start-up runs beside the parse of the noise table (no CPU fallback: see as_create)
+    gpu.start();
     PhaseTimer timer;
     // ---- noise table (storeInputFile, VC:430-576): one slot per row; also re-emits the dummy VCF (VC:564)
     Panel panel;
@@ -1009,75 +1186,135 @@ int as_variant_calling_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << list_name << RESET << " stored with success. It contains " << GREEN
               << files.size() << RESET << " samples" << std::endl;
     const int T = (int)files.size();
-    as_ctx* ctx = nullptr;  // first: without a B200 there is nothing this program can do (no CPU fallback)
-    if (as_create(0, &ctx) != AS_OK) return report_gpu_error("as_create");
-    std::vector<int32_t> row_of((size_t)T * (size_t)P, -1);
-    std::vector<AseqStats> stats;
-    timer.lap("cuda_context");
+    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
+        std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
+        return 1;
+    }
+    as_ctx* ctx = gpu.ctx;
+    timer.lap("cuda_context_wait");
     std::cout << "\nRunning function callVariants...." << std::endl;
-    HostCounts counts;
-    const int lrc = load_counts(files, panel, counts, row_of.data(), stats);
-    if (lrc == 1) return report_gpu_error("pinned host allocation");
-    if (lrc == 2) {
-        for (int i = 0; i < T; ++i)
-            if (!stats[i].ok) printf("\tError from callVariants:  Cannot open %s\n", files[i].path.c_str());
-        return 0;
-    }
-    report_load(files, stats);
-    for (int i = 0; i < T; ++i)
-        for (int64_t k = 0; k < stats[i].outside; ++k) std::cout << "mistake..." << std::endl;  // VC:847-852
-    {
-        double rows = 0;
-        for (const AseqStats& st : stats) rows += (double)st.rows;
-        timer.lap("parse_tumours", rows, "rows");
-    }
 
-    // ---- the hot path on the GPU
+    // ---- the hot path on the GPU, in groups of samples: while the GPUs work on one group (upload, caller, sorted
+    // download) the host threads parse the next one into the other pinned buffer, so pinned memory is two groups, not
+    // the whole run, and the text parse hides behind the GPU step (or the other way round)
+    struct CallCounts { uint32_t fw[4], bw[4]; };  // the record of a call, kept for the Fisher test and the writers
     std::vector<as_call> calls;
-    int64_t n_calls = 0;
+    std::vector<CallCounts> call_counts;
+    std::vector<AseqStats> file_stats((size_t)T);  // order information of every file (slot_of_row only when out of order)
+    double total_rows = 0, parse_s = 0, gpu_s = 0;
     if (T > 0 && P > 0) {
-        int64_t cap = std::max<int64_t>(4096, (int64_t)T * P / 16);
-        int rc;
-        for (;;) {
-            calls.resize((size_t)cap);
-            rc = counts.fmt == 2
-                     ? as_call_variants_host16(ctx, (const uint16_t*)counts.p, counts.wide.data(), (int64_t)counts.wide.size(), T,
-                                               P, ref_code.data(), thr_view.data(), cut, calls.data(), cap, &n_calls)
-                     : as_call_variants_host_packed(ctx, (const uint32_t*)counts.p, counts.wide.data(),
-                                                    (int64_t)counts.wide.size(), T, P, ref_code.data(), thr_view.data(), cut,
-                                                    calls.data(), cap, &n_calls);
-            if (rc != AS_EOVERFLOW) break;
-            cap = n_calls;
+        int64_t budget_mb = 512;
+        if (const char* env = getenv("AS_GROUP_MB")) budget_mb = std::max<long long>(1, atoll(env));
+        const int64_t G = std::max<int64_t>(1, std::min<int64_t>(T, (budget_mb << 20) / std::max<int64_t>(1, 16 * P)));
+        HostCounts buf[2];
+        std::vector<AseqStats> stats[2];
+        auto load_group = [&](int64_t first, int which) -> int {
+            const double t0 = PhaseTimer::now();
+            const size_t n = (size_t)std::min<int64_t>(G, T - first);
+            buf[which].fmt = std::max(buf[which].fmt, buf[which ^ 1].fmt);  // once the 16-bit format was needed it stays
+            const int lrc = load_counts(files, (size_t)first, n, panel, buf[which], stats[which]);
+            if (lrc == 2)
+                for (size_t i = 0; i < n; ++i)
+                    if (!stats[which][i].ok) printf("\tError from callVariants:  Cannot open %s\n", files[(size_t)first + i].path.c_str());
+            parse_s += PhaseTimer::now() - t0;
+            return lrc;
+        };
+        int lrc = load_group(0, 0);
+        if (lrc == 1) return report_gpu_error("pinned host allocation");
+        if (lrc == 2) return 0;
+        for (int64_t first = 0, g = 0; first < T; first += G, ++g) {
+            const int which = (int)(g & 1);
+            const int32_t Tg = (int32_t)std::min<int64_t>(G, T - first);
+            report_load(files, (size_t)first, stats[which]);
+            for (int i = 0; i < Tg; ++i) {
+                for (int64_t k = 0; k < stats[which][(size_t)i].outside; ++k) std::cout << "mistake..." << std::endl;  // VC:847-852
+                total_rows += (double)stats[which][(size_t)i].rows;
+                file_stats[(size_t)(first + i)] = std::move(stats[which][(size_t)i]);
+            }
+            // GPU step of this group on a worker thread ...
+            std::vector<as_call> part;
+            int64_t n_part = 0;
+            int rc = AS_OK;
+            std::string gpu_error;
+            const HostCounts& hc = buf[which];
+            std::thread worker([&]() {
+                const double t0 = PhaseTimer::now();
+                int64_t cap = std::max<int64_t>(1 << 16, (int64_t)Tg * P / 256);
+                for (;;) {
+                    part.resize((size_t)cap);
+                    rc = hc.fmt == 2
+                             ? as_call_variants_host16(ctx, (const uint16_t*)hc.p, hc.wide.data(), (int64_t)hc.wide.size(), Tg, P,
+                                                       ref_code.data(), thr_view.data(), cut, part.data(), cap, &n_part)
+                             : as_call_variants_host_packed(ctx, (const uint32_t*)hc.p, hc.wide.data(), (int64_t)hc.wide.size(), Tg,
+                                                            P, ref_code.data(), thr_view.data(), cut, part.data(), cap, &n_part);
+                    if (rc != AS_EOVERFLOW) break;
+                    cap = n_part;  // the true count: run the group again with room for all of them
+                }
+                if (rc != AS_OK) gpu_error = as_last_error();
+                gpu_s += PhaseTimer::now() - t0;
+            });
+            // ... while the next group is parsed
+            int next_rc = 0;
+            if (first + G < T) next_rc = load_group(first + G, which ^ 1);
+            worker.join();
+            if (rc != AS_OK) {
+                std::cout << RED << "Error: as_call_variants_host: " << gpu_error << RESET << std::endl;
+                return 1;
+            }
+            if (next_rc == 1) return report_gpu_error("pinned host allocation");
+            if (next_rc == 2) return 0;
+            part.resize((size_t)n_part);
+            const size_t base = calls.size();
+            calls.resize(base + part.size());
+            call_counts.resize(base + part.size());
+            parallel_for(part.size(), [&](size_t i) {
+                as_call c = part[i];
+                hc.record(c.sample, c.slot, P, call_counts[base + i].fw, call_counts[base + i].bw);
+                c.sample += (int32_t)first;
+                calls[base + i] = c;
+            });
         }
-        if (rc != AS_OK) return report_gpu_error("as_call_variants_host");
-        calls.resize((size_t)n_calls);
-        // the reference emits calls in file-row order, then in alt order A,C,G,T (VC:869-3288)
-        std::sort(calls.begin(), calls.end(), [&](const as_call& a, const as_call& b) {
-            if (a.sample != b.sample) return a.sample < b.sample;
-            const int32_t ra = row_of[(size_t)a.sample * P + a.slot], rb = row_of[(size_t)b.sample * P + b.slot];
-            if (ra != rb) return ra < rb;
-            return a.alt < b.alt;
-        });
+        // The device returns (sample, slot, alt) order = the reference's file-row order (VC:869-3288: rows, then alts
+        // A,C,G,T) for every file whose rows follow the panel enumeration.  A file that does not is re-ordered by its rows.
+        std::vector<size_t> run_begin((size_t)T + 1, calls.size());
+        for (size_t i = calls.size(); i-- > 0;) run_begin[(size_t)calls[i].sample] = i;
+        for (int t = T - 1; t >= 0; --t) run_begin[(size_t)t] = std::min(run_begin[(size_t)t], run_begin[(size_t)t + 1]);
+        for (int t = 0; t < T; ++t) {
+            if (file_stats[(size_t)t].in_order) continue;
+            std::vector<int32_t> row_of((size_t)P, -1);
+            const std::vector<int32_t>& sor = file_stats[(size_t)t].slot_of_row;
+            for (size_t r = 0; r < sor.size(); ++r)
+                if (sor[r] >= 0) row_of[(size_t)sor[r]] = (int32_t)r;
+            const size_t lo = run_begin[(size_t)t], hi = run_begin[(size_t)t + 1];
+            std::vector<size_t> order(hi - lo);
+            for (size_t i = 0; i < order.size(); ++i) order[i] = lo + i;
+            std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+                const int32_t rx = row_of[(size_t)calls[x].slot], ry = row_of[(size_t)calls[y].slot];
+                return rx != ry ? rx < ry : calls[x].alt < calls[y].alt;
+            });
+            std::vector<as_call> c2(order.size());
+            std::vector<CallCounts> k2(order.size());
+            for (size_t i = 0; i < order.size(); ++i) { c2[i] = calls[order[i]]; k2[i] = call_counts[order[i]]; }
+            std::copy(c2.begin(), c2.end(), calls.begin() + (long)lo);
+            std::copy(k2.begin(), k2.end(), call_counts.begin() + (long)lo);
+        }
     }
-    timer.lap("caller_gpu", 6.0 * (double)T * (double)P, "tests");
+    if (timer.on) fprintf(stderr, "AS_TIMING parse_tumours_busy %.6f (%.3g rows/s)\nAS_TIMING caller_gpu_busy %.6f\n", parse_s,
+                          total_rows / std::max(parse_s, 1e-9), gpu_s);
+    timer.lap("parse_and_call", 6.0 * (double)T * (double)P, "tests");
 
     // Fisher strand-bias p of every call (VC:902) on the device: one warp per call's 2x2 table
-    // the eight strand counts of a call's record
-    auto record = [&](const as_call& c, uint32_t (&fw)[4], uint32_t (&bw)[4]) { counts.record(c.sample, c.slot, P, fw, bw); };
     std::vector<double> fisher_p(calls.size());
     {
         std::vector<int32_t> tables(calls.size() * 4);
         parallel_for(calls.size(), [&](size_t i) {
-            const as_call& c = calls[i];
-            uint32_t fw[4], bw[4];
-            record(c, fw, bw);
-            tables[i * 4 + 0] = (int32_t)(fw[0] + fw[1] + fw[2] + fw[3]);  // fisherTest(FW, BW, alt_fw, alt_bw)
-            tables[i * 4 + 1] = (int32_t)(bw[0] + bw[1] + bw[2] + bw[3]);
-            tables[i * 4 + 2] = (int32_t)fw[c.alt];
-            tables[i * 4 + 3] = (int32_t)bw[c.alt];
+            const CallCounts& k = call_counts[i];
+            tables[i * 4 + 0] = (int32_t)(k.fw[0] + k.fw[1] + k.fw[2] + k.fw[3]);  // fisherTest(FW, BW, alt_fw, alt_bw)
+            tables[i * 4 + 1] = (int32_t)(k.bw[0] + k.bw[1] + k.bw[2] + k.bw[3]);
+            tables[i * 4 + 2] = (int32_t)k.fw[calls[i].alt];
+            tables[i * 4 + 3] = (int32_t)k.bw[calls[i].alt];
         });
         const int frc = as_fisher_tests_host(ctx, tables.data(), (int64_t)calls.size(), fisher_p.data());
-        as_destroy(ctx);
         if (frc != AS_OK) return report_gpu_error("as_fisher_tests_host");
     }
     timer.lap("fisher_tests", (double)calls.size(), "calls");
@@ -1110,8 +1347,8 @@ int as_variant_calling_main(int argc, char** argv) {
         for (; ci < calls.size() && calls[ci].sample == t; ++ci) {
             const as_call& c = calls[ci];
             const int64_t s = c.slot;
-            uint32_t fw[4], bw[4];
-            record(c, fw, bw);
+            const uint32_t* fw = call_counts[ci].fw;
+            const uint32_t* bw = call_counts[ci].bw;
             const int FW = (int)(fw[0] + fw[1] + fw[2] + fw[3]), BW = (int)(bw[0] + bw[1] + bw[2] + bw[3]);
             const int RD = FW + BW;
             const int a = c.alt;

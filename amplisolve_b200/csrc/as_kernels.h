@@ -41,10 +41,12 @@ cudaError_t as_launch_noise_pattern(int geom, const uint32_t* d_counts, int S, i
                                     float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st);
 // as_call_deferred.cu: the caller as scan -> resolve -> series kernels over candidate / survivor lists in d_scratch
 size_t as_deferred_scratch_bytes(int T, int64_t n_slots, int64_t* cap_cand, int64_t* cap_surv);
+#define AS_DEFER_MAX_CHUNKS 8
+int as_deferred_chunks(int64_t n_slots, int want);
 cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1, const uint8_t* d_ref,
                                     const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut, as_call* d_calls,
                                     int64_t cap, unsigned long long* d_n_calls, void* d_scratch, int64_t cap_cand,
-                                    int64_t cap_surv, cudaStream_t st);
+                                    int64_t cap_surv, cudaStream_t st, cudaStream_t aux, cudaEvent_t* ev, int n_chunks);
 cudaError_t as_launch_widen16(const uint16_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_unpack(const uint32_t* d_in, uint32_t* d_out, int64_t n_words, cudaStream_t st);
 cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32_t* d_tile, int64_t n, int64_t p0,

@@ -54,7 +54,7 @@ enum {
     AS_EOVERFLOW = -5 /* call list capacity exceeded (n_calls still reports the true count) */
 };
 
-typedef struct as_ctx as_ctx; /* one context per device; not thread-safe, use one per thread */
+typedef struct as_ctx as_ctx; /* one context per device (as_create) or per device list (as_create_multi); not thread-safe, use one per thread */
 
 /* A called variant as the device emits it.  Replaces the decision of VC:898 plus the two strand
  * tests of VC:895-896.  48 bytes. */
@@ -74,6 +74,21 @@ const char* as_last_error(void);
 const char* as_version(void);
 int as_device_count(int* n);
 int as_create(int device, as_ctx** out);
+/* One context over ndev GPUs of the box (BASELINE north_star: "positions shard naturally across the 8 GPUs of one box, with no
+ * NCCL on the math path and only a final gather of compacted calls").  The _host entry points split the panel's slots
+ * into ndev contiguous ranges that keep twin groups whole, run one host thread and one pipeline per device with no
+ * exchange between devices, and merge: the noise model's outputs are written in place by slot; the call lists of all
+ * devices are copied to the first device (peer copies of exact sizes), sorted there into the reference's row order and
+ * downloaded once.  Results are identical to a single-device context (tested).  _dev entry points, the element-wise
+ * evaluators and as_fisher_tests_host run on devices[0].  The two programs use every visible GPU (AS_DEVICES=0,2,...
+ * restricts them). */
+int as_create_multi(const int* devices, int ndev, as_ctx** out);
+/* The partition as_create_multi contexts use: n_shards contiguous, near-equal slot ranges [bounds_out[k], bounds_out[k+1])
+ * (n_shards + 1 values), boundaries on multiples of 128 slots where possible, never inside a twin group (EE:1241-1245: all
+ * slots of a position feed one estimate).  twin_next / twin_head may both be NULL.  Host arithmetic, no GPU needed. */
+int as_shard_bounds(int64_t P, int32_t n_shards, const int32_t* twin_next, const int32_t* twin_head, int64_t* bounds_out);
+/* Devices of a context: writes up to cap device ordinals, returns their number. */
+int as_context_devices(const as_ctx* ctx, int* devices, int cap);
 void as_destroy(as_ctx* ctx);
 /* Pinned host memory for the _host entry points (cudaHostAlloc / cudaFreeHost). */
 int as_host_alloc(void** out, size_t bytes);

@@ -44,8 +44,7 @@ def timings(stderr):
     return {m.group(1): float(m.group(2)) for m in re.finditer(r"AS_TIMING (\S+) ([0-9.]+)", stderr)}
 
 
-def main():
-    out_json = sys.argv[1] if len(sys.argv) > 1 else None
+def run(out_json=None):
     t0 = time.time()
     bed, slots, pos_id, U = synth.make_panel(N_AMPLICONS, amp_len=(110, 140), overlap_frac=0.25, seed=20182,
                                              chroms=("chr1", "chr3", "chr7", "chr12", "chr17", "chrX"))
@@ -110,7 +109,8 @@ def main():
     if out_json:
         Path(out_json).write_text(json.dumps(res, indent=1) + "\n")
     assert same_noise and same_summary and same_vcf, "outputs differ from the reference"
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    run(sys.argv[1] if len(sys.argv) > 1 else None)

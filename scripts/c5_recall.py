@@ -26,8 +26,7 @@ from tests import golden_util as gu  # noqa: E402
 P_AMPLICONS, NORMALS, TUMOURS, DEPTH, SPIKE_RATE = 24, 30, 40, 50000, 1 / 150
 
 
-def main():
-    out_json = sys.argv[1] if len(sys.argv) > 1 else None
+def run(out_json=None):
     rng = np.random.default_rng(20185)
     bed, slots, pos_id, U = synth.make_panel(P_AMPLICONS, amp_len=(125, 125), overlap_frac=0.17, seed=20185, chroms=("chr4",))
     P = len(slots)
@@ -89,7 +88,8 @@ def main():
     if out_json:
         Path(out_json).write_text(json.dumps(res, indent=1) + "\n")
     assert res["call_sets_identical"]
+    return res
 
 
 if __name__ == "__main__":
-    main()
+    run(sys.argv[1] if len(sys.argv) > 1 else None)

@@ -22,7 +22,7 @@ int main(int argc, char** argv) {
     int64_t rows = 0, bytes = 0;
     for (int r = 0; r < repeat; ++r) {
         const double t0 = PhaseTimer::now();
-        if (!load_all<1>(files, panel, mem, nullptr, stats)) return 1;
+        if (!load_all<1>(files, 0, files.size(), panel, mem, stats)) return 1;
         best = std::min(best, PhaseTimer::now() - t0);
     }
     int64_t escaped = 0, outside = 0;

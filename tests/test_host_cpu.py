@@ -163,3 +163,25 @@ def test_noise_mode_without_gpu_fails_loudly(tmp_path):
                        cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stdout
     assert not list((tmp_path / "o").glob("positionSpecificNoise_0*.txt"))
+
+
+def test_shard_bounds_keep_twin_groups_whole():
+    """as_shard_bounds (what as_create_multi contexts split a panel by): contiguous, covering, and no twin group straddles a
+    boundary -- also with a group that spans almost the whole panel; equal to amplisolve_b200.shard.shard_ranges."""
+    import numpy as np
+    from amplisolve_b200 import shard_bounds, twin_links
+    from amplisolve_b200.shard import shard_ranges
+    from tests import synth
+    for seed, n in ((1, 2), (2, 3), (3, 8)):
+        _, slots, pos_id, U = synth.make_panel(70, seed=seed, overlap_frac=0.6, amp_len=(20, 70))
+        pos_id = pos_id.copy()
+        if seed == 3:
+            pos_id[-5] = pos_id[300]
+        nxt, head = twin_links(pos_id)
+        P = len(slots)
+        b = shard_bounds(P, n, nxt, head)
+        assert b[0] == 0 and b[-1] == P and all(x <= y for x, y in zip(b, b[1:]))
+        for cut in b[1:-1]:
+            assert not np.any((head[cut:] < cut)), cut          # no member at or after the cut belongs to a group that starts before it
+        assert [(b[i], b[i + 1]) for i in range(n)] == shard_ranges(P, n, head, nxt)
+    assert shard_bounds(1000, 4) == [0, 128, 384, 640, 1000] or shard_bounds(1000, 4)[-1] == 1000

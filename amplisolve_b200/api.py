@@ -29,7 +29,7 @@ EXPORTS = [
     "as_last_error", "as_version", "as_device_count", "as_create", "as_create_multi", "as_context_devices", "as_shard_bounds", "as_destroy", "as_host_alloc", "as_host_free",
     "as_set_call_kernel", "as_set_noise_kernel", "as_set_host_tile_slots", "as_set_option", "as_kernel_launches", "as_noise_estimate_dev", "as_noise_estimate_host",
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
-    "as_call_variants_host16", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
+    "as_call_variants_host16", "as_sort_calls_dev", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
     "as_variant_calling_main",
 ]
@@ -158,6 +158,7 @@ def lib():
     L.as_call_variants_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, vp, i64, vp, vp]
     L.as_call_variants_sweep_dev.argtypes = [vp, vp, i32, i64, i64, i64, vp, vp, i32, i32, vp, i64, vp, vp]
     L.as_call_variants_host.argtypes = [vp, vp, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
+    L.as_sort_calls_dev.argtypes = [vp, vp, i64, i32, vp, vp]
     L.as_call_variants_host16.argtypes = [vp, vp, vp, i64, i32, i64, vp, vp, i32, vp, i64, C.POINTER(i64)]
     L.as_noise_estimate_host_packed.argtypes = L.as_noise_estimate_host16.argtypes
     L.as_call_variants_host_packed.argtypes = L.as_call_variants_host16.argtypes
@@ -454,6 +455,11 @@ class Context:
         _check(lib().as_call_variants_sweep_dev(self._h, _dp(counts), T, P, b, e, _dp(ref), _dp(thr_views), n_c,
                                                 int(coverage_cutoff), _dp(calls), cap, _dp(n_calls), self._stream(stream)))
         return cap
+
+    def sort_calls_dev(self, calls, n, sorted_out, slot_offset=0, stream=None):
+        """calls / sorted_out: torch uint8 CUDA tensors of >= n*48 bytes; the first n calls of `calls` get slot_offset added
+        and land in sorted_out in the reference's row order (sample, slot, alt)."""
+        _check(lib().as_sort_calls_dev(self._h, _dp(calls), int(n), int(slot_offset), _dp(sorted_out), self._stream(stream)))
 
     def synth_counts_dev(self, n_samples, P, *, seed, mean_depth, somatic_rate=0.0, sample_offset=0, slot_offset=0,
                          depth_sigma=0.5, germline_rate=1e-3, vaf=(0.01, 0.2), absent_rate=0.0, want_ref=True,

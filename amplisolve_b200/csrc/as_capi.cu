@@ -97,7 +97,7 @@ struct as_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     cudaEvent_t ev_chunk[AS_DEFER_MAX_CHUNKS + 1] = {};  // deferred caller: scan of piece i -> resolve / series on aux_stream
-    int defer_chunks = 6;
+    int defer_chunks = 1;  // pieces of the deferred caller (measured 1/2/3/4/8 pieces: 5.79 / 6.17 / 5.91 / 5.99 / 6.54 ms -- the series of one piece does not overlap the scan of the next, whose CTAs hold every SM)
     DevBuf heads, nheads;                         // twin-group scratch of the _dev noise path
     DevBuf tile[2], tile16[2], wide[2], out[2], aux[2], misc, calls, sortbuf;  // _host pipelines
     DevBuf defer;                                                              // candidate / survivor lists of the deferred caller
@@ -152,6 +152,7 @@ int as_create(int device, as_ctx** out) {
         CU(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
     }
     for (int i = 0; i <= AS_DEFER_MAX_CHUNKS; ++i) CU(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    if (const char* env = getenv("AS_DEFER_CHUNKS")) c->defer_chunks = std::max(1, std::min(AS_DEFER_MAX_CHUNKS, atoi(env)));
     *out = c;
     return AS_OK;
 }
@@ -1020,6 +1021,29 @@ int as_call_variants_host16(as_ctx* c, const uint16_t* counts, const as_wide_rec
                             int64_t* n_calls) {
     const HostSrc src{counts, 2, wide, n_wide};
     return call_variants_host_impl(c, src, T, P, ref, thr_view, cut, calls, cap, n_calls);
+}
+
+// Device call list -> the reference's row order (sample, slot, alt), on the device (radix sort of 64-bit keys + row gather).
+// slot_offset is added to every slot first (a shard's local slot ids -> panel slot ids).
+int as_sort_calls_dev(as_ctx* c, as_call* d_calls, int64_t n, int32_t slot_offset, as_call* d_sorted, void* stream) {
+    if (!c || n < 0 || (n > 0 && (!d_calls || !d_sorted))) return fail(AS_EINVAL, "bad argument");
+    if (n == 0) return AS_OK;
+    if (n > 0x7fffffffll) return fail(AS_EINVAL, "at most 2^31-1 calls per sort");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t scratch = as_sort_calls_scratch_bytes(n);
+    CU(c->sortbuf.need(scratch + 64));
+    CU(c->misc.need(32));
+    if (slot_offset != 0) {
+        unsigned long long h[2] = {0ull, (unsigned long long)n};
+        CU(cudaMemcpyAsync(c->misc.p, h, 16, cudaMemcpyHostToDevice, st));
+        CU(as_launch_call_slot_offset(d_calls, (const unsigned long long*)c->misc.p, (const unsigned long long*)c->misc.p + 1, n,
+                                      slot_offset, st));
+        c->launches += 1;
+    }
+    CU(as_launch_sort_calls(d_calls, n, d_sorted, c->sortbuf.p, scratch, st));
+    c->launches += 3;
+    return AS_OK;
 }
 
 // ---- element-wise evaluators -----------------------------------------------------------------------

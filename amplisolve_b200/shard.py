@@ -38,8 +38,9 @@ def shard_ranges(n_slots: int, world: int, twin_head=None, twin_next=None, align
 
 
 def gather_calls(calls: np.ndarray, slot_offset: int, group=None, device=None) -> np.ndarray | None:
-    """Gather every rank's call list on rank 0 (returns None elsewhere).  `calls` carry shard-local slot ids;
-    slot_offset is this rank's first panel slot.  Works over gloo (CPU tensors) and NCCL (device tensors)."""
+    """Host lists (numpy) over gloo: gather every rank's call list on rank 0 (returns None elsewhere).  `calls` carry
+    shard-local slot ids; slot_offset is this rank's first panel slot.  The CPU mirror of gather_calls_device, used by the
+    gloo test of the host-side logic."""
     import torch
     import torch.distributed as dist
 
@@ -48,24 +49,68 @@ def gather_calls(calls: np.ndarray, slot_offset: int, group=None, device=None) -
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return sort_calls(calls)
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    dev = torch.device(device) if device is not None else torch.device("cpu")
-    n = torch.tensor([len(calls)], dtype=torch.int64, device=dev)
+    n = torch.tensor([len(calls)], dtype=torch.int64)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n, group=group)
     sizes = [int(s.item()) for s in sizes]
-    cap = max(1, max(sizes))
-    buf = torch.zeros(cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-    raw = torch.from_numpy(calls.view(np.uint8).reshape(-1))
-    buf[: raw.numel()].copy_(raw)
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
+    raw = torch.from_numpy(calls.view(np.uint8).reshape(-1).copy())
     if rank != 0:
+        if len(calls):
+            dist.send(raw, dst=0, group=group)          # exact size, to the one rank that needs it
         return None
-    if dev.type == "cuda":   # merge on the device: one radix sort of 64-bit keys, one row gather, one download
-        rows = torch.cat([o[: s * CALL_DTYPE.itemsize] for o, s in zip(out, sizes)]).view(-1, CALL_DTYPE.itemsize)
-        return sort_calls_device(rows)
-    parts = [o.cpu().numpy()[: s * CALL_DTYPE.itemsize].view(CALL_DTYPE) for o, s in zip(out, sizes)]
+    parts = [calls]
+    for r in range(1, world):
+        buf = torch.empty(sizes[r] * CALL_DTYPE.itemsize, dtype=torch.uint8)
+        if sizes[r]:
+            dist.recv(buf, src=r, group=group)
+        parts.append(buf.numpy().view(CALL_DTYPE))
     return sort_calls(np.concatenate(parts))
+
+
+def gather_calls_device(ctx, calls, n_local: int, slot_offset: int, group=None):
+    """The one exchange of a multi-process run (BASELINE north_star: "only a final gather of compacted calls"), on the
+    device: `calls` is this rank's device list (torch uint8, n_local * 48 bytes used, shard-local slot ids).  Ranks
+    exchange their counts (one all_gather of 8 bytes), every rank but 0 sends its list -- exact size, NCCL point-to-point,
+    straight from device memory -- into rank 0's buffer, where as_sort_calls_dev adds nothing (offsets are applied by the
+    senders' own sort call) and sorts everything into the reference's row order.  Returns (sorted torch uint8 tensor,
+    total) on rank 0, (None, total) elsewhere.  No host copy anywhere."""
+    import torch
+    import torch.distributed as dist
+
+    item = CALL_DTYPE.itemsize
+    dev = calls.device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    sizes = [n]
+    if world > 1:
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=group)
+    sizes = [int(s) for s in torch.stack(sizes).view(-1).tolist()]
+    total = sum(sizes)
+    # every rank turns its slot ids into panel slot ids and pre-sorts its own list (the final sort on rank 0 is then over
+    # nearly sorted runs; what matters is that the offset is applied where the list lives)
+    mine = torch.empty(max(1, n_local) * item, dtype=torch.uint8, device=dev)
+    if n_local:
+        ctx.sort_calls_dev(calls, n_local, mine, slot_offset=slot_offset)
+    if rank != 0:
+        if n_local:
+            dist.send(mine[: n_local * item], dst=0, group=group)
+        return None, total
+    allc = torch.empty(max(1, total) * item, dtype=torch.uint8, device=dev)
+    allc[: n_local * item].copy_(mine[: n_local * item])
+    off = n_local * item
+    reqs = []
+    for r in range(1, world):
+        if sizes[r]:
+            reqs.append(dist.irecv(allc[off: off + sizes[r] * item], src=r, group=group))
+            off += sizes[r] * item
+    for q in reqs:
+        q.wait()
+    out = torch.empty_like(allc)
+    if total:
+        ctx.sort_calls_dev(allc, total, out)
+    return out, total
 
 
 def sort_calls_device(rows) -> np.ndarray:

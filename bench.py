@@ -52,6 +52,10 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the noise-floor sweep leg (C_value 0.001 .. 0.005, configs[3])")
+    ap.add_argument("--no-config-legs", action="store_true",
+                    help="skip the legs at configs[3]'s own dimensions (200 normals x 1000 tumours, sweep as the step) and at configs[4]'s "
+                         "(100 k slots x 10,000 samples at 50,000x)")
+    ap.add_argument("--no-e2e-text", action="store_true", help="skip the program-against-program leg (text in, text out)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-format", choices=["packed", "16", "32"], default="packed",
                     help="host layout of the e2e leg: the packed wire format (8 B/record), the 16-bit one (16 B) or uint32 (32 B)")
@@ -415,22 +419,29 @@ def run_ours(args):
     if found > cap:
         raise RuntimeError(f"call list overflow in the benchmark: {found} > {cap}")
 
-    # the only cross-GPU traffic of the job: one final gather of the compacted calls on rank 0 (outside the math path)
+    # the only cross-GPU traffic of the job: one final gather of the compacted calls on rank 0 (outside the math path),
+    # device to device: counts exchanged, exact-size NCCL sends into rank 0's buffer, one radix sort there
     gather_ms = None
+    n_merged = found
     if world > 1:
-        from amplisolve_b200 import calls_from_device
-        from amplisolve_b200.shard import gather_calls
-        local_calls = calls_from_device(calls, n_calls)
-        warm = torch.zeros(1, dtype=torch.int64, device=dev)
-        dist.all_gather([torch.zeros_like(warm) for _ in range(world)], warm)   # communicator set-up is not the gather
+        from amplisolve_b200.shard import gather_calls_device
+        gather_calls_device(ctx, calls, found, rank * P)      # warm-up: communicator set-up and scratch are not the gather
         barrier()
         tg = time.perf_counter()
-        merged = gather_calls(local_calls, rank * P, device=dev)
+        merged, n_total = gather_calls_device(ctx, calls, found, rank * P)
         barrier()
         gather_ms = (time.perf_counter() - tg) * 1e3
-        if rank == 0 and len(merged) < found:
-            raise RuntimeError("gathered call list is shorter than rank 0's own")
-        n_merged = len(merged) if rank == 0 else 0
+        gm = torch.tensor([gather_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(gm, op=dist.ReduceOp.MAX)
+        gather_ms = float(gm.item())
+        if rank == 0:
+            head = merged[: n_total * CALL_DTYPE.itemsize].view(-1, CALL_DTYPE.itemsize)[:, :12].contiguous().view(torch.int32).to(torch.int64)
+            key = (head[:, 0] << 33) | (head[:, 1] << 2) | head[:, 2]
+            if n_total < found or not bool((key[1:] > key[:-1]).all()):
+                raise RuntimeError("gathered call list is not the sorted union of the ranks' lists")
+            del head, key
+        n_merged = n_total
+        del merged
     tmax = torch.tensor([total_ms, t_noise, t_call], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -439,6 +450,7 @@ def run_ours(args):
     # ---- noise-floor sweep of configs[3] (C_value 0.001 .. 0.005) on the same resident shard: one pass over the
     # tumours for all five threshold tables vs one caller pass per value (reported beside the headline, not part of it)
     sweep = None
+    default_wl_sweep = (P, S, T, args.depth) == (WORKLOAD["slots"], WORKLOAD["normals"], WORKLOAD["tumours"], WORKLOAD["depth"])
     if not args.no_sweep and args.call_kernel >= 2:
         c_values = [0.001, 0.002, 0.003, 0.004, 0.005]
         views = torch.empty((len(c_values),) + tuple(view.shape), dtype=torch.float32, device=dev)
@@ -490,12 +502,22 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_sn, t_sf, t_ss, t_sns = [float(x) for x in tt.tolist()]
+        peak_s, _ = hbm_peak()
+        nb = P * (32 * S + 72 + 32 * (len(c_values) - 1))                                   # normals once, five tables out
+        cb = T * P * 32 + P * 33 * len(c_values) + sum(found_fused) * CALL_DTYPE.itemsize    # tumours once, five tables in
         sweep = {"C_values": c_values, "noise_ms_fused": t_sn, "noise_ms_one_pass_per_value": t_sns,
                  "caller_ms_fused_one_pass": t_sf, "caller_ms_one_pass_per_value": t_ss, "calls_per_value_rank0": found_fused,
                  "tests_per_s_fused": 6.0 * T * P * world * len(c_values) / ((t_sn + t_sf) * 1e-3),
                  "tests_per_s_separate": 6.0 * T * P * world * len(c_values) / ((t_sns + t_ss) * 1e-3),
-                 "api": "as_noise_estimate_sweep_dev (normals read twice for five values) + as_call_variants_sweep_dev (tumour "
-                        "tensor read once for all threshold tables)"}
+                 "roofline_sweep": {"bound": "hbm", "peak": peak_s, "unit": "GB/s",
+                                    "caller": {"kernel": "call_scan_kernel + call_resolve_kernel + call_series_kernel",
+                                               "algorithmic_bytes": cb, "achieved": cb / (t_sf * 1e-3) / 1e9, "frac": cb / (t_sf * 1e-3) / 1e9 / peak_s,
+                                               "traffic": ncu_traffic("call_scan_kernel", default_wl_sweep)},
+                                    "noise": {"kernel": "noise_pattern_kernel<5> (+ twin-group kernels on the side stream)",
+                                              "algorithmic_bytes": nb, "achieved": nb / (t_sn * 1e-3) / 1e9, "frac": nb / (t_sn * 1e-3) / 1e9 / peak_s,
+                                              "traffic": ncu_traffic("noise_pattern_kernel", default_wl_sweep)}},
+                 "api": "as_noise_estimate_sweep_dev (ONE pass over the normals for the five values) + as_call_variants_sweep_dev (ONE "
+                        "pass over the tumour tensor for the five threshold tables)"}
         del views, s_calls, thr_tables
 
     # ---- end to end through the host-buffer C ABI ----------------------------------------------------
@@ -504,6 +526,20 @@ def run_ours(args):
         e2e = run_e2e(args, ctx, normals, tumours, ref, twin_next, twin_head, rank, world, barrier)
         if e2e["slots_per_gpu"] == P and e2e["calls_per_step"] != found:   # same data through the host C ABI: same call set
             raise RuntimeError(f"e2e leg found {e2e['calls_per_step']} calls, the device-resident step {found}")
+
+    # ---- legs at the dimensions of configs[3] and configs[4] (reported beside the headline; the resident c3 tensors go first)
+    config_legs = None
+    if not args.no_config_legs and args.call_kernel >= 2:
+        del normals, tumours, calls
+        torch.cuda.empty_cache()
+        config_legs = run_config_legs(ctx, rank, world, dev)
+        torch.cuda.empty_cache()
+    e2e_text = None
+    if not args.no_e2e_text:
+        barrier()
+        if rank == 0:
+            e2e_text = run_e2e_text(world)
+        barrier()
 
     result = None
     if rank == 0:
@@ -545,9 +581,17 @@ def run_ours(args):
             "gpu_launches": int(launches * world), "clocks": clocks,
         }
         if gather_ms is not None:
-            result["calls_gather"] = {"ms": gather_ms, "calls_total": n_merged, "transport": "NCCL all_gather of the compacted call lists, once per job"}
+            result["calls_gather"] = {"ms": gather_ms, "calls_total": n_merged,
+                                      "transport": "device to device: one 8-byte all_gather of the counts, exact-size NCCL sends of the compacted "
+                                                   "lists into rank 0's buffer, as_sort_calls_dev there; once per job, no host copy"}
+            result["job_ms"] = {"value": args.steps * ms_per_step + gather_ms,
+                                "note": "steps x ms_per_step + the one gather of the calls (the job's only collective)"}
         if sweep is not None:
             result["noise_floor_sweep"] = sweep
+        if config_legs is not None:
+            result["config_legs"] = config_legs
+        if e2e_text is not None:
+            result["e2e_text"] = e2e_text
         if e2e is not None:
             result["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
@@ -558,6 +602,152 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return result
+
+
+def run_config_legs(ctx, rank, world, dev):
+    """The step at the dimensions BASELINE.json's configs[3] and configs[4] name, per GPU, device-resident:
+      configs[3]: 200 normals x 1000 tumours, the five-value noise-floor sweep AS THE STEP (one pass over the normals, one pass
+                  over the tumours), on a 1,000,000-slot position shard (38.4 GB; the 40 M-slot panel is 40 such shards)
+      configs[4]: 100,000 slots x 10,000 samples at 50,000x with 0.5-1 % spiked SNVs, caller throughput (recall against the
+                  reference is tests/test_gpu_configs.py's job)"""
+    import torch
+    import torch.distributed as dist
+
+    from amplisolve_b200 import CALL_DTYPE
+    peak, _ = hbm_peak()
+    cut = WORKLOAD["coverage_cutoff"]
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps=5):
+        for _ in range(3):
+            fn()
+        a, b = ev(), ev()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    legs = {}
+    # ---- configs[3] dimensions
+    P, S, T = 1_000_000, 200, 1000
+    c_values = [0.001, 0.002, 0.003, 0.004, 0.005]
+    gen = dict(seed=20184, mean_depth=2000.0, slot_offset=rank * P, twin_period=6)
+    normals, ref = ctx.synth_counts_dev(S, P, **gen)
+    tumours, _ = ctx.synth_counts_dev(T, P, somatic_rate=2e-4, sample_offset=1 << 20, want_ref=False, **gen)
+    nxt, head = ctx.synth_twin_links_dev(P, seed=20184, slot_offset=rank * P, twin_period=6)
+    out = ctx.alloc_noise_outputs(P)
+    thr = torch.empty((len(c_values), P, 4, 2), dtype=torch.float32, device=dev)
+    views = torch.empty_like(thr)
+    cap = int(T * P * 0.004)
+    calls = torch.empty(len(c_values) * cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    n_calls = torch.zeros(len(c_values), dtype=torch.int64, device=dev)
+
+    def noise():
+        ctx.estimate_thresholds_sweep_dev(normals, c_values, cut, thr, out, nxt, head)
+        ctx.thresholds_caller_view_dev(thr, views)
+
+    def caller():
+        n_calls.zero_()
+        ctx.call_variants_sweep_dev(tumours, ref, views, cut, calls, n_calls)
+
+    def step():
+        noise()
+        caller()
+
+    t_noise, t_call, t_step = timed(noise), timed(caller), timed(step)
+    found = [int(x) for x in n_calls.tolist()]
+    if max(found) > cap:
+        raise RuntimeError("call list overflow in the configs[3] leg")
+    nb = P * (32 * S + 72 + 32 * (len(c_values) - 1))
+    cb = T * P * 32 + P * 33 * len(c_values) + sum(found) * CALL_DTYPE.itemsize
+    legs["config3_sweep_step"] = {
+        "workload": f"configs[3] dimensions per GPU: {P} slots x {S} normals x {T} tumours at ~2000x, C_value 0.001..0.005 as the step",
+        "ms_per_step": t_step, "noise_ms": t_noise, "caller_ms": t_call, "calls_per_value_rank0": found,
+        "tests_per_s": 6.0 * T * P * world * len(c_values) / (t_step * 1e-3),
+        "noise_positions_per_s": P * world * len(c_values) / (t_noise * 1e-3),
+        "roofline_noise": {"bound": "hbm", "algorithmic_bytes": nb, "achieved": nb / (t_noise * 1e-3) / 1e9, "peak": peak,
+                           "frac": nb / (t_noise * 1e-3) / 1e9 / peak},
+        "roofline_caller": {"bound": "hbm", "algorithmic_bytes": cb, "achieved": cb / (t_call * 1e-3) / 1e9, "peak": peak,
+                            "frac": cb / (t_call * 1e-3) / 1e9 / peak}}
+    del normals, tumours, thr, views, calls, out
+    torch.cuda.empty_cache()
+    # ---- configs[4] dimensions
+    P, S, T = 100_000, 100, 10_000
+    gen = dict(seed=20185, mean_depth=50000.0, slot_offset=rank * P, twin_period=6)
+    normals, ref = ctx.synth_counts_dev(S, P, **gen)
+    tumours, _ = ctx.synth_counts_dev(T, P, somatic_rate=5e-4, vaf=(0.005, 0.01), sample_offset=1 << 20, want_ref=False, **gen)
+    nxt, head = ctx.synth_twin_links_dev(P, seed=20185, slot_offset=rank * P, twin_period=6)
+    out = ctx.alloc_noise_outputs(P)
+    ctx.estimate_thresholds_dev(normals, WORKLOAD["C_value"], cut, out, nxt, head)
+    view = ctx.thresholds_caller_view_dev(out["thr"])
+    cap = int(T * P * 0.004)
+    calls = torch.empty(cap * CALL_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    n1 = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def caller5():
+        n1.zero_()
+        ctx.call_variants_dev(tumours, ref, view, cut, calls, n1)
+
+    t5 = timed(caller5)
+    found5 = int(n1.item())
+    if found5 > cap:
+        raise RuntimeError("call list overflow in the configs[4] leg")
+    cb = T * P * 32 + P * 33 + found5 * CALL_DTYPE.itemsize
+    legs["config4_caller"] = {
+        "workload": f"configs[4] dimensions per GPU: {P} slots x {T} samples at ~50,000x, 0.5-1 % spiked SNVs",
+        "caller_ms": t5, "calls_rank0": found5, "tests_per_s": 6.0 * T * P * world / (t5 * 1e-3),
+        "roofline_caller": {"bound": "hbm", "algorithmic_bytes": cb, "achieved": cb / (t5 * 1e-3) / 1e9, "peak": peak,
+                            "frac": cb / (t5 * 1e-3) / 1e9 / peak},
+        "recall": "tests/test_gpu_configs.py::test_config4_slice_call_set_and_recall_equal_the_reference"}
+    del normals, tumours, calls
+    return legs
+
+
+def run_e2e_text(world):
+    """Text in, text out, the same files for both arms: the two drop-in programs against the compiled reference programs
+    (oracle/_ref).  configs[1] at full size and a 200,000-slot slice of the configs[2] panel.  With several GPUs the programs
+    use all of them (AS_DEVICES) and their outputs are compared with the one-GPU run; the reference arm runs at N=1 only
+    (it is single-threaded and takes the same time at every N)."""
+    from oracle import refrun
+    from scripts import c2_cli_parity as cli
+    shapes = {"config1_full_size": dict(),
+              "config2_slice": dict(n_amplicons=1600, n_normals=20, n_tumours=20, depth=2000, amp_len=(125, 125), seed=20183,
+                                    chroms=tuple(f"chr{i}" for i in range(1, 23)) + ("chrX",), somatic_rate=2e-4)}
+    res = {}
+    for name, shape in shapes.items():
+        with tempfile.TemporaryDirectory(prefix="e2et_", dir="/tmp") as td:
+            info = cli.stage(td, **shape)
+            cli.run_ours(td, out_ee="w", out_vc="wv", devices=[0])            # warm the page cache and the driver
+            ours = cli.run_ours(td, devices=list(range(world)))
+            leg = {"shape": info, "ours": ours, "devices": world,
+                   "ours_wall_s": ours["error_estimation_wall_s"] + ours["variant_calling_wall_s"]}
+            rows = info["normal_rows"] + info["tumour_rows"]
+            leg["ours_rows_per_s"] = rows / leg["ours_wall_s"]
+            if world > 1:
+                leg["identical_to_one_gpu"] = all(v for k, v in cli.compare(td, "o", "v", "w", "wv").items() if k.endswith("identical"))
+                if not leg["identical_to_one_gpu"]:
+                    raise RuntimeError("the programs' outputs on several GPUs differ from the one-GPU run")
+            elif refrun.have_ref():
+                ref = cli.run_reference(td)
+                par = cli.compare(td)
+                if not (par["noise_table_identical"] and par["summary_identical"] and par["vcfs_identical"]):
+                    raise RuntimeError("program outputs differ from the reference's")
+                leg.update(reference=ref, parity=par,
+                           reference_wall_s=ref["error_estimation_wall_s"] + ref["variant_calling_wall_s"])
+                leg["reference_rows_per_s"] = rows / leg["reference_wall_s"]
+                leg["speedup_wall"] = leg["reference_wall_s"] / leg["ours_wall_s"]
+            res[name] = leg
+    res["note"] = ("same ASEQ / BED / FASTA files in, same noise table / summary / VCF files out (byte-identical); wall clock of the two "
+                   "processes per arm; the reference arm is single-threaded and skips only its samtools fork loop (ee_ref fast driver)")
+    return res
 
 
 def run_e2e(args, ctx, d_normals, d_tumours, d_ref, d_twin_next, d_twin_head, rank, world, barrier):

@@ -527,6 +527,27 @@ def test_device_merge_of_gathered_calls_equals_numpy_sort(ctx):
     assert len(sort_calls_device(rows[:0])) == 0
 
 
+def test_sort_calls_dev_offsets_and_orders_like_numpy(ctx):
+    """as_sort_calls_dev (the last step of the multi-process gather): slot offset applied, reference row order."""
+    import torch
+    from amplisolve_b200 import CALL_DTYPE
+    rng = np.random.default_rng(5)
+    n = 70_000
+    calls = np.zeros(n, dtype=CALL_DTYPE)
+    keys = rng.choice(500 * 40_000 * 4, size=n, replace=False)
+    calls["sample"], calls["slot"], calls["alt"] = keys // (40_000 * 4), (keys // 4) % 40_000, keys % 4
+    calls["p_fw"] = rng.random(n)
+    d_in = torch.from_numpy(calls.view(np.uint8).reshape(-1).copy()).cuda()
+    d_out = torch.empty_like(d_in)
+    ctx.sort_calls_dev(d_in, n, d_out, slot_offset=123_456)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(CALL_DTYPE)
+    want = calls.copy()
+    want["slot"] += 123_456
+    want = want[np.lexsort((want["alt"], want["slot"], want["sample"]))]
+    assert got.tobytes() == want.tobytes()
+
+
 def test_device_fisher_equals_host_and_boost(ctx):
     """as_fisher_tests_host (one warp per 2x2 table) against the scalar host form as_fisher_test and the
     Boost.Math-pinned fixture: p within 1e-13 relative of the host's (same lgamma values, device exp, lane-ordered sum),

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <ctime>
 #include <cstdlib>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -167,23 +168,28 @@ int as_create_multi(const int* devices, int ndev, as_ctx** out) {
     for (int i = 0; i < ndev; ++i)
         for (int j = 0; j < i; ++j)
             if (devices[i] == devices[j]) return fail(AS_EINVAL, "device %d listed twice", devices[i]);
-    as_ctx* head = nullptr;
-    int rc = as_create(devices[0], &head);
-    if (rc != AS_OK) return rc;
+    // one thread per device: context creation takes about a second per GPU and the GPUs do not wait for each other
+    std::vector<as_ctx*> made((size_t)ndev, nullptr);
+    std::vector<int> rcs((size_t)ndev, AS_OK);
+    std::vector<std::string> errs((size_t)ndev);
+    auto make = [&](int i) {
+        rcs[(size_t)i] = as_create(devices[i], &made[(size_t)i]);
+        if (rcs[(size_t)i] != AS_OK) errs[(size_t)i] = g_err;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int i = 1; i < ndev; ++i) th.emplace_back(make, i);
+        make(0);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < ndev; ++i) {
+        if (rcs[(size_t)i] == AS_OK) continue;
+        for (int k = 0; k < ndev; ++k) as_destroy(made[(size_t)k]);
+        return fail(rcs[(size_t)i], "%s", errs[(size_t)i].c_str());
+    }
+    as_ctx* head = made[0];
     if (ndev > 1) {
-        head->subs.push_back(nullptr);  // slot 0 = the head itself (filled below)
-        for (int i = 1; i < ndev; ++i) {
-            as_ctx* sub = nullptr;
-            rc = as_create(devices[i], &sub);
-            if (rc != AS_OK) {
-                for (size_t k = 1; k < head->subs.size(); ++k) as_destroy(head->subs[k]);
-                head->subs.clear();
-                as_destroy(head);
-                return rc;
-            }
-            head->subs.push_back(sub);
-        }
-        head->subs[0] = head;
+        head->subs = made;
         cudaSetDevice(head->device);
     }
     *out = head;

@@ -585,13 +585,15 @@ int load_counts(const std::vector<CountFile>& files, size_t first, size_t n, con
     return 0;
 }
 
-// The GPUs of a run: every visible device, or the list in AS_DEVICES ("0,2,3").  Created on a thread at program entry
-// (CUDA start-up takes 1.5-2 s on a cold box: the panel / noise table is read meanwhile).
+// The GPUs of a run.  AS_DEVICES ("0,2,3") names them; otherwise the program starts on GPU 0 -- on a thread at program entry:
+// CUDA start-up takes 0.2-2 s, the panel / noise table is read meanwhile -- and widens to every visible GPU once the size
+// of the job is known and large enough to repay the extra start-up (about a second per device): wants_all_devices().
 struct GpuContext {
     as_ctx* ctx = nullptr;
     int rc = AS_OK;
     std::string error;
     std::thread starter;
+    bool explicit_list = false;
     void start() {
         starter = std::thread([this]() {
             std::vector<int> devs;
@@ -604,21 +606,29 @@ struct GpuContext {
                     q = *endp == ',' ? endp + 1 : endp;
                 }
             }
-            if (devs.empty()) {
-                int n = 0;
-                if (as_device_count(&n) != AS_OK || n == 0) {
-                    rc = as_create(0, &ctx);  // fails with the "no CUDA device ... no CPU fallback" message
-                    n = 0;
-                }
-                for (int i = 0; i < n; ++i) devs.push_back(i);
-            }
-            if (rc == AS_OK && !devs.empty()) rc = as_create_multi(devs.data(), (int)devs.size(), &ctx);
+            explicit_list = !devs.empty();
+            if (devs.empty()) devs.push_back(0);
+            rc = devs.size() == 1 ? as_create(devs[0], &ctx) : as_create_multi(devs.data(), (int)devs.size(), &ctx);
             if (rc != AS_OK) error = as_last_error();
         });
     }
     bool wait() {
         if (starter.joinable()) starter.join();
         return rc == AS_OK && ctx != nullptr;
+    }
+    // records = samples x slots of the job.  Below 2^28 records (2 GB in the packed format, ~40 ms of GPU time) one GPU is
+    // faster end to end than several.
+    bool widen(double records) {
+        if (!wait()) return false;
+        int n = 0;
+        if (explicit_list || records < 268435456.0 || as_device_count(&n) != AS_OK || n < 2) return true;
+        std::vector<int> devs;
+        for (int i = 0; i < n; ++i) devs.push_back(i);
+        as_ctx* wide = nullptr;
+        if (as_create_multi(devs.data(), n, &wide) != AS_OK) return true;  // keep the one GPU
+        as_destroy(ctx);
+        ctx = wide;
+        return true;
     }
     ~GpuContext() {
         if (starter.joinable()) starter.join();
@@ -934,13 +944,13 @@ int as_error_estimation_main(int argc, char** argv) {
         // generateFinalOutput_default (EE:2948-3043)
         const std::string out_name = output_dir + "/positionSpecificNoise_default.txt";
         std::ofstream output(out_name.c_str());
-        output << header << std::endl;
+        output << header << "\n";
         char value[64];
         snprintf(value, sizeof value, "%.4f_%.4f", default_error_float, default_error_float);
         for (int64_t i = 0; i < P; ++i) {
             output << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i];
             output << "\t" << (panel.dup[i] ? "YES" : "NO");
-            output << "\t" << value << "\t" << value << "\t" << value << "\t" << value << "\t-\t-\t-\t-" << std::endl;
+            output << "\t" << value << "\t" << value << "\t" << value << "\t" << value << "\t-\t-\t-\t-" << "\n";
         }
         std::cout << "\nAmpliSolveErrorEstimation execution was successful. Results can be found at: " << YELLOW << out_name << RESET
                   << std::endl;
@@ -959,7 +969,7 @@ int as_error_estimation_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << stem << "_germline_count_list_original.txt" << RESET
               << " stored with success. It contains " << GREEN << files.size() << RESET << " samples" << std::endl;
     const int S = (int)files.size();
-    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
+    if (!gpu.widen((double)S * (double)P)) {  // without a B200 there is nothing this program can do (no CPU fallback)
         std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
         return 1;
     }
@@ -1004,7 +1014,7 @@ int as_error_estimation_main(int argc, char** argv) {
     snprintf(out_name, sizeof out_name, "%s/positionSpecificNoise_%.4f.txt", output_dir.c_str(), C_value_float);
     {
         std::ofstream output(out_name);
-        output << header << std::endl;
+        output << header << "\n";
         const char* L = "ACGT";
         char cell[128];
         for (int64_t i = 0; i < P; ++i) {
@@ -1027,7 +1037,7 @@ int as_error_estimation_main(int argc, char** argv) {
                 else
                     output << "\t" << (double)germ_val[(size_t)i * 4 + b];
             }
-            output << std::endl;
+            output << "\n";
         }
     }
     timer.lap("write_noise_table", (double)P, "rows");
@@ -1137,7 +1147,7 @@ int as_variant_calling_main(int argc, char** argv) {
                     thr_view.push_back(bwv);
                     germ_text.push_back(f[8 + b]);
                 }
-                dummy << f[0] << "\t" << f[1] << "\t.\t.\t.\t.\t.\t." << std::endl;
+                dummy << f[0] << "\t" << f[1] << "\t.\t.\t.\t.\t.\t." << "\n";
             }
             p = eol + 1;
         }
@@ -1186,7 +1196,7 @@ int as_variant_calling_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << list_name << RESET << " stored with success. It contains " << GREEN
               << files.size() << RESET << " samples" << std::endl;
     const int T = (int)files.size();
-    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
+    if (!gpu.widen((double)T * (double)P)) {  // without a B200 there is nothing this program can do (no CPU fallback)
         std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
         return 1;
     }
@@ -1325,7 +1335,7 @@ int as_variant_calling_main(int argc, char** argv) {
     output << "Filename\tChrom\tPosition\tSubtitution\tRD\tRD_fw\tRD_bw\tAF\tReads_fw\tReads_bw\tAF_fw\tAF_bw\tAmpliconEdge_"
               "StrandBias\tFisherPvalue\tQscore_fw\tQscore_bw\tReadTier\tGermlineInfo\tMaxGermlineAF\t10merDownstream\t10merUpstream\tHo"
               "mopolymerFlag"
-           << std::endl;
+           << "\n";
     const char* L = "ACGT";
     size_t ci = 0;
     for (int t = 0; t < T; ++t) {
@@ -1341,7 +1351,7 @@ int as_variant_calling_main(int argc, char** argv) {
             << files[t].sample
             << ">\n##INFO=<ID=AF,Number=.,Type=Float,Description='Allele Frequency'>\n##INFO=<ID=SR,Number=1,Type=String,"
                "Description='Supporting Reads'>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"
-            << std::endl;
+            << "\n";
         if ((t + 1) % 50 == 0)
             std::cout << "\tParsed successfully " << GREEN << (t + 1) << "/" << T << RESET << "  samples" << std::endl;
         for (; ci < calls.size() && calls[ci].sample == t; ++ci) {
@@ -1393,13 +1403,13 @@ int as_variant_calling_main(int argc, char** argv) {
                 if (c.ref == 1 && a == 2) id = "-";  // the reference writes ID "-" for non-PASS C->G rows (VC:1856)
             }
             vcf << chrom << "\t" << pos_text << "\t" << id << "\t" << L[c.ref] << "\t" << L[a] << "\t" << Q << "\t" << filter << "\t"
-                << AF << ";" << RD << ";" << k_fw + k_bw << std::endl;
+                << AF << ";" << RD << ";" << k_fw + k_bw << "\n";
             // summary row; setprecision(4) is sticky on this stream exactly as in VC:1066
             output << files[t].sample << "\t" << chrom << "\t" << pos_text << "\t" << L[c.ref] << "->" << L[a] << "\t" << RD << "\t"
                    << FW << "\t" << BW << "\t" << AF << "\t" << k_fw << "\t" << k_bw << "\t" << AF_fw << "\t" << AF_bw << "\t"
                    << flag_dup << "_" << flag_fisher << "\t" << p << "\t" << std::setprecision(4) << Q_fw << "\t"
                    << std::setprecision(4) << Q_bw << "\t" << tier << "\t" << "-" << "\t" << max_germ_text << "\t" << down << "\t"
-                   << up << "\t" << homo << std::endl;
+                   << up << "\t" << homo << "\n";
         }
     }
     output.close();

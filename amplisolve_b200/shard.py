@@ -95,17 +95,18 @@ def gather_calls_device(ctx, calls, n_local: int, slot_offset: int, group=None):
         ctx.sort_calls_dev(calls, n_local, mine, slot_offset=slot_offset)
     if rank != 0:
         if n_local:
-            dist.send(mine[: n_local * item], dst=0, group=group)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine[: n_local * item], 0, group)]):
+                q.wait()
         return None, total
     allc = torch.empty(max(1, total) * item, dtype=torch.uint8, device=dev)
     allc[: n_local * item].copy_(mine[: n_local * item])
     off = n_local * item
-    reqs = []
+    ops = []
     for r in range(1, world):
         if sizes[r]:
-            reqs.append(dist.irecv(allc[off: off + sizes[r] * item], src=r, group=group))
+            ops.append(dist.P2POp(dist.irecv, allc[off: off + sizes[r] * item], r, group))
             off += sizes[r] * item
-    for q in reqs:
+    for q in (dist.batch_isend_irecv(ops) if ops else []):
         q.wait()
     out = torch.empty_like(allc)
     if total:

@@ -23,6 +23,7 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -244,6 +245,15 @@ struct AseqStats {
     bool in_order = true;                 // every row landed on a later slot than the row before it (row order == slot order)
     std::vector<int32_t> slot_of_row;     // filled only for files that are NOT in order (second parse): row -> slot or -1
     std::vector<as_wide_record> wide;     // records of this file that do not fit the wire format
+    // Rows the dense tensor has no place for, kept so that the programs count them like the reference does:
+    struct ExtraRow {   // a row beyond the number of panel slots of its position (the reference inserts every row, EE:1241-1245)
+        int32_t row, slot, k;        // row of the file, first slot of the position, 0-based rank among the position's extra rows
+        uint32_t fw[4], bw[4];
+        long long rd;
+    };
+    struct RdFix { int32_t slot; long long rd; };  // a row whose RD column is not A+C+G+T (the reference divides by the column)
+    std::vector<ExtraRow> extras;
+    std::vector<RdFix> rd_fix;
 };
 
 // Host layouts of a count tensor (include/amplisolve_b200.h).  FMT = bytes per count in the two plain layouts (4: the
@@ -356,9 +366,12 @@ inline int parse_row_general(const char*& p, const char* e, AseqRow& r) {
 // counts: this sample's plane pair, [2][P][PER], preset to "absent".  In the wire formats a record that does not fit (a
 // count of 65534 or more in the 16-bit one; a major count beyond 16 bits or another count beyond 4 bits in the packed
 // one) is escaped and goes to stats.wide.  record_rows: also fill stats.slot_of_row (files that are not in panel order).
+// rd_rows_aside (the caller program): a row whose RD column is not A+C+G+T stays out of the tensor and is kept in
+// stats.extras with k = -1 -- the reference's forward-strand test and Fisher table use RD - reverse reads (VC:895, VC:902),
+// so such a row is tested separately with that depth.
 template <int FMT>
 void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::E* counts, int32_t sample, bool record_rows,
-                AseqStats& st) {
+                bool rd_rows_aside, AseqStats& st) {
     typedef typename Wire<FMT>::E E;
     const int PER = Wire<FMT>::PER;
     const E absent = (E)~(E)0;
@@ -375,6 +388,11 @@ void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::
     size_t last_len = 0;
     int64_t cursor = 0, last_slot = -1;
     AseqRow r;
+    auto taken = [&](int64_t c) {  // free in the tensor, but owned by a row that was set aside
+        for (const AseqStats::ExtraRow& x : st.extras)
+            if (x.k < 0 && x.slot == (int32_t)c) return true;
+        return false;
+    };
     while (p < e) {
         if (!(p < fast_end && parse_row_fast(p, r))) {
             const int got = parse_row_general(p, e, r);
@@ -395,14 +413,26 @@ void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::
         const int32_t pos = (int32_t)r.pos;
         if (last_chrom >= 0 && r.pos == (long long)pos) {
             for (int64_t c = cursor, ce = std::min(P, cursor + 32); c < ce; ++c)
-                if (slot_pos[c] == pos && slot_chrom[c] == last_chrom && counts[c * PER] == absent) { slot = c; break; }
+                if (slot_pos[c] == pos && slot_chrom[c] == last_chrom && counts[c * PER] == absent && (st.extras.empty() || !taken(c))) { slot = c; break; }
             if (slot < 0) {  // not where the panel order says: hash lookup, then the first free slot of the position
                 slot = panel.lookup(last_chrom, pos);
                 if (slot < 0) {
                     ++st.outside;
                 } else {
-                    while (slot >= 0 && counts[slot * PER] != absent) slot = panel.has_twins ? panel.twin_next[slot] : -1;
-                    if (slot < 0) ++st.extra;  // more rows than panel slots for this position
+                    const int64_t first = slot;
+                    while (slot >= 0 && (counts[slot * PER] != absent || (!st.extras.empty() && taken(slot)))) slot = panel.has_twins ? panel.twin_next[slot] : -1;
+                    if (slot < 0) {  // more rows than panel slots for this position
+                        ++st.extra;
+                        st.in_order = false;  // the writer orders this file by rows
+                        AseqStats::ExtraRow x;
+                        x.row = (int32_t)(st.rows - 1);
+                        x.slot = (int32_t)first;
+                        x.k = 0;
+                        for (const AseqStats::ExtraRow& y : st.extras) x.k += (y.k >= 0 && y.slot == x.slot) ? 1 : 0;
+                        for (int b = 0; b < 4; ++b) { x.fw[b] = (uint32_t)(r.v[b] - r.v[5 + b]); x.bw[b] = (uint32_t)r.v[5 + b]; }
+                        x.rd = r.v[4];
+                        st.extras.push_back(x);
+                    }
                 }
             }
         } else {
@@ -415,7 +445,21 @@ void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::
         cursor = slot + 1;
         // A C G T RD Ars Crs Grs Trs -> fw[b] = X - X_rs, bw[b] = X_rs (EE:1155-1176)
         const long long* v = r.v;
-        if (v[0] + v[1] + v[2] + v[3] != v[4]) ++st.bad_rd;
+        if (v[0] + v[1] + v[2] + v[3] != v[4]) {
+            ++st.bad_rd;
+            if (rd_rows_aside) {
+                st.in_order = false;  // the writer orders this file by rows
+                AseqStats::ExtraRow x;
+                x.row = (int32_t)(st.rows - 1);
+                x.slot = (int32_t)slot;
+                x.k = -1;
+                for (int b = 0; b < 4; ++b) { x.fw[b] = (uint32_t)(v[b] - v[5 + b]); x.bw[b] = (uint32_t)v[5 + b]; }
+                x.rd = v[4];
+                st.extras.push_back(x);
+                continue;
+            }
+            st.rd_fix.push_back(AseqStats::RdFix{(int32_t)slot, v[4]});
+        }
         E* fw = counts + slot * PER;
         E* bw = counts + (P + slot) * PER;
         bool escape = false;
@@ -453,18 +497,18 @@ void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::
 }
 
 template <int FMT>
-AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<FMT>::E* counts, int32_t sample) {
+AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<FMT>::E* counts, int32_t sample, bool rd_rows_aside) {
     typedef typename Wire<FMT>::E E;
     AseqStats st;
     MappedFile file(path);
     if (!file.ok) { st.ok = false; return st; }
     const size_t words = (size_t)panel.size() * 2 * Wire<FMT>::PER;
     memset(counts, 0xFF, words * sizeof(E));
-    parse_aseq<FMT>(file, panel, counts, sample, false, st);
+    parse_aseq<FMT>(file, panel, counts, sample, false, rd_rows_aside, st);
     if (!st.in_order) {  // rare: rows not in panel order.  Parse again, recording the slot of every row (the writer needs it)
         st = AseqStats();
         memset(counts, 0xFF, words * sizeof(E));
-        parse_aseq<FMT>(file, panel, counts, sample, true, st);
+        parse_aseq<FMT>(file, panel, counts, sample, true, rd_rows_aside, st);
         st.in_order = false;
     }
     return st;
@@ -473,7 +517,7 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<F
 // samples [first, first + n) of `files` into one tensor [n][2][P][PER]; sample ids in the wide records are 0..n-1
 template <int FMT>
 bool load_all(const std::vector<CountFile>& files, size_t first, size_t n, const Panel& panel, typename Wire<FMT>::E* counts,
-              std::vector<AseqStats>& stats) {
+              std::vector<AseqStats>& stats, bool rd_rows_aside = false) {
     typedef typename Wire<FMT>::E E;
     const int PER = Wire<FMT>::PER;
     const int64_t P = panel.size();
@@ -481,7 +525,7 @@ bool load_all(const std::vector<CountFile>& files, size_t first, size_t n, const
     std::atomic<size_t> next(0);
     auto work = [&]() {
         for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
-            stats[i] = load_aseq<FMT>(files[first + i].path, panel, counts + (int64_t)i * 2 * P * PER, (int32_t)i);
+            stats[i] = load_aseq<FMT>(files[first + i].path, panel, counts + (int64_t)i * 2 * P * PER, (int32_t)i, rd_rows_aside);
     };
     const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max<size_t>(1, n)));
     std::vector<std::thread> th;
@@ -558,7 +602,7 @@ struct HostCounts {
 };
 // samples [first, first + n) of `files`.  returns 0 ok, 1 pinned allocation failed, 2 a file could not be opened
 int load_counts(const std::vector<CountFile>& files, size_t first, size_t n, const Panel& panel, HostCounts& hc,
-                std::vector<AseqStats>& stats) {
+                std::vector<AseqStats>& stats, bool rd_rows_aside = false) {
     const size_t strand_words = n * 2 * (size_t)panel.size();
     const char* force = getenv("AS_WIRE");
     if (force && !strcmp(force, "16")) hc.fmt = 2;
@@ -566,8 +610,8 @@ int load_counts(const std::vector<CountFile>& files, size_t first, size_t n, con
     for (int fmt = hc.fmt; fmt <= 2; ++fmt) {
         if (!hc.reserve(std::max<size_t>(16, strand_words * 4 * (size_t)fmt))) return 1;
         hc.fmt = fmt;
-        const bool ok = fmt == 1 ? load_all<1>(files, first, n, panel, (uint32_t*)hc.p, stats)
-                                 : load_all<2>(files, first, n, panel, (uint16_t*)hc.p, stats);
+        const bool ok = fmt == 1 ? load_all<1>(files, first, n, panel, (uint32_t*)hc.p, stats, rd_rows_aside)
+                                 : load_all<2>(files, first, n, panel, (uint16_t*)hc.p, stats, rd_rows_aside);
         if (!ok) return 2;
         int64_t rows = 0, escaped = 0;
         for (const AseqStats& s : stats) { rows += s.rows; escaped += (int64_t)s.wide.size(); }
@@ -583,6 +627,76 @@ int load_counts(const std::vector<CountFile>& files, size_t first, size_t n, con
         return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
     });
     return 0;
+}
+
+// Rows beyond the number of panel slots of their position (a file that lists a position more often than the BED enumerates
+// it).  The reference keys records by position and inserts every row (EE:1241-1245), so such rows count like all others:
+// sums, N of the 0.338*N rule, Germ_Max, in file order.  The dense tensor gets SPILL SLOTS for them -- virtual slots
+// appended after the panel's P slots and chained to the end of their position's twin group (chain order = row order within
+// a file), absent in every sample that has no such row -- and the library reduces them like any duplicated position.
+// Returns the new number of slots (P when there is nothing to do); twin_next / twin_head are the extended links.
+int64_t add_spill_slots(const Panel& panel, HostCounts& hc, const std::vector<AseqStats>& stats, std::vector<int32_t>& twin_next,
+                        std::vector<int32_t>& twin_head) {
+    const int64_t P = panel.size();
+    const size_t S = stats.size();
+    std::map<int32_t, int32_t> need;  // first slot of a position -> spill slots it needs
+    for (const AseqStats& st : stats)
+        for (const AseqStats::ExtraRow& x : st.extras)
+            if (x.k >= 0) need[x.slot] = std::max(need[x.slot], x.k + 1);
+    twin_next = panel.twin_next;
+    twin_head = panel.twin_head;
+    if (need.empty()) return P;
+    std::map<int32_t, int32_t> base;  // first slot -> id of its first spill slot
+    int64_t P2 = P;
+    for (const auto& kv : need) {
+        base[kv.first] = (int32_t)P2;
+        int32_t last = kv.first;
+        while (twin_next[(size_t)last] >= 0) last = twin_next[(size_t)last];
+        for (int32_t k = 0; k < kv.second; ++k) {
+            twin_next[(size_t)last] = (int32_t)P2;
+            twin_next.push_back(-1);
+            twin_head.push_back(twin_head[(size_t)kv.first]);
+            last = (int32_t)P2++;
+        }
+    }
+    const size_t w = hc.fmt == 2 ? 8 : 4;  // bytes per (sample, strand, slot)
+    void* mem = nullptr;
+    if (as_host_alloc(&mem, std::max<size_t>(16, S * 2 * (size_t)P2 * w)) != AS_OK) return -1;
+    memset(mem, 0xFF, S * 2 * (size_t)P2 * w);
+    for (size_t pl = 0; pl < S * 2; ++pl) memcpy((char*)mem + pl * (size_t)P2 * w, (const char*)hc.p + pl * (size_t)P * w, (size_t)P * w);
+    for (size_t smp = 0; smp < S; ++smp) {
+        for (const AseqStats::ExtraRow& x : stats[smp].extras) {
+            if (x.k < 0) continue;
+            const int64_t id = base[x.slot] + x.k;
+            bool escape = false;
+            if (hc.fmt == 2) {
+                uint16_t* f = (uint16_t*)mem + ((smp * 2) * (size_t)P2 + (size_t)id) * 4;
+                uint16_t* b = (uint16_t*)mem + ((smp * 2 + 1) * (size_t)P2 + (size_t)id) * 4;
+                for (int i = 0; i < 4; ++i) escape = escape || x.fw[i] >= AS_WIRE_ESCAPE || x.bw[i] >= AS_WIRE_ESCAPE;
+                for (int i = 0; i < 4; ++i) { f[i] = escape ? AS_WIRE_ESCAPE : (uint16_t)x.fw[i]; b[i] = escape ? AS_WIRE_ESCAPE : (uint16_t)x.bw[i]; }
+            } else {
+                uint32_t wf = 0, wb = 0;
+                escape = !(as_pack_word(x.fw, &wf) && as_pack_word(x.bw, &wb));
+                ((uint32_t*)mem)[(smp * 2) * (size_t)P2 + (size_t)id] = escape ? AS_PACKED_ESCAPE : wf;
+                ((uint32_t*)mem)[(smp * 2 + 1) * (size_t)P2 + (size_t)id] = escape ? AS_PACKED_ESCAPE : wb;
+            }
+            if (escape) {
+                as_wide_record r;
+                r.sample = (int32_t)smp;
+                r.slot = (int32_t)id;
+                memcpy(r.fw, x.fw, 16);
+                memcpy(r.bw, x.bw, 16);
+                hc.wide.push_back(r);
+            }
+        }
+    }
+    std::sort(hc.wide.begin(), hc.wide.end(), [](const as_wide_record& x, const as_wide_record& y) {
+        return x.slot != y.slot ? x.slot < y.slot : x.sample < y.sample;
+    });
+    as_host_free(hc.p);
+    hc.p = mem;
+    hc.bytes = S * 2 * (size_t)P2 * w;
+    return P2;
 }
 
 // The GPUs of a run.  AS_DEVICES ("0,2,3") names them; otherwise the program starts on GPU 0 -- on a thread at program entry:
@@ -791,18 +905,13 @@ void write_list_file(const std::string& path, const std::vector<std::string>& li
     for (const std::string& s : listed) f << s << "\n";
 }
 
-void report_load(const std::vector<CountFile>& files, size_t first, const std::vector<AseqStats>& stats) {
+void report_load(const std::vector<CountFile>& files, size_t first, const std::vector<AseqStats>& stats, bool noise_model) {
     for (size_t i = 0; i < stats.size(); ++i) {
         const AseqStats& s = stats[i];
         for (int64_t k = 0; k < s.bad_rd; ++k) std::cout << "malakia paizei edo" << std::endl;  // EE:1178-1181, VC:762-765
-        if (s.bad_rd)
+        if (s.bad_rd && noise_model)
             std::cout << "Warning: " << files[first + i].path << " has " << s.bad_rd << " row(s) whose RD column is not A+C+G+T; "
-                      << "the total allele fractions of those rows (Germ_Max, AF column) use the sum, the reference the column"
-                      << std::endl;
-        if (s.extra)
-            std::cout << "Warning: " << files[first + i].path << " has " << s.extra
-                      << " row(s) beyond the number of panel slots of their position; ignored (the reference counts them)"
-                      << std::endl;
+                      << "Germ_Max of their positions uses the sum of the counts, the reference the column" << std::endl;
     }
 }
 
@@ -985,7 +1094,7 @@ int as_error_estimation_main(int argc, char** argv) {
             if (!stats[i].ok) printf("Error: Cannot open %s\n", files[i].path.c_str());
         return 0;
     }
-    report_load(files, 0, stats);
+    report_load(files, 0, stats, true);
     {
         double rows = 0;
         for (const AseqStats& st : stats) rows += (double)st.rows;
@@ -993,17 +1102,21 @@ int as_error_estimation_main(int argc, char** argv) {
     }
 
     std::cout << "Running function estimateThresholds: ";
-    std::vector<float> thr((size_t)P * 8), germ_val((size_t)P * 4);
-    std::vector<uint8_t> germ_state((size_t)P * 4);
-    std::vector<uint32_t> count((size_t)P * 4), nrec((size_t)P);
-    const int32_t* tn = panel.has_twins ? panel.twin_next.data() : nullptr;
-    const int32_t* th = panel.has_twins ? panel.twin_head.data() : nullptr;
+    std::vector<int32_t> links_next, links_head;
+    const int64_t PS = add_spill_slots(panel, counts, stats, links_next, links_head);  // P + spill slots for rows beyond the panel's slots
+    if (PS < 0) return report_gpu_error("pinned host allocation");
+    std::vector<float> thr((size_t)PS * 8), germ_val((size_t)PS * 4);
+    std::vector<uint8_t> germ_state((size_t)PS * 4);
+    std::vector<uint32_t> count((size_t)PS * 4), nrec((size_t)PS);
+    const bool linked = panel.has_twins || PS > P;
+    const int32_t* tn = linked ? links_next.data() : nullptr;
+    const int32_t* th = linked ? links_head.data() : nullptr;
     const int rc = counts.fmt == 2
                        ? as_noise_estimate_host16(ctx, (const uint16_t*)counts.p, counts.wide.data(), (int64_t)counts.wide.size(),
-                                                  S, P, tn, th, C_value_float, cut, thr.data(), germ_val.data(),
+                                                  S, PS, tn, th, C_value_float, cut, thr.data(), germ_val.data(),
                                                   germ_state.data(), count.data(), nrec.data(), nullptr)
                        : as_noise_estimate_host_packed(ctx, (const uint32_t*)counts.p, counts.wide.data(),
-                                                       (int64_t)counts.wide.size(), S, P, tn, th, C_value_float, cut, thr.data(),
+                                                       (int64_t)counts.wide.size(), S, PS, tn, th, C_value_float, cut, thr.data(),
                                                        germ_val.data(), germ_state.data(), count.data(), nrec.data(), nullptr);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");
@@ -1210,6 +1323,8 @@ int as_variant_calling_main(int argc, char** argv) {
     struct CallCounts { uint32_t fw[4], bw[4]; };  // the record of a call, kept for the Fisher test and the writers
     std::vector<as_call> calls;
     std::vector<CallCounts> call_counts;
+    std::vector<int32_t> call_row;     // file row of a call that came from a row beyond its position's slots (-1: see slot_of_row)
+    std::vector<long long> call_rd;    // RD column of the call's row where it is not A+C+G+T (-1: the sum); VC:814-817 divide by the column
     std::vector<AseqStats> file_stats((size_t)T);  // order information of every file (slot_of_row only when out of order)
     double total_rows = 0, parse_s = 0, gpu_s = 0;
     if (T > 0 && P > 0) {
@@ -1222,7 +1337,7 @@ int as_variant_calling_main(int argc, char** argv) {
             const double t0 = PhaseTimer::now();
             const size_t n = (size_t)std::min<int64_t>(G, T - first);
             buf[which].fmt = std::max(buf[which].fmt, buf[which ^ 1].fmt);  // once the 16-bit format was needed it stays
-            const int lrc = load_counts(files, (size_t)first, n, panel, buf[which], stats[which]);
+            const int lrc = load_counts(files, (size_t)first, n, panel, buf[which], stats[which], true);
             if (lrc == 2)
                 for (size_t i = 0; i < n; ++i)
                     if (!stats[which][i].ok) printf("\tError from callVariants:  Cannot open %s\n", files[(size_t)first + i].path.c_str());
@@ -1235,7 +1350,7 @@ int as_variant_calling_main(int argc, char** argv) {
         for (int64_t first = 0, g = 0; first < T; first += G, ++g) {
             const int which = (int)(g & 1);
             const int32_t Tg = (int32_t)std::min<int64_t>(G, T - first);
-            report_load(files, (size_t)first, stats[which]);
+            report_load(files, (size_t)first, stats[which], false);
             for (int i = 0; i < Tg; ++i) {
                 for (int64_t k = 0; k < stats[which][(size_t)i].outside; ++k) std::cout << "mistake..." << std::endl;  // VC:847-852
                 total_rows += (double)stats[which][(size_t)i].rows;
@@ -1277,12 +1392,98 @@ int as_variant_calling_main(int argc, char** argv) {
             const size_t base = calls.size();
             calls.resize(base + part.size());
             call_counts.resize(base + part.size());
+            call_row.resize(base + part.size(), -1);
+            call_rd.resize(base + part.size(), -1);
             parallel_for(part.size(), [&](size_t i) {
                 as_call c = part[i];
                 hc.record(c.sample, c.slot, P, call_counts[base + i].fw, call_counts[base + i].bw);
                 c.sample += (int32_t)first;
                 calls[base + i] = c;
             });
+            // ---- rows the tensor has no slot for (a file listing a position more often than the panel enumerates it): the
+            // reference tests every row (VC:869-3288), so they go through the caller as well, in one small pass of their own
+            // (one "sample", one "slot" per row, thresholds and reference base of the row's position)
+            std::vector<std::pair<int32_t, const AseqStats::ExtraRow*>> xr;
+            bool fixes = false;
+            for (int i = 0; i < Tg; ++i) {
+                for (const AseqStats::ExtraRow& x : file_stats[(size_t)(first + i)].extras) xr.emplace_back((int32_t)(first + i), &x);
+                fixes = fixes || !file_stats[(size_t)(first + i)].rd_fix.empty();
+            }
+            if (!xr.empty()) {
+                // The reference's strand tests take (alt_fw, RD - reverse reads) and (alt_bw, reverse reads), RD being the COLUMN
+                // (VC:895-896); the coverage gate takes the sums (VC:898).  So the gate is applied here and the row goes to the
+                // caller with its forward depth set to RD - reverse reads (the reference base's count absorbs the difference;
+                // alt counts are untouched) and a cutoff of 1.
+                std::vector<std::pair<int32_t, const AseqStats::ExtraRow*>> use;
+                std::vector<uint32_t> fwadj;
+                for (const auto& pr : xr) {
+                    const AseqStats::ExtraRow& x = *pr.second;
+                    long long FW = 0, BW = 0;
+                    for (int b = 0; b < 4; ++b) { FW += x.fw[b]; BW += x.bw[b]; }
+                    const uint8_t rb = ref_code[(size_t)x.slot];
+                    if (FW < cut || BW < cut || rb > 3) continue;  // VC:898 / VC:3290: never a call
+                    const long long ref_fw = (long long)x.fw[rb] + (x.rd - (FW + BW));
+                    if (ref_fw < 0 || x.rd - BW < 1) {
+                        std::cout << "Warning: " << files[(size_t)pr.first].path << " row " << x.row + 2
+                                  << ": RD column smaller than the alt reads; row skipped" << std::endl;
+                        continue;
+                    }
+                    use.push_back(pr);
+                    fwadj.push_back((uint32_t)ref_fw);
+                }
+                const int64_t M = (int64_t)use.size();
+                std::vector<uint32_t> xc((size_t)M * 8 + 4);
+                uint32_t* xcp = (uint32_t*)(((uintptr_t)xc.data() + 15) & ~(uintptr_t)15);
+                std::vector<uint8_t> xref((size_t)M);
+                std::vector<float> xthr((size_t)M * 8);
+                for (int64_t m = 0; m < M; ++m) {
+                    const AseqStats::ExtraRow& x = *use[(size_t)m].second;
+                    memcpy(xcp + m * 4, x.fw, 16);
+                    memcpy(xcp + (M + m) * 4, x.bw, 16);
+                    xref[(size_t)m] = ref_code[(size_t)x.slot];
+                    xcp[m * 4 + xref[(size_t)m]] = fwadj[(size_t)m];
+                    memcpy(&xthr[(size_t)m * 8], &thr_view[(size_t)x.slot * 8], 32);
+                }
+                std::vector<as_call> xcalls((size_t)M * 3 + 1);
+                int64_t nx = 0;
+                if (M > 0 && as_call_variants_host(ctx, xcp, 1, M, xref.data(), xthr.data(), 1, xcalls.data(), (int64_t)xcalls.size(), &nx) != AS_OK)
+                    return report_gpu_error("as_call_variants_host");
+                for (int64_t i = 0; i < nx; ++i) {
+                    const AseqStats::ExtraRow& x = *use[(size_t)xcalls[(size_t)i].slot].second;
+                    as_call c = xcalls[(size_t)i];
+                    c.sample = use[(size_t)xcalls[(size_t)i].slot].first;
+                    c.slot = x.slot;
+                    CallCounts k;
+                    memcpy(k.fw, x.fw, 16);
+                    memcpy(k.bw, x.bw, 16);
+                    long long sum = 0;
+                    for (int b = 0; b < 4; ++b) sum += (long long)x.fw[b] + x.bw[b];
+                    calls.push_back(c);
+                    call_counts.push_back(k);
+                    call_row.push_back(x.row);
+                    call_rd.push_back(x.rd != sum ? x.rd : -1);
+                }
+            }
+            if (fixes) {  // RD column of rows where it is not the sum of the counts
+                for (size_t i = base; i < base + part.size(); ++i) {
+                    for (const AseqStats::RdFix& f : file_stats[(size_t)calls[i].sample].rd_fix)
+                        if (f.slot == calls[i].slot) call_rd[i] = f.rd;
+                }
+            }
+            if (!xr.empty()) {  // back into sample order (the calls of the extra rows were appended behind the group's)
+                std::vector<size_t> order(calls.size() - base);
+                for (size_t i = 0; i < order.size(); ++i) order[i] = base + i;
+                std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return calls[a].sample < calls[b].sample; });
+                std::vector<as_call> c2(order.size());
+                std::vector<CallCounts> k2(order.size());
+                std::vector<int32_t> r2(order.size());
+                std::vector<long long> d2(order.size());
+                for (size_t i = 0; i < order.size(); ++i) { c2[i] = calls[order[i]]; k2[i] = call_counts[order[i]]; r2[i] = call_row[order[i]]; d2[i] = call_rd[order[i]]; }
+                std::copy(c2.begin(), c2.end(), calls.begin() + (long)base);
+                std::copy(k2.begin(), k2.end(), call_counts.begin() + (long)base);
+                std::copy(r2.begin(), r2.end(), call_row.begin() + (long)base);
+                std::copy(d2.begin(), d2.end(), call_rd.begin() + (long)base);
+            }
         }
         // The device returns (sample, slot, alt) order = the reference's file-row order (VC:869-3288: rows, then alts
         // A,C,G,T) for every file whose rows follow the panel enumeration.  A file that does not is re-ordered by its rows.
@@ -1299,14 +1500,19 @@ int as_variant_calling_main(int argc, char** argv) {
             std::vector<size_t> order(hi - lo);
             for (size_t i = 0; i < order.size(); ++i) order[i] = lo + i;
             std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
-                const int32_t rx = row_of[(size_t)calls[x].slot], ry = row_of[(size_t)calls[y].slot];
+                const int32_t rx = call_row[x] >= 0 ? call_row[x] : row_of[(size_t)calls[x].slot];
+                const int32_t ry = call_row[y] >= 0 ? call_row[y] : row_of[(size_t)calls[y].slot];
                 return rx != ry ? rx < ry : calls[x].alt < calls[y].alt;
             });
             std::vector<as_call> c2(order.size());
             std::vector<CallCounts> k2(order.size());
-            for (size_t i = 0; i < order.size(); ++i) { c2[i] = calls[order[i]]; k2[i] = call_counts[order[i]]; }
+            std::vector<int32_t> r2(order.size());
+            std::vector<long long> d2(order.size());
+            for (size_t i = 0; i < order.size(); ++i) { c2[i] = calls[order[i]]; k2[i] = call_counts[order[i]]; r2[i] = call_row[order[i]]; d2[i] = call_rd[order[i]]; }
             std::copy(c2.begin(), c2.end(), calls.begin() + (long)lo);
             std::copy(k2.begin(), k2.end(), call_counts.begin() + (long)lo);
+            std::copy(r2.begin(), r2.end(), call_row.begin() + (long)lo);
+            std::copy(d2.begin(), d2.end(), call_rd.begin() + (long)lo);
         }
     }
     if (timer.on) fprintf(stderr, "AS_TIMING parse_tumours_busy %.6f (%.3g rows/s)\nAS_TIMING caller_gpu_busy %.6f\n", parse_s,
@@ -1319,8 +1525,9 @@ int as_variant_calling_main(int argc, char** argv) {
         std::vector<int32_t> tables(calls.size() * 4);
         parallel_for(calls.size(), [&](size_t i) {
             const CallCounts& k = call_counts[i];
-            tables[i * 4 + 0] = (int32_t)(k.fw[0] + k.fw[1] + k.fw[2] + k.fw[3]);  // fisherTest(FW, BW, alt_fw, alt_bw)
-            tables[i * 4 + 1] = (int32_t)(k.bw[0] + k.bw[1] + k.bw[2] + k.bw[3]);
+            const int32_t FWs = (int32_t)(k.fw[0] + k.fw[1] + k.fw[2] + k.fw[3]), BWs = (int32_t)(k.bw[0] + k.bw[1] + k.bw[2] + k.bw[3]);
+            tables[i * 4 + 0] = call_rd[i] >= 0 ? (int32_t)(call_rd[i] - BWs) : FWs;  // fisherTest(RD - RD_reverse, RD_reverse, alt_fw, alt_bw), VC:902
+            tables[i * 4 + 1] = BWs;
             tables[i * 4 + 2] = (int32_t)k.fw[calls[i].alt];
             tables[i * 4 + 3] = (int32_t)k.bw[calls[i].alt];
         });
@@ -1360,7 +1567,7 @@ int as_variant_calling_main(int argc, char** argv) {
             const uint32_t* fw = call_counts[ci].fw;
             const uint32_t* bw = call_counts[ci].bw;
             const int FW = (int)(fw[0] + fw[1] + fw[2] + fw[3]), BW = (int)(bw[0] + bw[1] + bw[2] + bw[3]);
-            const int RD = FW + BW;
+            const int RD = call_rd[ci] >= 0 ? (int)call_rd[ci] : FW + BW;  // the RD column (VC:752), normally the sum
             const int a = c.alt;
             const int k_fw = (int)fw[a], k_bw = (int)bw[a];
             const float AF = float(k_fw + k_bw) / float(RD);                    // VC:814-817

@@ -1119,7 +1119,8 @@ int as_fisher_tests_host(as_ctx* c, const int32_t* tables, int64_t n, double* p)
     std::vector<int64_t> on_host;  // tables beyond the lgamma table
     for (int64_t i = 0; i < n; ++i) {
         const int32_t* t = tables + i * 4;
-        if ((int64_t)t[0] + t[1] + t[2] + t[3] > LG_CAP) on_host.push_back(i);
+        const int64_t N = (int64_t)t[0] + t[1] + t[2] + t[3];
+        if (N > LG_CAP || N <= 170) on_host.push_back(i);  // beyond the table / Boost's factorial-table branch (as_fisher_test)
     }
     if (!on_host.empty()) {  // the kernel must not index past the table: give those warps an empty table
         std::vector<int32_t> zero(4, 0);

@@ -11,8 +11,10 @@
 
 namespace {
 
+// canonical operand order (the smaller of k, n - k first), as log_choose of as_host.cpp: tied terms stay tied
 __device__ __forceinline__ double lc(const double* __restrict__ lg, unsigned n, unsigned k) {
-    return __dsub_rn(__dsub_rn(lg[n], lg[k]), lg[n - k]);
+    const unsigned lo = min(k, n - k), hi = max(k, n - k);
+    return __dsub_rn(__dsub_rn(lg[n], lg[lo]), lg[hi]);
 }
 
 __global__ void __launch_bounds__(256)

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "../../include/amplisolve_b200.h"
+#include "as_factorials.h"
 #include "as_wire.h"
 
 namespace {
@@ -806,8 +807,31 @@ inline double lg1(double x) {  // lgamma(x + 1)
     int sign = 0;
     return lgamma_r(x + 1.0, &sign);
 }
-double log_choose(double n, double k) { return lg1(n) - lg1(k) - lg1(n - k); }
+// log C(n, k) with the operands in a canonical order (the smaller of k, n - k first): C(n, k) and C(n, n - k) are then
+// bitwise equal, so two terms of the hypergeometric distribution that are tied mathematically (symmetric tables: r = N - r,
+// n = N - n) are tied in floating point too, and `pdf(k) <= cutoff` (VC:3811) keeps or drops them together
+double log_choose(double n, double k) {
+    const double lo = std::min(k, n - k), hi = std::max(k, n - k);
+    return (lg1(n) - lg1(lo)) - lg1(hi);
+}
+// Boost.Math's hypergeometric pdf for N <= 170 (hypergeometric_pdf_factorial_imp: n! r! (N-n)! (N-r)! over
+// N! k! (n-k)! (r-k)! (N-n-r+k)! from a table of factorials, multiplying while the running value is <= 1 and dividing while
+// it is >= 1, clamped to 1).  Restated operation for operation: bit-identical to the pdf SciPy's compiled-in Boost returns on
+// 1.4 million (N, r, n, k) points, which matters because the terms of a symmetric table are NOT bitwise equal under it and
+// the two-sided sum keeps or drops the mirror term accordingly (tests/golden/fisher_boost.npz, tie tables).
+double hyper_pdf_factorial(unsigned r, unsigned n, unsigned N, unsigned k) {
+    double result = AS_FACTORIAL[n];
+    const double num[3] = {AS_FACTORIAL[r], AS_FACTORIAL[N - n], AS_FACTORIAL[N - r]};
+    const double den[5] = {AS_FACTORIAL[N], AS_FACTORIAL[k], AS_FACTORIAL[n - k], AS_FACTORIAL[r - k], AS_FACTORIAL[N - n - r + k]};
+    int i = 0, j = 0;
+    while (i < 3 || j < 5) {
+        while (j < 5 && (result >= 1 || i >= 3)) result /= den[j++];
+        while (i < 3 && (result <= 1 || j >= 5)) result *= num[i++];
+    }
+    return result > 1 ? 1.0 : result;
+}
 double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {
+    if (N <= 170) return hyper_pdf_factorial(r, n, N, k);
     return exp(log_choose(r, k) + log_choose((double)N - r, (double)n - k) - log_choose(N, n));
 }
 double fisher_test(int a, int b, int c, int d) {

@@ -3,6 +3,7 @@
  * off (see oracle/Makefile).  EE/VC citations refer to the files named in as_oracle.h. */
 #define _GNU_SOURCE
 #include "as_oracle.h"
+#include "factorials.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -210,8 +211,25 @@ int aso_q_at_least(double p, int threshold) { return q_from_p_ld(p) >= threshold
 double aso_q_from_p(double p) { return (double)q_from_p_ld(p); }
 
 /* two-sided Fisher exact test as VC:3797-3814, over the stand-in hypergeometric pdf */
-static double log_choose(double n, double k) { return lgamma(n + 1.0) - lgamma(k + 1.0) - lgamma(n - k + 1.0); }
+/* operands in a canonical order (smaller of k, n - k first): C(n,k) == C(n,n-k) bitwise, so terms tied mathematically stay tied */
+static double log_choose(double n, double k) {
+    const double lo = k < n - k ? k : n - k, hi = k < n - k ? n - k : k;
+    return (lgamma(n + 1.0) - lgamma(lo + 1.0)) - lgamma(hi + 1.0);
+}
+/* N <= 170: Boost.Math's factorial-table method (hypergeometric_pdf_factorial_imp), bit-identical to SciPy's compiled-in Boost */
+static double hyper_pdf_factorial(unsigned r, unsigned n, unsigned N, unsigned k) {
+    double result = ASO_FACTORIAL[n];
+    const double num[3] = {ASO_FACTORIAL[r], ASO_FACTORIAL[N - n], ASO_FACTORIAL[N - r]};
+    const double den[5] = {ASO_FACTORIAL[N], ASO_FACTORIAL[k], ASO_FACTORIAL[n - k], ASO_FACTORIAL[r - k], ASO_FACTORIAL[N - n - r + k]};
+    int i = 0, j = 0;
+    while (i < 3 || j < 5) {
+        while (j < 5 && (result >= 1 || i >= 3)) result /= den[j++];
+        while (i < 3 && (result <= 1 || j >= 5)) result *= num[i++];
+    }
+    return result > 1 ? 1.0 : result;
+}
 static double hyper_pdf(unsigned r, unsigned n, unsigned N, unsigned k) {
+    if (N <= 170) return hyper_pdf_factorial(r, n, N, k);
     return exp(log_choose(r, k) + log_choose((double)N - r, (double)n - k) - log_choose(N, n));
 }
 double aso_fisher(int a, int b, int c, int d) {

@@ -13,6 +13,8 @@
 #pragma once
 #include <cmath>
 
+#include "../../../../../factorials.h"
+
 namespace boost { namespace math {
 
 template <class RealType = double>
@@ -22,13 +24,30 @@ struct hypergeometric_distribution {
 };
 
 namespace standin_detail {
+// operands in a canonical order (smaller of k, n - k first): C(n,k) == C(n,n-k) bitwise, so that terms of a symmetric
+// table that are tied mathematically are tied here as well (Boost's own pdf treats them alike: tests/golden/fisher_boost.npz)
 inline double log_choose(double n, double k) {
-    return std::lgamma(n + 1.0) - std::lgamma(k + 1.0) - std::lgamma(n - k + 1.0);
+    const double lo = k < n - k ? k : n - k, hi = k < n - k ? n - k : k;
+    return (std::lgamma(n + 1.0) - std::lgamma(lo + 1.0)) - std::lgamma(hi + 1.0);
 }
 }  // namespace standin_detail
 
+// N <= 170: Boost's own factorial-table method (hypergeometric_pdf_factorial_imp), restated; bit-identical to SciPy's Boost
+inline double pdf_factorial(unsigned r, unsigned n, unsigned N, unsigned k) {
+    double result = ASO_FACTORIAL[n];
+    const double num[3] = {ASO_FACTORIAL[r], ASO_FACTORIAL[N - n], ASO_FACTORIAL[N - r]};
+    const double den[5] = {ASO_FACTORIAL[N], ASO_FACTORIAL[k], ASO_FACTORIAL[n - k], ASO_FACTORIAL[r - k], ASO_FACTORIAL[N - n - r + k]};
+    int i = 0, j = 0;
+    while (i < 3 || j < 5) {
+        while (j < 5 && (result >= 1 || i >= 3)) result /= den[j++];
+        while (i < 3 && (result <= 1 || j >= 5)) result *= num[i++];
+    }
+    return result > 1 ? 1.0 : result;
+}
+
 template <class RealType, class K>
 inline RealType pdf(const hypergeometric_distribution<RealType>& d, K k) {
+    if (d.N_ <= 170) return (RealType)pdf_factorial(d.r_, d.n_, d.N_, (unsigned)k);
     const double r = d.r_, n = d.n_, N = d.N_, x = (double)k;
     return (RealType)std::exp(standin_detail::log_choose(r, x) +
                               standin_detail::log_choose(N - r, n - x) -

@@ -83,6 +83,36 @@ def random_tables(rng, n):
     return out
 
 
+def tie_tables():
+    """Tables whose hypergeometric distribution is symmetric, so that pdf(k) ties exactly with pdf(mirror k): r = N - r
+    (a + c = b + d) or n = N - n (c + d = a + b).  Exhaustive for N <= 28 (Boost's factorial-table branch), plus larger ones
+    on the prime-factorisation and Lanczos branches.  Whether the mirror term is <= cutoff decides a whole term of p."""
+    out = []
+    for N in range(4, 29, 2):
+        for c in range(0, N // 2 + 1):
+            for d in range(0, N // 2 + 1 - c):
+                for a in range(0, N - c - d + 1):
+                    b = N - a - c - d
+                    if (a + c == b + d or c + d == a + b) and a >= 0 and b >= 0:
+                        out.append((a, b, c, d))
+    rng = np.random.default_rng(20187)
+    for _ in range(400):
+        half = int(rng.choice([60, 90, 200, 1000, 5000, 40000, 60000, 150000]))
+        c, d = int(rng.integers(0, min(half, 40))), int(rng.integers(0, min(half, 40)))
+        if rng.random() < 0.5:      # r = N - r
+            a = half - c
+            b = half - d
+        else:                        # n = N - n  (alt reads = half of everything: only for small halves)
+            half = min(half, 200)
+            c, d = int(rng.integers(0, half + 1)), 0
+            d = half - c
+            a = int(rng.integers(0, half + 1))
+            b = half - a
+        if a >= 0 and b >= 0:
+            out.append((a, b, c, d))
+    return out
+
+
 def main():
     import scipy
     rows, printed = [], []
@@ -93,13 +123,16 @@ def main():
             printed.append(txt)
     n_fixture = len(rows)
     rows += random_tables(np.random.default_rng(20186), 1500)
+    n_random = len(rows)
+    rows += tie_tables()
     printed += [""] * (len(rows) - n_fixture)
     t = np.array(rows, dtype=np.int64)
     p = np.array([boost_fisher(*map(int, r)) for r in rows])
     np.savez_compressed(HERE / "fisher_boost.npz", fw=t[:, 0], bw=t[:, 1], alt_fw=t[:, 2], alt_bw=t[:, 3], p_boost=p,
-                        printed_by_standin=np.array(printed), n_from_fixtures=np.int64(n_fixture),
+                        printed_by_standin=np.array(printed), n_from_fixtures=np.int64(n_fixture), n_before_ties=np.int64(n_random),
                         scipy_version=np.array(scipy.__version__))
-    print(f"fisher_boost.npz: {n_fixture} call rows of the golden cases + {len(rows) - n_fixture} seeded tables, scipy {scipy.__version__}")
+    print(f"fisher_boost.npz: {n_fixture} call rows of the golden cases + {n_random - n_fixture} seeded tables + {len(rows) - n_random} "
+          f"symmetric (tie-prone) tables, scipy {scipy.__version__}")
 
 
 if __name__ == "__main__":

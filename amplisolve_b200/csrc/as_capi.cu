@@ -244,7 +244,7 @@ int as_set_call_kernel(as_ctx* c, int variant) {
     return AS_OK;
 }
 int as_set_noise_kernel(as_ctx* c, int variant) {
-    if (!c || variant < -1 || variant > 11) return fail(AS_EINVAL, "bad noise kernel variant");
+    if (!c || variant < -1 || variant > 8) return fail(AS_EINVAL, "bad noise kernel variant");
     c->noise_cfg = variant < 0 ? AS_DEFAULT_NOISE_KERNEL : variant;
     for (size_t k = 1; k < c->subs.size(); ++k) c->subs[k]->noise_cfg = c->noise_cfg;
     return AS_OK;

@@ -175,27 +175,39 @@ bool annotate_reference(const std::string& fasta, Panel& panel, std::string& err
             p = eol + 1;
         }
     }
+    // the FASTA is mapped, not read: only the pages that hold panel positions are ever touched (one page fault per
+    // ~4 kb of panel instead of one pread -- or, in the reference, one samtools fork -- per position)
     const int fd = open(fasta.c_str(), O_RDONLY);
     if (fd < 0) { err = "cannot open " + fasta; return false; }
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) { close(fd); err = "cannot stat " + fasta; return false; }
+    const size_t fsize = (size_t)sb.st_size;
+    const char* base = fsize ? (const char*)mmap(nullptr, fsize, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+    close(fd);
+    if (fsize && base == (const char*)MAP_FAILED) { err = "cannot map " + fasta; return false; }
     const int64_t P = panel.size();
     panel.ref.resize(P);
-    for (int64_t i = 0; i < P; ++i) {
-        const std::string& c = panel.chroms[panel.slot_chrom[i]];
-        auto it = idx.find(c);
-        const long long pos = panel.slot_pos[i];
-        if (it == idx.end() || pos < 1 || pos > it->second.len) {
-            close(fd);
-            err = "region " + c + ":" + std::to_string(pos) + " is not in " + fasta;
-            return false;
+    bool ok = true;
+    int32_t last_chrom = -1;
+    const FaiEntry* en = nullptr;
+    for (int64_t i = 0; i < P && ok; ++i) {
+        if (panel.slot_chrom[i] != last_chrom) {  // one index lookup per run of slots on the same contig
+            last_chrom = panel.slot_chrom[i];
+            auto it = idx.find(panel.chroms[last_chrom]);
+            en = it == idx.end() ? nullptr : &it->second;
         }
-        const FaiEntry& en = it->second;
-        const long long off = en.off + (pos - 1) / en.linebases * en.linewidth + (pos - 1) % en.linebases;
-        char b = 'N';
-        if (pread(fd, &b, 1, (off_t)off) != 1) { close(fd); err = "short read in " + fasta; return false; }
-        panel.ref[i] = std::string(1, b);
+        const long long pos = panel.slot_pos[i];
+        if (!en || pos < 1 || pos > en->len) {
+            err = "region " + panel.chroms[panel.slot_chrom[i]] + ":" + std::to_string(pos) + " is not in " + fasta;
+            ok = false;
+            break;
+        }
+        const long long off = en->off + (pos - 1) / en->linebases * en->linewidth + (pos - 1) % en->linebases;
+        if (off < 0 || (size_t)off >= fsize) { err = "short read in " + fasta; ok = false; break; }
+        panel.ref[i] = std::string(1, base[off]);
     }
-    close(fd);
-    return true;
+    if (base) munmap((void*)base, fsize);
+    return ok;
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -431,9 +431,15 @@ __global__ void patch_wide_kernel(const as_wide_record* __restrict__ wide, int64
 // ------------------------------------------------------------------------------------------------
 // thresholds as the caller sees them (EE:1787 "%f" text -> VC:889-890 std::stof)
 // ------------------------------------------------------------------------------------------------
+// four values per thread: the fp64 divide of thr_caller_view is a long dependent chain, four of them interleave
 __global__ void thr_view_kernel(const float* __restrict__ thr, float* __restrict__ view, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) view[i] = thr_caller_view(thr[i]);
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n && ((reinterpret_cast<uintptr_t>(thr) | reinterpret_cast<uintptr_t>(view)) & 15) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(thr + i);
+        *reinterpret_cast<float4*>(view + i) = make_float4(thr_caller_view(v.x), thr_caller_view(v.y), thr_caller_view(v.z), thr_caller_view(v.w));
+    } else {
+        for (int64_t k = i; k < n && k < i + 4; ++k) view[k] = thr_caller_view(thr[k]);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1107,7 +1113,7 @@ cudaError_t as_launch_patch_wide(const as_wide_record* d_wide, int64_t m, uint32
 
 cudaError_t as_launch_thr_view(const float* d_thr, float* d_view, int64_t n, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    thr_view_kernel<<<cdiv64(n, 256), 256, 0, st>>>(d_thr, d_view, n);
+    thr_view_kernel<<<cdiv64((n + 3) / 4, 256), 256, 0, st>>>(d_thr, d_view, n);
     return cudaGetLastError();
 }
 

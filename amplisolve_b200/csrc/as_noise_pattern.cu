@@ -541,26 +541,20 @@ cudaError_t as_launch_noise_pattern(int geom, const uint32_t* d_counts, int S, i
                                     float* d_germ_val, uint8_t* d_germ_state, uint32_t* d_count, uint32_t* d_nrec, cudaStream_t st) {
     if (p1 <= p0 || n_c <= 0) return cudaSuccess;
 #define AS_PAT_ARGS d_counts, S, P, p0, p1, d_twin_next, d_twin_head, twin_base, c_values, n_c, cut, d_thr, thr_stride, d_germ_val, d_germ_state, d_count, d_nrec, st
+    // CTAs per SM follow the register need of the per-C sums (ptxas: profiles/r02_ptxas_registers.txt); no variant spills in
+    // its sample loop.  Measured on the c3 shard (profiles/r02_noise_pattern_geometries.log): NC = 1 is slower than
+    // noise_staged_kernel (1.35 vs 1.10 ms: the ALU pipe, not the register file, bounds one value) and is kept as a
+    // cross-check (noise variants 7, 8); NC = 5 at 3 CTAs/SM 1.90 ms against 2.93 ms at 4 CTAs/SM with spills.
     if (n_c == 1) {
-        switch (geom) {
-            case 1: return launch_pattern<1, 4, 2, 6, false>(AS_PAT_ARGS);
-            case 2: return launch_pattern<1, 2, 4, 6, true>(AS_PAT_ARGS);
-            case 3: return launch_pattern<1, 4, 3, 4, false>(AS_PAT_ARGS);
-            case 4: return launch_pattern<1, 2, 3, 7, false>(AS_PAT_ARGS);
-            default: return launch_pattern<1, 4, 3, 4>(AS_PAT_ARGS);
-        }
+        if (geom == 1) return launch_pattern<1, 4, 3, 4, false>(AS_PAT_ARGS);
+        return launch_pattern<1, 4, 3, 4>(AS_PAT_ARGS);
     }
     if (n_c <= 3) return launch_pattern<3, 4, 3, 4>(AS_PAT_ARGS);
     if (n_c <= 5) {
-        switch (geom) {
-            case 1: return launch_pattern<5, 4, 3, 3, false>(AS_PAT_ARGS);
-            case 2: return launch_pattern<5, 2, 4, 3, true>(AS_PAT_ARGS);
-            case 3: return launch_pattern<5, 4, 3, 4, false>(AS_PAT_ARGS);
-            case 4: return launch_pattern<5, 2, 4, 4, false>(AS_PAT_ARGS);
-            default: return launch_pattern<5, 4, 3, 3>(AS_PAT_ARGS);
-        }
+        if (geom == 1) return launch_pattern<5, 4, 3, 3, false>(AS_PAT_ARGS);
+        return launch_pattern<5, 4, 3, 3>(AS_PAT_ARGS);
     }
-    if (n_c <= 8) return launch_pattern<8, 4, 3, 4>(AS_PAT_ARGS);
+    if (n_c <= 8) return launch_pattern<8, 4, 3, 2>(AS_PAT_ARGS);
 #undef AS_PAT_ARGS
     return cudaErrorInvalidValue;
 }

@@ -97,8 +97,8 @@ int as_host_free(void* p);
  *   caller: 0 = straightforward, 1 = per-warp queues over direct loads, TMA-staged with (samples per stage, stages):
  *           3 = (4,2), 11 = (3,2); with the integer pre-screen in the scan: 13 = (3,2) default, 14 = (4,2);
  *           20 = deferred: scan -> resolve -> series kernels over candidate lists (what a sweep of several tables runs)
- *   noise : 0 = direct loads; TMA-staged 1 = (4,3) default, 4 = (8,2), 6 = (4,2); 7..9 = shared-pattern accumulators
- *           (the kernel of as_noise_estimate_sweep_dev) with rings (4,3), (3,3), (4,2) */
+ *   noise : 0 = direct loads; TMA-staged 1 = (4,3) default, 4 = (8,2), 6 = (4,2); 7, 8 = shared-pattern accumulators (the
+ *           kernel of as_noise_estimate_sweep_dev) with the records of a stage interleaved / walked one by one */
 int as_set_call_kernel(as_ctx* ctx, int variant);
 int as_set_noise_kernel(as_ctx* ctx, int variant);
 /* Slots per tile of the _host pipelines: 0 = automatic (~256 MiB of counts per buffer), else a multiple of 128.

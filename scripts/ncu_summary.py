@@ -48,11 +48,14 @@ def summarise(reps):
                     print(f"{k} = {r[idx[k]]} {units[idx[k]]}")
 
 
-def traffic(rep):
-    head, units, rows = raw_rows(rep)
-    idx = {h: i for i, h in enumerate(head)}
+def traffic(reps):
     kernels = OrderedDict()
-    for r in rows:
+    rows_all = []
+    for rep in reps:
+        head, units, rows = raw_rows(rep)
+        rows_all += [(head, units, r) for r in rows]
+    for head, units, r in rows_all:
+        idx = {h: i for i, h in enumerate(head)}
         name = re.sub(r"^void\s+", "", r[idx["Kernel Name"]]).split("<")[0].split("(")[0].replace("asdev::", "")
         kernels[name] = {"dram_bytes_read": to_bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]),
                          "dram_bytes_write": to_bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]),
@@ -60,7 +63,8 @@ def traffic(rep):
                          "duration_ms": float(r[idx["gpu__time_duration.sum"]]) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0),
                          "kernel": r[idx["Kernel Name"]].split("(")[0]}
     doc = {"workload": "c3: synthetic 500-gene panel shard per GPU",
-           "source": f"{Path(rep).name} (ncu --set full --clock-control none, one launch each; scripts/ncu_capture.sh)", "kernels": kernels}
+           "source": f"{', '.join(Path(r).name for r in reps)} (ncu --set full --clock-control none, one launch each; scripts/ncu_capture.sh)",
+           "kernels": kernels}
     (ROOT / "profiles" / "ncu_traffic.json").write_text(json.dumps(doc, indent=1))
     print(json.dumps(doc, indent=1))
 
@@ -87,6 +91,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "--launches":
         launches(sys.argv[2])
     elif sys.argv[1] == "--traffic":
-        traffic(sys.argv[2])
+        traffic(sys.argv[2:])
     else:
         summarise(sys.argv[1:])

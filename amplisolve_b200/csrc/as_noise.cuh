@@ -34,6 +34,10 @@ __device__ __forceinline__ uint32_t af_limit(uint32_t depth_as_float) {
     return (uint32_t)((AS_AF_LIMIT_NUM * (unsigned long long)depth_as_float) >> 29);
 }
 
+// the same for depths below 2^29 (fast paths: a depth of 2^24 or more raises `big` and the slot is redone anyway): the high
+// word of (8 * D) * 26843545, one multiply on the FMA pipe instead of a wide multiply and a 64-bit shift on the ALU pipe
+__device__ __forceinline__ uint32_t af_limit_fast(uint32_t depth) { return __umulhi(depth * 8u, (uint32_t)AS_AF_LIMIT_NUM); }
+
 struct NoiseBase {
     unsigned long long s_b_fw, s_b_bw;  // sum of alt reads over kept records (EE:1617, EE:1619)
     unsigned long long s_d_fw, s_d_bw;  // sum of strand depth over kept records (EE:1618, EE:1620)
@@ -172,9 +176,9 @@ __device__ __forceinline__ void fast_record(FastRecord& r, const uint4 fw, const
     const uint32_t BW = bw.x + bw.y + bw.z + bw.w;
     r.RD = FW + BW;
     const bool cov = min(FW, BW) >= cut;  // counts are < 2^31, so the signed compares below are safe
-    r.lim_fw = cov ? (int32_t)af_limit(FW) : -1;
-    r.lim_bw = cov ? (int32_t)af_limit(BW) : -1;
-    r.lim_rd = cov ? (int32_t)af_limit(r.RD) : -1;
+    r.lim_fw = cov ? (int32_t)af_limit_fast(FW) : -1;
+    r.lim_bw = cov ? (int32_t)af_limit_fast(BW) : -1;
+    r.lim_rd = cov ? (int32_t)af_limit_fast(r.RD) : -1;
     r.d_fw = u32_to_double(FW);
     r.d_bw = u32_to_double(BW);
     r.p_fw = (double)__fmul_rn(__uint2float_rn(FW), C);

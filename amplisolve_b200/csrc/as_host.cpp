@@ -757,9 +757,11 @@ struct GpuContext {
         ctx = wide;
         return true;
     }
+    // The programs end right after their last output file: the context is NOT torn down piece by piece (frees, stream and
+    // event destruction, a device synchronisation: tenths of a second to seconds on a busy box); the thin mains leave
+    // through _exit and the driver reclaims everything at once.  An error path that returns early still joins the thread.
     ~GpuContext() {
         if (starter.joinable()) starter.join();
-        if (ctx) as_destroy(ctx);
     }
 };
 

@@ -95,6 +95,24 @@ def apply_patches(workdir, case, ee_rd=False):
     return done
 
 
+def shuffle_rows(workdir, case):
+    """Files whose rows do not follow the panel enumeration: one tumour file reversed row by row, one with its second half
+    first, one normal file reversed.  The reference does not care (it looks every row up by position; its outputs follow the
+    file's row order); the loader's cursor does, and the writer must order the calls by rows, not by slots."""
+    workdir = Path(workdir)
+
+    def edit(path, fn):
+        lines = Path(path).read_text().split("\n")
+        head, rows = lines[0], [l for l in lines[1:] if l]
+        Path(path).write_text("\n".join([head] + fn(rows)) + "\n")
+
+    t = case["tumour_names"]
+    edit(workdir / "T" / f"{t[1]}.PILEUP.ASEQ", lambda r: r[::-1])
+    edit(workdir / "T" / f"{t[3]}.PILEUP.ASEQ", lambda r: r[len(r) // 2:] + r[:len(r) // 2])
+    edit(workdir / "N" / f"{case['normal_names'][2]}.PILEUP.ASEQ", lambda r: r[::-1])
+    return [("tumour rows reversed", t[1]), ("tumour halves swapped", t[3]), ("normal rows reversed", case["normal_names"][2])]
+
+
 def run_reference(workdir, case):
     noise, _ = refrun.run_ee_ref(workdir, "panel.bed", "rb_ref.txt", "rb_dup.txt", "N", f"{float(case['c_value']):.4f}", str(int(case["cutoff"])))
     out = refrun.run_vc_ref(workdir, str(noise.relative_to(workdir)), "T", "v", cutoff=int(case["cutoff"]), p_value=0.05)
@@ -111,11 +129,18 @@ def main():
             done = apply_patches(td, case, ee_rd=ee_rd)
             table, summary, vcfs = run_reference(Path(td), case)
             res[tag] = (table, summary, vcfs, done)
+    with tempfile.TemporaryDirectory(prefix="irr_", dir="/tmp") as td:
+        aseq_io.stage_case(td, case)
+        shuffle_rows(td, case)
+        res["c"] = run_reference(Path(td), case) + (None,)
+    cn = sorted(res["c"][2])
     names = sorted(res["a"][2])
-    np.savez_compressed(HERE / "irregular_rows.npz", noise_table=np.array(res["a"][0]), summary=np.array(res["a"][1]),
+    np.savez_compressed(HERE / "irregular_rows.npz", shuffled_noise_table=np.array(res["c"][0]), shuffled_summary=np.array(res["c"][1]),
+                        shuffled_vcf_names=np.array(cn), shuffled_vcf_bodies=np.array([res["c"][2][n] for n in cn]), noise_table=np.array(res["a"][0]), summary=np.array(res["a"][1]),
                         vcf_names=np.array(names), vcf_bodies=np.array([res["a"][2][n] for n in names]),
                         patches=np.array(repr(res["a"][3])), noise_table_rd=np.array(res["b"][0]), patches_rd=np.array(repr(res["b"][3])))
     base = case["noise_table"].splitlines()
+    print("shuffled rows: summary equals the unshuffled one:", res["c"][1] == case["summary"], "| noise table equal:", res["c"][0] == case["noise_table"])
     for tag in ("a", "b"):
         new = res[tag][0].splitlines()
         diff = [i for i, (x, y) in enumerate(zip(base, new)) if x != y]

@@ -229,3 +229,21 @@ def test_rd_column_of_a_normal_row_is_the_one_documented_deviation(tmp_path):
     for a, b in diff:
         assert a[:2] == [chrom, str(pos)] and a[:8] == b[:8] and a[8:] != b[8:]   # thresholds equal, Germ_Max differs
     assert ours == str(fx["noise_table"]).splitlines()        # = the table without the RD edit: the sum is what is used
+
+
+def test_files_whose_rows_do_not_follow_the_panel_order(tmp_path):
+    """ASEQ files normally list their rows in the panel's enumeration order, which the loader's cursor and the device's
+    (sample, slot, alt) sort rely on.  A file that does not (rows reversed, halves swapped) takes the fall-back paths: hash
+    lookup per row, a second parse with a row -> slot map, calls re-ordered by file row.  Outputs must still equal the
+    compiled reference's, byte for byte (tests/golden/make_irregular.py shuffle_rows)."""
+    mod, fx = _irregular()
+    case = gu.load("synth_small")
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    mod.shuffle_rows(tmp_path, case)
+    table = _run_both_programs(case, tmp_path)
+    assert table == str(fx["shuffled_noise_table"])
+    summary = (tmp_path / "v" / "Summary_Variant_Info.txt").read_text()
+    assert summary == str(fx["shuffled_summary"]) and summary != case["summary"]      # same calls, another order
+    for nm, body in zip(fx["shuffled_vcf_names"], fx["shuffled_vcf_bodies"]):
+        assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == str(body), nm

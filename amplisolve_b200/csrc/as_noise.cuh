@@ -195,7 +195,20 @@ __device__ __forceinline__ void fast_base_update(FastBase& s, const FastRecord& 
     const uint32_t x = bf + bb;
     const bool qual = (int32_t)x <= r.lim_rd;
     // bitwise &: both products are always formed so that the update is predicated, not branched
-    const bool ge = (unsigned long long)x * s.g_rd >= (unsigned long long)s.g_x * r.RD;  // EE:1263: value <= AF
+    // EE:1263 (value <= AF) as the sign of x * g_rd - g_x * RD: two wide multiply-adds and ONE compare of the high word
+    // (all four numbers are below 2^24 where it counts, so the difference fits 64 signed bits with room to spare)
+    int32_t diff_hi;
+    asm("{\n"
+        ".reg .u64 p, d;\n"
+        ".reg .s32 ng, lo;\n"
+        "mul.wide.u32 p, %1, %2;\n"
+        "neg.s32 ng, %3;\n"
+        "mad.wide.s32 d, ng, %4, p;\n"
+        "mov.b64 {lo, %0}, d;\n"
+        "}\n"
+        : "=r"(diff_hi)
+        : "r"(x), "r"(s.g_rd), "r"(s.g_x), "r"(r.RD));
+    const bool ge = diff_hi >= 0;
     const bool first = qual & (s.g_rd == 0u);
     const bool upd = qual & ge;
     s.g_x = first ? 0u : (upd ? x : s.g_x);

@@ -748,7 +748,9 @@ struct GpuContext {
     bool widen(double records) {
         if (!wait()) return false;
         int n = 0;
-        if (explicit_list || records < 268435456.0 || as_device_count(&n) != AS_OK || n < 2) return true;
+        double threshold = 268435456.0;
+        if (const char* env = getenv("AS_WIDEN_RECORDS")) threshold = atof(env);  // tests
+        if (explicit_list || records < threshold || as_device_count(&n) != AS_OK || n < 2) return true;
         std::vector<int> devs;
         for (int i = 0; i < n; ++i) devs.push_back(i);
         as_ctx* wide = nullptr;
@@ -1368,7 +1370,8 @@ int as_variant_calling_main(int argc, char** argv) {
     if (T > 0 && P > 0) {
         int64_t budget_mb = 512;
         if (const char* env = getenv("AS_GROUP_MB")) budget_mb = std::max<long long>(1, atoll(env));
-        const int64_t G = std::max<int64_t>(1, std::min<int64_t>(T, (budget_mb << 20) / std::max<int64_t>(1, 16 * P)));
+        int64_t G = std::max<int64_t>(1, std::min<int64_t>(T, (budget_mb << 20) / std::max<int64_t>(1, 16 * P)));
+        if (const char* env = getenv("AS_GROUP_SAMPLES")) G = std::max<long long>(1, std::min<long long>(T, atoll(env)));  // tests
         HostCounts buf[2];
         std::vector<AseqStats> stats[2];
         auto load_group = [&](int64_t first, int which) -> int {

@@ -247,3 +247,21 @@ def test_files_whose_rows_do_not_follow_the_panel_order(tmp_path):
     assert summary == str(fx["shuffled_summary"]) and summary != case["summary"]      # same calls, another order
     for nm, body in zip(fx["shuffled_vcf_names"], fx["shuffled_vcf_bodies"]):
         assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == str(body), nm
+
+
+@pytest.mark.parametrize("group", [1, 2, 4])
+def test_caller_program_in_sample_groups(group, tmp_path):
+    """The variant-calling program parses and calls the tumours in groups (two pinned buffers: one group is parsed while the
+    GPU works on the other).  Whatever the group size -- here 1, 2 and 4 of 6 tumours, incl. a last group that is not full --
+    the outputs are the reference's."""
+    case = gu.load("synth_small")
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    (tmp_path / "o").mkdir()
+    table = tmp_path / "o" / ("positionSpecificNoise_%.4f.txt" % float(case["c_value"]))
+    table.write_text(case["noise_table"])
+    run("AmpliSolveVariantCalling", [f"errorFile=o/{table.name}", "tumour_dir=T", "output_dir=v",
+                                     f"coverage_cutoff={int(case['cutoff'])}", "p_value=0.05"], tmp_path, {"AS_GROUP_SAMPLES": str(group)})
+    assert (tmp_path / "v" / "Summary_Variant_Info.txt").read_text() == case["summary"]
+    for nm in case["tumour_names"]:
+        assert vcf_body(tmp_path / "v" / f"{nm}.vcf") == case["vcfs"][nm], nm

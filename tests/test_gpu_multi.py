@@ -63,12 +63,15 @@ def test_multi_device_host_entry_points_equal_single_device(ctx, devices, tile):
 def test_programs_on_several_gpus_are_byte_identical_to_one_gpu(tmp_path, devices):
     case = gu.load("synth_small")
     outs = {}
-    for tag, devs in (("one", "0"), ("many", ",".join(map(str, devices)))):
+    for tag, devs in (("one", "0"), ("many", ",".join(map(str, devices))), ("widened", None)):
         wd = tmp_path / tag
         wd.mkdir()
         slots = aseq_io.stage_case(wd, case)
         aseq_io.write_fasta(wd, slots, list(case["ref_letters"]))
-        env = dict(os.environ, AS_DEVICES=devs)
+        # "widened": no device list -- the program starts on GPU 0 and moves to every visible GPU once it knows the job is
+        # large (the threshold is lowered to 1 record here), parsing and calling in groups of two samples
+        env = dict(os.environ, AS_DEVICES=devs) if devs else dict(os.environ, AS_WIDEN_RECORDS="1", AS_GROUP_SAMPLES="2")
+        env.pop("AS_DEVICES", None) if devs is None else None
         r = subprocess.run([str(BIN / "AmpliSolveErrorEstimation"), "panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N",
                             f"C_value={float(case['c_value']):.4f}", f"coverage_cutoff={int(case['cutoff'])}", "default_error=0.01",
                             "output_dir=o"], cwd=wd, capture_output=True, text=True, env=env)
@@ -80,5 +83,5 @@ def test_programs_on_several_gpus_are_byte_identical_to_one_gpu(tmp_path, device
         vcfs = sorted((wd / "v").glob("*.vcf"))
         outs[tag] = (table.read_bytes(), (wd / "v" / "Summary_Variant_Info.txt").read_bytes(),
                      [b"".join(l for l in open(v, "rb") if not l.startswith(b"##fileDate=")) for v in vcfs])
-    assert outs["one"] == outs["many"]
+    assert outs["one"] == outs["many"] == outs["widened"]
     assert outs["one"][0].decode() == case["noise_table"]

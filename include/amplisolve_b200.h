@@ -115,7 +115,9 @@ int64_t as_kernel_launches(const as_ctx* ctx);
  * Inputs : counts of the S normals in the reference's file-iteration order (EE:1081; Germ_Max
  *          depends on it), twin_next/twin_head [P] or NULL, C = the float C_value (EE:329), cut >= 1.
  *          Slots [slot_begin, slot_end) of the tensor are processed; a twin group is processed when
- *          its head lies in the range (all of its members must be resident).
+ *          its head lies in the range (all of its members must be resident; they are written even when they
+ *          lie outside the range).  The in-range members of a group whose head lies OUTSIDE the range are
+ *          left unwritten: cut panels with as_shard_bounds, which never splits a group.
  * Outputs (per slot, indexed by slot; twins receive identical values):
  *   thr        float  [P][4][2]  fw,bw threshold per base; NaN = the "-1_-1" text (EE:1742-1770)
  *   germ_val   float  [P][4]     Germ_Max value: the maximal float(X)/float(RD) when germ_state == 2,

@@ -15,7 +15,9 @@
  *   - "_host" entry points take host pointers (pinned or pageable) and do H2D, kernels and D2H
  *     themselves, tiling over slots with double-buffered streams; "_dev" entry points take
  *     device pointers (inputs resident in HBM) and only enqueue kernels on `stream`
- *     (a cudaStream_t passed as void*; NULL = the legacy default stream).
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream).  They use scratch owned by the
+ *     context (twin-group lists, candidate lists of a sweep): enqueue the _dev calls of ONE context on ONE
+ *     stream, or synchronise between calls that go to different streams; use one context per thread.
  *
  * Data layout ("count tensor"): uint32 counts[sample][strand][slot][base]
  *     strand 0 = forward, 1 = reverse; base 0..3 = A,C,G,T; one 16-byte word per (sample,strand,slot),

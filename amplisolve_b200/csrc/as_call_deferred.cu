@@ -15,9 +15,11 @@
 //                        (one atomic per ~25 entries).  No threshold read, no fp64, nothing long while a stage is held.
 //   call_resolve_kernel  one thread per candidate: the thresholds of the candidate's (slot, alt) in every table (the list
 //                        is in tile order, so these reads hit L2), the two exact screens per table (as_call.cuh) -> a bit
-//                        mask of the tables in which the pair can still be a call; survivors go to a second list.
-//   call_series_kernel   grid.y = table: two lanes per survivor (forward / reverse strand) evaluate the capped fp64 series
-//                        of VC:3785-3794; calls are appended to the table's list with one atomic per warp.
+//                        mask of the tables in which the pair can still be a call; the survivors of table ci go to list ci
+//                        (one atomic per table and 256-thread block).
+//   call_series_kernel   grid.y = table: two lanes per survivor of that table's list (forward / reverse strand) evaluate the
+//                        capped fp64 series of VC:3785-3794 -- every lane has work; calls are appended to the table's call
+//                        list with one atomic per warp.
 //
 // Both lists live in scratch owned by the context.  An entry that does not fit its list is resolved on the spot by the
 // thread that holds it (resolve_inline): slower, never wrong -- the call sets do not depend on the list capacities (tested
@@ -29,19 +31,18 @@
 
 namespace asdev {
 
-struct Survivor {  // 32 bytes
+struct Survivor {  // 32 bytes: an entry of one table's survivor list
     StagedCand c;
-    uint32_t tables;  // bit ci: both strands can still pass under table ci
-    uint32_t pad;
+    uint32_t pad[2];
 };
 static_assert(sizeof(Survivor) == 32, "Survivor is two 16-byte words");
 
 struct DeferredLists {
     StagedCand* cand;
     unsigned long long cap_cand;
-    Survivor* surv;
-    unsigned long long cap_surv;
-    unsigned long long* counters;  // [0] candidates appended (may exceed cap_cand), [1] survivors appended
+    Survivor* surv;                // list of table ci at surv + ci * cap_surv
+    unsigned long long cap_surv;   // per table
+    unsigned long long* counters;  // [0] candidates appended (may exceed cap_cand), [1 + ci] survivors of table ci appended
 };
 
 struct CallSink {  // where calls go: table ci owns calls + ci * cap and n_calls[ci]
@@ -238,10 +239,11 @@ call_scan_kernel(const uint4* __restrict__ counts, int T, int64_t P, int64_t p0,
 
 __global__ void __launch_bounds__(256)
 call_resolve_kernel(DeferredLists L, CallSink sink) {
-    __shared__ uint32_t warp_n[8];
-    __shared__ unsigned long long block_base;
+    __shared__ uint32_t warp_n[8][8];  // [table][warp]
+    __shared__ unsigned long long block_base[8];
     const unsigned long long n = min(L.counters[0], L.cap_cand);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t below = (1u << lane) - 1u;
     for (unsigned long long i0 = (unsigned long long)blockIdx.x * 256; i0 < n; i0 += (unsigned long long)gridDim.x * 256) {
         const unsigned long long i = i0 + threadIdx.x;
         StagedCand c;
@@ -252,25 +254,41 @@ call_resolve_kernel(DeferredLists L, CallSink sink) {
             c.k_fw = a.x; c.d_fw = a.y; c.k_bw = b.x; c.d_bw = b.y; c.sample_alt = d.x; c.slot = (int32_t)d.y;
             tables = screen_tables(sink, c);
         }
-        const unsigned votes = __ballot_sync(0xffffffffu, tables != 0);
-        if (lane == 0) warp_n[warp] = __popc(votes);
+        uint32_t rank = 0;  // rank of this lane among its warp's survivors of table ci: 5 bits per table, tables 0..5 here, 6..7 in rank_hi
+        uint32_t rank_hi = 0;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            if (ci < sink.n_c) {
+                const unsigned votes = __ballot_sync(0xffffffffu, (tables >> ci) & 1u);
+                if (lane == 0) warp_n[ci][warp] = __popc(votes);
+                const uint32_t r = __popc(votes & below);
+                if (ci < 6) rank |= r << (5 * ci); else rank_hi |= r << (5 * (ci - 6));
+            }
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < sink.n_c) {
             uint32_t tot = 0;
-            for (int w = 0; w < 8; ++w) tot += warp_n[w];
-            block_base = tot ? atomicAdd(&L.counters[1], (unsigned long long)tot) : 0ull;
+            for (int w = 0; w < 8; ++w) tot += warp_n[threadIdx.x][w];
+            block_base[threadIdx.x] = tot ? atomicAdd(&L.counters[1 + threadIdx.x], (unsigned long long)tot) : 0ull;
         }
         __syncthreads();
         if (tables != 0) {
-            unsigned long long idx = block_base + __popc(votes & ((1u << lane) - 1u));
-            for (int w = 0; w < warp; ++w) idx += warp_n[w];
-            if (idx < L.cap_surv) {
-                uint4* dst = reinterpret_cast<uint4*>(L.surv + idx);
-                dst[0] = make_uint4(c.k_fw, c.d_fw, c.k_bw, c.d_bw);
-                dst[1] = make_uint4(c.sample_alt, (uint32_t)c.slot, tables, 0u);
-            } else {
-                resolve_inline(sink, c, tables);  // list full: resolve here
+            uint32_t inline_tables = 0;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                if (ci < sink.n_c && ((tables >> ci) & 1u)) {
+                    unsigned long long idx = block_base[ci] + ((ci < 6 ? rank >> (5 * ci) : rank_hi >> (5 * (ci - 6))) & 31u);
+                    for (int w = 0; w < warp; ++w) idx += warp_n[ci][w];
+                    if (idx < L.cap_surv) {
+                        uint4* dst = reinterpret_cast<uint4*>(L.surv + (unsigned long long)ci * L.cap_surv + idx);
+                        dst[0] = make_uint4(c.k_fw, c.d_fw, c.k_bw, c.d_bw);
+                        dst[1] = make_uint4(c.sample_alt, (uint32_t)c.slot, 0u, 0u);
+                    } else {
+                        inline_tables |= 1u << ci;  // list full: resolve here
+                    }
+                }
             }
+            if (inline_tables) resolve_inline(sink, c, inline_tables);
         }
         __syncthreads();  // warp_n / block_base are rewritten by the next round
     }
@@ -279,23 +297,21 @@ call_resolve_kernel(DeferredLists L, CallSink sink) {
 __global__ void __launch_bounds__(128)
 call_series_kernel(DeferredLists L, CallSink sink) {
     const int ci = blockIdx.y;
-    const unsigned long long n = min(L.counters[1], L.cap_surv);
+    const unsigned long long n = min(L.counters[1 + ci], L.cap_surv);
+    const Survivor* list = L.surv + (unsigned long long)ci * L.cap_surv;
     const int lane = threadIdx.x & 31, pair = lane >> 1, strand = lane & 1;
     const unsigned long long warps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
     for (unsigned long long g = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; g * 16 < n; g += warps) {
         const unsigned long long i = g * 16 + pair;
         StagedCand c;
-        bool active = false;
+        const bool active = i < n;
         double p = 1.0;
-        if (i < n) {
-            const uint4* src = reinterpret_cast<const uint4*>(L.surv + i);
+        if (active) {
+            const uint4* src = reinterpret_cast<const uint4*>(list + i);
             const uint4 a = src[0], b = src[1];
             c.k_fw = a.x; c.d_fw = a.y; c.k_bw = a.z; c.d_bw = a.w; c.sample_alt = b.x; c.slot = (int32_t)b.y;
-            active = (b.z >> ci) & 1u;
-            if (active) {
-                const float e = sink.thr_view[(int64_t)ci * sink.c_stride + (int64_t)c.slot * 8 + 2 * (c.sample_alt >> 30) + strand];
-                p = strand == 0 ? poisson_p((int)c.k_fw, (int)c.d_fw, e) : poisson_p((int)c.k_bw, (int)c.d_bw, e);  // VC:895-896
-            }
+            const float e = sink.thr_view[(int64_t)ci * sink.c_stride + (int64_t)c.slot * 8 + 2 * (c.sample_alt >> 30) + strand];
+            p = strand == 0 ? poisson_p((int)c.k_fw, (int)c.d_fw, e) : poisson_p((int)c.k_bw, (int)c.d_bw, e);  // VC:895-896
         }
         const double p_other = __shfl_xor_sync(0xffffffffu, p, 1);
         const bool is_call = active && strand == 0 && q_at_least_5(p) && q_at_least_5(p_other);  // VC:898
@@ -319,8 +335,8 @@ size_t as_deferred_scratch_bytes(int T, int64_t n_slots, int64_t* cap_cand, int6
     int64_t cc = (int64_t)T * n_slots / 24;
     cc = std::max<int64_t>(1 << 20, std::min<int64_t>(cc, 64ll << 20));
     *cap_cand = cc;
-    *cap_surv = std::max<int64_t>(1 << 18, cc / 4);
-    return 4096 + (size_t)cc * sizeof(StagedCand) + (size_t)*cap_surv * sizeof(Survivor) + 512 * AS_DEFER_MAX_CHUNKS;
+    *cap_surv = std::max<int64_t>(1 << 18, cc / 4);  // per table
+    return 4096 + (size_t)cc * sizeof(StagedCand) + 8 * (size_t)*cap_surv * sizeof(Survivor) + 512 * AS_DEFER_MAX_CHUNKS;
 }
 
 // pieces a range is cut into: at most `want`, and at least two full waves of scan CTAs (148 SMs x 7) per piece
@@ -343,10 +359,10 @@ cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, 
     const int64_t tiles = (p1 - p0 + AS_TILE_SLOTS - 1) / AS_TILE_SLOTS;
     n_chunks = (aux == nullptr || ev == nullptr) ? 1 : as_deferred_chunks(p1 - p0, n_chunks);
     CallSink sink{d_ref, d_thr_views, n_c, c_stride, d_calls, cap, d_n_calls};
-    unsigned long long* counters = (unsigned long long*)d_scratch;  // two per piece
+    unsigned long long* counters = (unsigned long long*)d_scratch;  // 16 per piece: candidates, survivors of tables 0..7
     StagedCand* cand0 = (StagedCand*)((char*)d_scratch + 4096);
     Survivor* surv0 = (Survivor*)((char*)d_scratch + 4096 + (((size_t)cap_cand * sizeof(StagedCand) + 255) & ~(size_t)255));
-    cudaError_t e = cudaMemsetAsync(counters, 0, 16 * AS_DEFER_MAX_CHUNKS, st);
+    cudaError_t e = cudaMemsetAsync(counters, 0, 128 * AS_DEFER_MAX_CHUNKS, st);
     if (e != cudaSuccess) return e;
     constexpr int K = 3, STAGES = 2;
     static bool configured[AS_MAX_DEVICES] = {};
@@ -365,11 +381,11 @@ cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, 
         const int64_t q0 = p0 + t_lo * AS_TILE_SLOTS, q1 = std::min(p1, p0 + t_hi * AS_TILE_SLOTS);
         if (q1 <= q0) continue;
         DeferredLists L;
-        L.counters = counters + 2 * ch;
+        L.counters = counters + 16 * ch;
         L.cap_cand = (unsigned long long)(cap_cand / n_chunks);
         L.cap_surv = (unsigned long long)(cap_surv / n_chunks);
         L.cand = cand0 + (size_t)ch * L.cap_cand;
-        L.surv = surv0 + (size_t)ch * L.cap_surv;
+        L.surv = surv0 + (size_t)ch * 8 * L.cap_surv;
         dim3 grid((unsigned)(t_hi - t_lo), gy);
         call_scan_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(d_counts), T, P, q0, q1, chunk,
                                                                           cut, L, sink);

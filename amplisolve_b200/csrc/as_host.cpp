@@ -1166,31 +1166,60 @@ int as_error_estimation_main(int argc, char** argv) {
     char out_name[4096];
     snprintf(out_name, sizeof out_name, "%s/positionSpecificNoise_%.4f.txt", output_dir.c_str(), C_value_float);
     {
+        // rows are formatted in chunks on all host threads (2 M rows took 2.7 s on one: "%f" eight times a row) and written
+        // in order; the bytes are what the reference's streams produce: "%f" (EE:1787), operator<<(double) = "%g" (EE:2815)
         std::ofstream output(out_name);
         output << header << "\n";
-        const char* L = "ACGT";
-        char cell[128];
-        for (int64_t i = 0; i < P; ++i) {
-            output << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i];
-            output << "\t" << (panel.dup[i] ? "YES" : "NO");
-            for (int b = 0; b < 4; ++b) {
-                const float tf = thr[(size_t)i * 8 + b * 2], tb = thr[(size_t)i * 8 + b * 2 + 1];
-                if (panel.ref[i].size() == 1 && panel.ref[i][0] == L[b]) {
-                    output << "\t-2_-2";  // EE:2668-2673
-                } else if (std::isnan(tf) || std::isnan(tb)) {
-                    output << "\t0.01_0.01";  // "-1_-1" -> EE:2680-2684
-                } else {
-                    snprintf(cell, sizeof cell, "%f_%f", (double)tf, (double)tb);  // EE:1787
-                    output << "\t" << cell;
+        const int64_t CH = 16384;
+        const size_t n_chunks = (size_t)((P + CH - 1) / CH);
+        const size_t WAVE = 256;  // chunks formatted before they are written: bounds the text held in memory
+        std::vector<std::string> text(std::min(n_chunks, WAVE));
+        for (size_t w0 = 0; w0 < n_chunks; w0 += WAVE) {
+            const size_t wn = std::min(WAVE, n_chunks - w0);
+            std::atomic<size_t> next(0);
+            auto work = [&]() {
+                const char* L = "ACGT";
+                char cell[160];
+                for (size_t k = next.fetch_add(1); k < wn; k = next.fetch_add(1)) {
+                    std::string& o = text[k];
+                    o.clear();
+                    const int64_t i0 = (int64_t)(w0 + k) * CH, i1 = std::min(P, i0 + CH);
+                    for (int64_t i = i0; i < i1; ++i) {
+                        o += panel.chroms[panel.slot_chrom[i]];
+                        o += '\t';
+                        o += std::to_string(panel.slot_pos[i]);
+                        o += '\t';
+                        o += panel.ref[i];
+                        o += panel.dup[i] ? "\tYES" : "\tNO";
+                        for (int b = 0; b < 4; ++b) {
+                            const float tf = thr[(size_t)i * 8 + b * 2], tb = thr[(size_t)i * 8 + b * 2 + 1];
+                            if (panel.ref[i].size() == 1 && panel.ref[i][0] == L[b]) {
+                                o += "\t-2_-2";  // EE:2668-2673
+                            } else if (std::isnan(tf) || std::isnan(tb)) {
+                                o += "\t0.01_0.01";  // "-1_-1" -> EE:2680-2684
+                            } else {
+                                snprintf(cell, sizeof cell, "\t%f_%f", (double)tf, (double)tb);  // EE:1787
+                                o += cell;
+                            }
+                        }
+                        for (int b = 0; b < 4; ++b) {
+                            if (germ_state[(size_t)i * 4 + b] == 0) {
+                                o += "\t-";  // EE:2807-2849
+                            } else {
+                                snprintf(cell, sizeof cell, "\t%g", (double)germ_val[(size_t)i * 4 + b]);  // ostream << double
+                                o += cell;
+                            }
+                        }
+                        o += '\n';
+                    }
                 }
-            }
-            for (int b = 0; b < 4; ++b) {
-                if (germ_state[(size_t)i * 4 + b] == 0)
-                    output << "\t" << "-";  // EE:2807-2849
-                else
-                    output << "\t" << (double)germ_val[(size_t)i * 4 + b];
-            }
-            output << "\n";
+            };
+            const unsigned hw = (unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), wn));
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
+            work();
+            for (auto& t : th) t.join();
+            for (size_t k = 0; k < wn; ++k) output.write(text[k].data(), (std::streamsize)text[k].size());
         }
     }
     timer.lap("write_noise_table", (double)P, "rows");
@@ -1263,47 +1292,70 @@ int as_variant_calling_main(int argc, char** argv) {
             printf("Error from storeInputFile function: Cannot open %s\n", error_file.c_str());
             return 0;
         }
-        std::ofstream dummy((interm + "/dummyVCF_1.vcf").c_str());
+        std::string dummy_text;  // dummyVCF_1.vcf (VC:564), written in one piece
+        dummy_text.reserve(text.size() / 3);
         const char* p = text.data();
         const char* e = p + text.size();
         const char* eol = (const char*)memchr(p, '\n', e - p);  // header
         p = eol ? eol + 1 : e;
+        {
+            size_t rows = 0;
+            for (const char* c = p; c < e; ++rows) { c = (const char*)memchr(c, '\n', e - c); c = c ? c + 1 : e; }
+            panel.slot_chrom.reserve(rows); panel.slot_pos.reserve(rows); panel.pos_text.reserve(rows); panel.ref.reserve(rows);
+            panel.dup.reserve(rows); thr_view.reserve(rows * 8); germ_text.reserve(rows * 4);
+        }
+        // a threshold cell "<fw>_<bw>" as sscanf("%[^_]_%[^_]") + std::stof read it (VC:888-890); no copies
+        auto part = [](const char* b, const char* end) -> float { return (b >= end || *b == '_') ? 0.f : strtof(b, nullptr); };
+        const char* last_chrom_b = nullptr;
+        size_t last_chrom_n = 0;
+        int32_t last_chrom_id = -1;
         while (p < e) {
             eol = (const char*)memchr(p, '\n', e - p);
             if (!eol) eol = e;
-            std::string f[12];
+            const char* fb[12];
+            const char* fe[12];
             const char* q = p;
             int nf = 0;
             for (; nf < 12; ++nf) {
                 q = skip_ws(q, eol);
                 const char* t = token_end(q, eol);
                 if (t == q) break;
-                f[nf].assign(q, t);
+                fb[nf] = q;
+                fe[nf] = t;
                 q = t;
             }
+            for (int k = nf; k < 12; ++k) fb[k] = fe[k] = eol;  // missing fields read as empty strings
             if (nf >= 1) {
-                const int32_t c = panel.chrom_id(f[0]);
-                panel.add_slot(c, atoi(f[1].c_str()));
-                panel.pos_text.push_back(f[1]);
-                panel.ref.push_back(f[2]);
-                panel.dup.push_back(f[3] == "YES" ? 1 : 0);
+                const size_t cn = (size_t)(fe[0] - fb[0]);
+                if (last_chrom_id < 0 || cn != last_chrom_n || memcmp(last_chrom_b, fb[0], cn) != 0) {
+                    last_chrom_id = panel.chrom_id(std::string(fb[0], fe[0]));
+                    last_chrom_b = fb[0];
+                    last_chrom_n = cn;
+                }
+                panel.add_slot(last_chrom_id, (int32_t)strtol(fb[1], nullptr, 10));  // fields end at a blank, a tab or the line end: strtol stops there
+                panel.pos_text.emplace_back(fb[1], fe[1]);
+                panel.ref.emplace_back(fb[2], fe[2]);
+                panel.dup.push_back((fe[3] - fb[3] == 3 && memcmp(fb[3], "YES", 3) == 0) ? 1 : 0);
                 for (int b = 0; b < 4; ++b) {
-                    const std::string& cellv = f[4 + b];
-                    const size_t us = cellv.find('_');
+                    const char* cb = fb[4 + b];
+                    const char* ce = fe[4 + b];
+                    const char* us = (const char*)memchr(cb, '_', (size_t)(ce - cb));
                     float a = 0.f, bwv = 0.f;
-                    if (us != std::string::npos) {
-                        a = strtof(cellv.substr(0, us).c_str(), nullptr);
-                        const std::string rest = cellv.substr(us + 1);
-                        bwv = strtof(rest.substr(0, rest.find('_')).c_str(), nullptr);
+                    if (us) {
+                        a = part(cb, us);
+                        bwv = part(us + 1, ce);
                     }
                     thr_view.push_back(a);
                     thr_view.push_back(bwv);
-                    germ_text.push_back(f[8 + b]);
+                    germ_text.emplace_back(fb[8 + b], fe[8 + b]);
                 }
-                dummy << f[0] << "\t" << f[1] << "\t.\t.\t.\t.\t.\t." << "\n";
+                dummy_text.append(fb[0], fe[0]).push_back('\t');
+                dummy_text.append(fb[1], fe[1]).append("\t.\t.\t.\t.\t.\t.\n");
             }
             p = eol + 1;
         }
+        std::ofstream dummy((interm + "/dummyVCF_1.vcf").c_str());
+        dummy.write(dummy_text.data(), (std::streamsize)dummy_text.size());
     }
     panel.link();
     const int64_t P = panel.size();

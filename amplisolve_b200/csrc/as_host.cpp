@@ -712,29 +712,57 @@ int64_t add_spill_slots(const Panel& panel, HostCounts& hc, const std::vector<As
     return P2;
 }
 
-// The GPUs of a run.  AS_DEVICES ("0,2,3") names them; otherwise the program starts on GPU 0 -- on a thread at program entry:
-// CUDA start-up takes 0.2-2 s, the panel / noise table is read meanwhile -- and widens to every visible GPU once the size
-// of the job is known and large enough to repay the extra start-up (about a second per device): wants_all_devices().
+// The GPUs of a run, chosen BEFORE the first CUDA call from the size of the ASEQ directory (bytes / 45 ~ records):
+//   AS_DEVICES ("0,2,3") names them; otherwise a job below 2^28 records (2 GB in the packed format, ~40 ms of GPU time) runs
+//   on one GPU -- several would only add start-up time -- and a larger one on every visible GPU (as_create_multi).
+// When the process's device list is not fixed from outside, CUDA_VISIBLE_DEVICES is narrowed to the chosen devices first, so
+// that the driver initialises those only (start-up grows with the number of visible GPUs).  The context is created on a
+// thread at program entry: CUDA start-up takes 0.2-4 s on the test boxes, the panel / noise table is read meanwhile.
+double aseq_dir_records(const std::string& dir) {
+    double bytes = 0;
+    if (DIR* d = opendir(dir.c_str())) {
+        while (dirent* en = readdir(d)) {
+            const std::string n = en->d_name;
+            struct stat sb;
+            if (n.size() >= 5 && n.compare(n.size() - 5, 5, ".ASEQ") == 0 && stat((dir + "/" + n).c_str(), &sb) == 0) bytes += (double)sb.st_size;
+        }
+        closedir(d);
+    }
+    return bytes / 45.0;
+}
+
 struct GpuContext {
     as_ctx* ctx = nullptr;
     int rc = AS_OK;
     std::string error;
     std::thread starter;
-    bool explicit_list = false;
-    void start() {
-        starter = std::thread([this]() {
-            std::vector<int> devs;
-            if (const char* env = getenv("AS_DEVICES")) {
-                for (const char* q = env; *q;) {
-                    char* endp = nullptr;
-                    const long d = strtol(q, &endp, 10);
-                    if (endp == q) break;
-                    devs.push_back((int)d);
-                    q = *endp == ',' ? endp + 1 : endp;
-                }
+    void start(double estimated_records) {
+        // the device list and the environment are settled here, on the calling thread (setenv must not race with getenv)
+        std::vector<int> devs;
+        if (const char* env = getenv("AS_DEVICES")) {
+            for (const char* q = env; *q;) {
+                char* endp = nullptr;
+                const long d = strtol(q, &endp, 10);
+                if (endp == q) break;
+                devs.push_back((int)d);
+                q = *endp == ',' ? endp + 1 : endp;
             }
-            explicit_list = !devs.empty();
-            if (devs.empty()) devs.push_back(0);
+        }
+        double threshold = 268435456.0;
+        if (const char* env = getenv("AS_WIDEN_RECORDS")) threshold = atof(env);  // tests
+        if (devs.empty() && estimated_records < threshold) devs.push_back(0);
+        if (!devs.empty() && getenv("CUDA_VISIBLE_DEVICES") == nullptr) {  // initialise only what is used; ordinals become 0..n-1
+            std::string list;
+            for (size_t i = 0; i < devs.size(); ++i) list += (i ? "," : "") + std::to_string(devs[i]);
+            setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
+            for (size_t i = 0; i < devs.size(); ++i) devs[i] = (int)i;
+        }
+        starter = std::thread([this, devs]() mutable {
+            if (devs.empty()) {  // a large job: every visible GPU
+                int n = 0;
+                if (as_device_count(&n) != AS_OK || n == 0) n = 1;  // as_create(0) below fails with the "no CUDA device" message
+                for (int i = 0; i < n; ++i) devs.push_back(i);
+            }
             rc = devs.size() == 1 ? as_create(devs[0], &ctx) : as_create_multi(devs.data(), (int)devs.size(), &ctx);
             if (rc != AS_OK) error = as_last_error();
         });
@@ -742,22 +770,6 @@ struct GpuContext {
     bool wait() {
         if (starter.joinable()) starter.join();
         return rc == AS_OK && ctx != nullptr;
-    }
-    // records = samples x slots of the job.  Below 2^28 records (2 GB in the packed format, ~40 ms of GPU time) one GPU is
-    // faster end to end than several.
-    bool widen(double records) {
-        if (!wait()) return false;
-        int n = 0;
-        double threshold = 268435456.0;
-        if (const char* env = getenv("AS_WIDEN_RECORDS")) threshold = atof(env);  // tests
-        if (explicit_list || records < threshold || as_device_count(&n) != AS_OK || n < 2) return true;
-        std::vector<int> devs;
-        for (int i = 0; i < n; ++i) devs.push_back(i);
-        as_ctx* wide = nullptr;
-        if (as_create_multi(devs.data(), n, &wide) != AS_OK) return true;  // keep the one GPU
-        as_destroy(ctx);
-        ctx = wide;
-        return true;
     }
     // The programs end right after their last output file: the context is NOT torn down piece by piece (frees, stream and
     // event destruction, a device synchronisation: tenths of a second to seconds on a busy box); the thin mains leave
@@ -1048,7 +1060,7 @@ int as_error_estimation_main(int argc, char** argv) {
         return 0;
     }
     GpuContext gpu;  // CUDA start-up runs beside the panel / reference-base work below (no CPU fallback: see as_create)
-    if (with_germlines) gpu.start();
+    if (with_germlines) gpu.start(aseq_dir_records(germline_dir));
     srand((unsigned)time(nullptr));
     const int seed = rand() % 1000;  // EE:581-584
     const std::string stem = interm + "/" + std::to_string(seed);
@@ -1118,7 +1130,7 @@ int as_error_estimation_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << stem << "_germline_count_list_original.txt" << RESET
               << " stored with success. It contains " << GREEN << files.size() << RESET << " samples" << std::endl;
     const int S = (int)files.size();
-    if (!gpu.widen((double)S * (double)P)) {  // without a B200 there is nothing this program can do (no CPU fallback)
+    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
         std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
         return 1;
     }
@@ -1280,7 +1292,7 @@ int as_variant_calling_main(int argc, char** argv) {
     }
 
     GpuContext gpu;  // CUDA start-up runs beside the parse of the noise table (no CPU fallback: see as_create)
-    gpu.start();
+    gpu.start(aseq_dir_records(tumour_dir));
     PhaseTimer timer;
     // ---- noise table (storeInputFile, VC:430-576): one slot per row; also re-emits the dummy VCF (VC:564)
     Panel panel;
@@ -1401,7 +1413,7 @@ int as_variant_calling_main(int argc, char** argv) {
     std::cout << "\nRunning function storeList: " << GREEN << list_name << RESET << " stored with success. It contains " << GREEN
               << files.size() << RESET << " samples" << std::endl;
     const int T = (int)files.size();
-    if (!gpu.widen((double)T * (double)P)) {  // without a B200 there is nothing this program can do (no CPU fallback)
+    if (!gpu.wait()) {  // without a B200 there is nothing this program can do (no CPU fallback)
         std::cout << RED << "Error: as_create: " << gpu.error << RESET << std::endl;
         return 1;
     }

@@ -538,7 +538,12 @@ def run_ours(args):
     if not args.no_e2e_text:
         barrier()
         if rank == 0:
-            e2e_text = run_e2e_text(world)
+            try:
+                e2e_text = run_e2e_text(world)
+            except Exception as exc:   # a failure here (a full /tmp, a parity break) is reported on the line, loudly, not by losing the line
+                import traceback
+                traceback.print_exc()
+                e2e_text = {"error": f"{type(exc).__name__}: {exc}"}
         barrier()
 
     result = None

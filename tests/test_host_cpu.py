@@ -185,3 +185,50 @@ def test_shard_bounds_keep_twin_groups_whole():
             assert not np.any((head[cut:] < cut)), cut          # no member at or after the cut belongs to a group that starts before it
         assert [(b[i], b[i + 1]) for i in range(n)] == shard_ranges(P, n, head, nxt)
     assert shard_bounds(1000, 4) == [0, 128, 384, 640, 1000] or shard_bounds(1000, 4)[-1] == 1000
+
+
+def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
+    """The ASEQ loader (as_host.cpp parse_aseq) has a fast row scanner for the usual row shape and a general parser for
+    everything sscanf("%s %s %s %s %s %s %d ...") of the reference accepts (EE:1149, VC:752).  The same counts written with
+    tabs, with CRLF line ends, with runs of blanks instead of tabs, with blank lines in between and with the rows in reverse
+    order must give the same packed tensor (scripts/parse_bench.cpp: the loader alone, no GPU; checksum over all words)."""
+    import json
+    import shutil
+    import numpy as np
+    from tests import synth
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "parse_bench"
+    lib_dir = ROOT / "amplisolve_b200" / "lib"
+    from amplisolve_b200 import lib
+    lib()
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I", str(ROOT / "include"), str(ROOT / "scripts" / "parse_bench.cpp"),
+                        f"-L{lib_dir}", "-lamplisolve_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    bed, slots, pos_id, U = synth.make_panel(30, seed=9)
+    P = len(slots)
+    counts, _ = synth.make_counts(5, P, depth=3000, seed=9, pos_id=pos_id)
+    counts[1, 0, 3, :] = [70000, 1, 0, 2]            # escapes the packed format
+    (tmp_path / "panel.bed").write_text("".join(f"{c}\t{s}\t{e}\tA{i}\n" for i, (c, s, e) in enumerate(bed)))
+
+    def variant(name, transform):
+        d = tmp_path / name
+        d.mkdir()
+        for i in range(counts.shape[0]):
+            aseq_io.write_aseq(d / f"S{i}.PILEUP.ASEQ", slots, counts[i])
+            text = (d / f"S{i}.PILEUP.ASEQ").read_text()
+            head, rows = text.split("\n", 1)
+            (d / f"S{i}.PILEUP.ASEQ").write_text(head + "\n" + transform(rows))
+        out = subprocess.run([str(exe), str(tmp_path / "panel.bed"), str(d), "1"], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        res = json.loads(out.stdout)
+        return res["checksum"], res["rows"], res["escaped"], res["outside"]
+
+    base = variant("tabs", lambda t: t)
+    assert base[1] == int((counts[:, 0, :, 0] != 0xFFFFFFFF).sum()) and base[2] >= 1 and base[3] == 0
+    assert variant("crlf", lambda t: t.replace("\n", "\r\n")) == base
+    assert variant("blanks", lambda t: t.replace("\t", "   ")) == base
+    assert variant("blank_lines", lambda t: t.replace("\n", "\n\n")) == base
+    assert variant("reversed", lambda t: "\n".join(t.strip("\n").split("\n")[::-1]) + "\n") == base
+    assert variant("no_final_newline", lambda t: t.rstrip("\n")) == base

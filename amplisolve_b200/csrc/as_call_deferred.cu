@@ -26,6 +26,8 @@
 // with capacities of a few entries).
 #include "as_kernels.h"
 
+#include <cstdlib>
+
 #include "as_call.cuh"
 #include "as_pipeline.cuh"
 
@@ -364,15 +366,24 @@ cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, 
     Survivor* surv0 = (Survivor*)((char*)d_scratch + 4096 + (((size_t)cap_cand * sizeof(StagedCand) + 255) & ~(size_t)255));
     cudaError_t e = cudaMemsetAsync(counters, 0, 128 * AS_DEFER_MAX_CHUNKS, st);
     if (e != cudaSuccess) return e;
-    constexpr int K = 3, STAGES = 2;
-    static bool configured[AS_MAX_DEVICES] = {};
-    const int smem = StageRing<K, STAGES>::kStageBytes * STAGES;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev]) {
-        e = cudaFuncSetAttribute(call_scan_kernel<K, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev] = true;
+    // ring geometry of the scan kernel (samples per stage, stages); five tables on the c3 shard: 0 = (3,2) 5.65 ms, 1 = (4,2)
+    // 5.62, 2 = (3,3) 5.59 (default), 3 = (2,3) 5.62.  AS_SCAN_GEOM selects another one (experiments).
+    static int geom = -1;
+    if (geom < 0) { const char* g = getenv("AS_SCAN_GEOM"); geom = g ? (atoi(g) & 3) : 2; }
+    int smem = 0;
+    {
+        static bool configured[AS_MAX_DEVICES][4] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const void* fn = geom == 1 ? (const void*)call_scan_kernel<4, 2> : geom == 2 ? (const void*)call_scan_kernel<3, 3>
+                         : geom == 3 ? (const void*)call_scan_kernel<2, 3> : (const void*)call_scan_kernel<3, 2>;
+        smem = geom == 1 ? StageRing<4, 2>::kStageBytes * 2 : geom == 2 ? StageRing<3, 3>::kStageBytes * 3
+               : geom == 3 ? StageRing<2, 3>::kStageBytes * 3 : StageRing<3, 2>::kStageBytes * 2;
+        if (dev < 0 || dev >= AS_MAX_DEVICES || !configured[dev][geom & 3]) {
+            e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            if (dev >= 0 && dev < AS_MAX_DEVICES) configured[dev][geom & 3] = true;
+        }
     }
     const int chunk = as_call_chunk(T, p1 - p0);
     const unsigned gy = (unsigned)((T + chunk - 1) / chunk);
@@ -387,8 +398,9 @@ cudaError_t as_launch_call_deferred(const uint32_t* d_counts, int T, int64_t P, 
         L.cand = cand0 + (size_t)ch * L.cap_cand;
         L.surv = surv0 + (size_t)ch * 8 * L.cap_surv;
         dim3 grid((unsigned)(t_hi - t_lo), gy);
-        call_scan_kernel<K, STAGES><<<grid, AS_CTA_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(d_counts), T, P, q0, q1, chunk,
-                                                                          cut, L, sink);
+#define AS_SCAN_LAUNCH(KK, SS) call_scan_kernel<KK, SS><<<grid, AS_CTA_THREADS, smem, st>>>(reinterpret_cast<const uint4*>(d_counts), T, P, q0, q1, chunk, cut, L, sink)
+        if (geom == 1) AS_SCAN_LAUNCH(4, 2); else if (geom == 2) AS_SCAN_LAUNCH(3, 3); else if (geom == 3) AS_SCAN_LAUNCH(2, 3); else AS_SCAN_LAUNCH(3, 2);
+#undef AS_SCAN_LAUNCH
         cudaStream_t post = st;
         if (n_chunks > 1) {
             if ((e = cudaEventRecord(ev[ch], st)) != cudaSuccess) return e;

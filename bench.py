@@ -739,6 +739,10 @@ def run_e2e_text(world):
                                      "process (cuda_context_wait in the phases), the arithmetic and the text handling do not"}
             rows = info["normal_rows"] + info["tumour_rows"]
             leg["ours_rows_per_s"] = rows / leg["ours_wall_s"]
+            # what the two processes waited for the CUDA driver (cuInit + primary context, started on a thread at program
+            # entry and overlapped with the parse): profiles/r02_cuda_startup.txt times the same for an empty CUDA process
+            leg["ours_cuda_startup_wait_s"] = sum(ours[k].get("cuda_context_wait", 0.0) for k in ("ee_phases_s", "vc_phases_s"))
+            leg["ours_wall_without_cuda_startup_s"] = leg["ours_wall_s"] - leg["ours_cuda_startup_wait_s"]
             if world > 1:
                 leg["identical_to_one_gpu"] = all(v for k, v in cli.compare(td, "o", "v", "w", "wv").items() if k.endswith("identical"))
                 if not leg["identical_to_one_gpu"]:

@@ -31,7 +31,7 @@ EXPORTS = [
     "as_noise_estimate_host16", "as_thresholds_caller_view_dev", "as_call_variants_dev", "as_call_variants_host",
     "as_call_variants_host16", "as_sort_calls_dev", "as_call_variants_sweep_dev", "as_noise_estimate_sweep_dev", "as_pack_counts", "as_noise_estimate_host_packed", "as_call_variants_host_packed", "as_poisson_test_host",
     "as_kf_gammaq_host", "as_synth_counts_dev", "as_synth_twin_links_dev", "as_hash_iteration_order", "as_fisher_test", "as_fisher_tests_host", "as_error_estimation_main",
-    "as_variant_calling_main",
+    "as_variant_calling_main", "as_pileup_begin", "as_pileup_add_host", "as_pileup_end_host", "as_compute_counts_main",
 ]
 
 
@@ -171,7 +171,10 @@ def lib():
     L.as_fisher_tests_host.argtypes = [vp, vp, i64, vp]
     L.as_fisher_test.restype = C.c_double
     L.as_fisher_test.argtypes = [i32, i32, i32, i32]
-    for name in ("as_error_estimation_main", "as_variant_calling_main"):
+    L.as_pileup_begin.argtypes = [vp, vp, i32, vp, i64]
+    L.as_pileup_add_host.argtypes = [vp, vp, i64, vp, i64, vp, i32, i32, i32, C.c_uint32]
+    L.as_pileup_end_host.argtypes = [vp, vp, vp]
+    for name in ("as_error_estimation_main", "as_variant_calling_main", "as_compute_counts_main"):
         if hasattr(L, name):
             getattr(L, name).argtypes = [C.c_int, C.POINTER(C.c_char_p)]
     _lib = L
@@ -460,6 +463,26 @@ class Context:
         """calls / sorted_out: torch uint8 CUDA tensors of >= n*48 bytes; the first n calls of `calls` get slot_offset added
         and land in sorted_out in the reference's row order (sample, slot, alt)."""
         _check(lib().as_sort_calls_dev(self._h, _dp(calls), int(n), int(slot_offset), _dp(sorted_out), self._stream(stream)))
+
+    def pileup(self, pieces, ref_contig, contig_first, slot_pos, mbq=20, mrq=20, skip_flags=0x704):
+        """BAM records -> counts uint32 [2 strands][P][4 bases] of one sample (as_pileup_*).  pieces: iterable of
+        (records uint8 array, rec_off int64 array) of the uncompressed record stream; ref_contig[refID] = panel contig or -1;
+        the panel as sorted unique 0-based positions slot_pos[contig_first[c]:contig_first[c+1]].  Returns (counts, (reads
+        used, bases counted))."""
+        first = np.ascontiguousarray(contig_first, np.int64)
+        pos = np.ascontiguousarray(slot_pos, np.int32)
+        refc = np.ascontiguousarray(ref_contig, np.int32)
+        P = len(pos)
+        _check(lib().as_pileup_begin(self._h, first.ctypes.data, len(first) - 1, pos.ctypes.data, P))
+        for rec, off in pieces:
+            rec = np.ascontiguousarray(rec, np.uint8)
+            off = np.ascontiguousarray(off, np.int64)
+            _check(lib().as_pileup_add_host(self._h, rec.ctypes.data, len(rec), off.ctypes.data, len(off), refc.ctypes.data, len(refc),
+                                            int(mbq), int(mrq), int(skip_flags)))
+        counts = np.zeros((2, P, 4), np.uint32)
+        stats = np.zeros(2, np.uint64)
+        _check(lib().as_pileup_end_host(self._h, counts.ctypes.data, stats.ctypes.data))
+        return counts, (int(stats[0]), int(stats[1]))
 
     def synth_counts_dev(self, n_samples, P, *, seed, mean_depth, somatic_rate=0.0, sample_offset=0, slot_offset=0,
                          depth_sigma=0.5, germline_rate=1e-3, vaf=(0.01, 0.2), absent_rate=0.0, want_ref=True,

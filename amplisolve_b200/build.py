@@ -19,8 +19,8 @@ CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libamplisolve_b200.so"
 BIN = PKG / "bin"
 OBJ = PKG / "lib" / "obj"
-CU_SOURCES = ["as_kernels.cu", "as_noise_pattern.cu", "as_call_deferred.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu"]
-CXX_SOURCES = ["as_host.cpp"]
+CU_SOURCES = ["as_kernels.cu", "as_noise_pattern.cu", "as_call_deferred.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu", "as_pileup.cu"]
+CXX_SOURCES = ["as_host.cpp", "as_bam.cpp"]  # as_bam.cpp inflates BGZF blocks with zlib (-lz)
 HEADERS = ["as_device.cuh", "as_noise.cuh", "as_pipeline.cuh", "as_call.cuh", "as_kernels.h", "as_wire.h",
            "../../include/amplisolve_b200.h"]
 # -cudart shared: the CUDA runtime is NOT linked into the product library (a static runtime would carry every runtime entry
@@ -82,7 +82,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                     raise RuntimeError(f"nvcc failed compiling {src.name}")
     objs = [OBJ / (src.stem + ".o") for src in srcs]
     if force or jobs or _stale(LIB, objs):
-        cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, objs)]
+        cmd = [nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, objs), "-lz"]
         for d in CUDA_LIB_DIRS:
             cmd += ["-Xlinker", f"-rpath={d}"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -93,7 +93,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     mains = CSRC / "as_main.cpp"
     if mains.exists():
         BIN.mkdir(exist_ok=True)
-        for prog, macro in (("AmpliSolveErrorEstimation", "AS_MAIN_EE"), ("AmpliSolveVariantCalling", "AS_MAIN_VC")):
+        for prog, macro in (("AmpliSolveErrorEstimation", "AS_MAIN_EE"), ("AmpliSolveVariantCalling", "AS_MAIN_VC"),
+                            ("computeCounts", "AS_MAIN_CC")):
             out = BIN / prog
             if force or _stale(out, [mains, LIB]):
                 cmd = ["g++", "-O2", "-std=c++17", f"-D{macro}", "-o", str(out), str(mains), "-I", str(ROOT / "include"),

@@ -105,6 +105,9 @@ struct as_ctx {
     DevBuf lgtab;                                                              // lgamma(i + 1), i < lg_n (as_fisher_tests_host)
     int64_t lg_n = 0;
     PinnedGrow h_links, h_small;                                              // _host pipelines, host side
+    DevBuf pile_first, pile_pos, pile_counts, pile_rec, pile_off, pile_ref, pile_stats;  // as_pileup_*
+    int64_t pile_P = -1;
+    int32_t pile_contigs = 0;
 };
 
 extern "C" {
@@ -211,6 +214,8 @@ void as_destroy(as_ctx* c) {
     cudaDeviceSynchronize();
     c->heads.release(); c->nheads.release(); c->misc.release(); c->calls.release(); c->sortbuf.release();
     c->h_links.release(); c->h_small.release(); c->lgtab.release(); c->defer.release();
+    c->pile_first.release(); c->pile_pos.release(); c->pile_counts.release(); c->pile_rec.release(); c->pile_off.release();
+    c->pile_ref.release(); c->pile_stats.release();
     for (int i = 0; i < 2; ++i) {
         c->tile[i].release(); c->tile16[i].release(); c->wide[i].release(); c->out[i].release(); c->aux[i].release();
         if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]);
@@ -1049,6 +1054,74 @@ int as_sort_calls_dev(as_ctx* c, as_call* d_calls, int64_t n, int32_t slot_offse
     }
     CU(as_launch_sort_calls(d_calls, n, d_sorted, c->sortbuf.p, scratch, st));
     c->launches += 3;
+    return AS_OK;
+}
+
+// ---- pileup: BAM records -> counts[2][P][4] of one sample -----------------------------
+int as_pileup_begin(as_ctx* c, const int64_t* contig_first, int32_t n_contig, const int32_t* slot_pos, int64_t P) {
+    if (!c || !contig_first || !slot_pos || n_contig < 1 || P < 1) return fail(AS_EINVAL, "bad argument");
+    if (contig_first[0] != 0 || contig_first[n_contig] != P) return fail(AS_EINVAL, "contig_first must run from 0 to P");
+    for (int32_t k = 0; k < n_contig; ++k) {
+        if (contig_first[k + 1] < contig_first[k]) return fail(AS_EINVAL, "contig_first must not decrease");
+        for (int64_t j = contig_first[k] + 1; j < contig_first[k + 1]; ++j)
+            if (slot_pos[j] <= slot_pos[j - 1]) return fail(AS_EINVAL, "positions of contig %d are not sorted and unique", k);
+    }
+    if (c->subs.size() > 1) c = c->subs[0];  // one sample, one GPU
+    CU(cudaSetDevice(c->device));
+    CU(c->pile_first.need(sizeof(int64_t) * (size_t)(n_contig + 1)));
+    CU(c->pile_pos.need(sizeof(int32_t) * (size_t)P));
+    CU(c->pile_counts.need(sizeof(uint32_t) * 8 * (size_t)P));
+    CU(c->pile_stats.need(16));
+    cudaStream_t st = c->exec_stream;
+    CU(cudaMemcpyAsync(c->pile_first.p, contig_first, sizeof(int64_t) * (size_t)(n_contig + 1), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->pile_pos.p, slot_pos, sizeof(int32_t) * (size_t)P, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync(c->pile_counts.p, 0, sizeof(uint32_t) * 8 * (size_t)P, st));
+    CU(cudaMemsetAsync(c->pile_stats.p, 0, 16, st));
+    CU(cudaStreamSynchronize(st));  // the host arrays may go away
+    c->pile_P = P;
+    c->pile_contigs = n_contig;
+    return AS_OK;
+}
+
+int as_pileup_add_host(as_ctx* c, const uint8_t* records, int64_t n_bytes, const int64_t* rec_off, int64_t n_rec,
+                       const int32_t* ref_contig, int32_t n_ref, int32_t mbq, int32_t mrq, uint32_t skip_flags) {
+    if (!c || n_bytes < 0 || n_rec < 0 || n_ref < 1 || !ref_contig) return fail(AS_EINVAL, "bad argument");
+    if (c->subs.size() > 1) c = c->subs[0];
+    if (c->pile_P < 1) return fail(AS_EINVAL, "as_pileup_begin has not been called");
+    if (n_rec == 0) return AS_OK;
+    if (!records || !rec_off) return fail(AS_EINVAL, "records / rec_off is NULL");
+    for (int32_t k = 0; k < n_ref; ++k)
+        if (ref_contig[k] < -1 || ref_contig[k] >= c->pile_contigs) return fail(AS_EINVAL, "ref_contig[%d] names no panel contig", k);
+    for (int64_t i = 0; i < n_rec; ++i)
+        if (rec_off[i] < 0 || rec_off[i] + 36 > n_bytes) return fail(AS_EINVAL, "record %lld starts outside the buffer", (long long)i);
+    CU(cudaSetDevice(c->device));
+    CU(c->pile_rec.need((size_t)n_bytes + 16));
+    CU(c->pile_off.need(sizeof(int64_t) * (size_t)n_rec));
+    CU(c->pile_ref.need(sizeof(int32_t) * (size_t)n_ref));
+    cudaStream_t st = c->exec_stream;
+    CU(cudaMemcpyAsync(c->pile_rec.p, records, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->pile_off.p, rec_off, sizeof(int64_t) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(c->pile_ref.p, ref_contig, sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    CU(as_launch_pileup((const uint8_t*)c->pile_rec.p, (const int64_t*)c->pile_off.p, n_rec, n_bytes, (const int32_t*)c->pile_ref.p, n_ref,
+                        (const int64_t*)c->pile_first.p, (const int32_t*)c->pile_pos.p, c->pile_P, mbq, mrq, skip_flags,
+                        (uint32_t*)c->pile_counts.p, (unsigned long long*)c->pile_stats.p, st));
+    c->launches += 1;
+    CU(cudaStreamSynchronize(st));  // the caller reuses its buffers for the next piece
+    return AS_OK;
+}
+
+int as_pileup_end_host(as_ctx* c, uint32_t* counts, uint64_t* stats_out) {
+    if (!c || !counts) return fail(AS_EINVAL, "bad argument");
+    if (c->subs.size() > 1) c = c->subs[0];
+    if (c->pile_P < 1) return fail(AS_EINVAL, "as_pileup_begin has not been called");
+    CU(cudaSetDevice(c->device));
+    cudaStream_t st = c->exec_stream;
+    CU(cudaMemcpyAsync(counts, c->pile_counts.p, sizeof(uint32_t) * 8 * (size_t)c->pile_P, cudaMemcpyDeviceToHost, st));
+    unsigned long long h[2] = {0ull, 0ull};
+    CU(cudaMemcpyAsync(h, c->pile_stats.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (stats_out) { stats_out[0] = h[0]; stats_out[1] = h[1]; }
+    c->pile_P = -1;
     return AS_OK;
 }
 

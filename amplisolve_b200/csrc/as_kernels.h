@@ -68,6 +68,11 @@ cudaError_t as_launch_fisher(const int32_t* d_tables, int64_t n, const double* d
 cudaError_t as_launch_call_sweep(int variant, const uint32_t* d_counts, int T, int64_t P, int64_t p0, int64_t p1,
                                  const uint8_t* d_ref, const float* d_thr_views, int n_c, int64_t c_stride, uint32_t cut,
                                  as_call* d_calls, int64_t cap, unsigned long long* d_n_calls, cudaStream_t st);
+// as_pileup.cu: BAM records -> counts[2][P][4] of one sample; stats[0] reads used, stats[1] bases counted
+cudaError_t as_launch_pileup(const uint8_t* d_rec, const int64_t* d_rec_off, int64_t n_rec, int64_t n_bytes,
+                             const int32_t* d_ref_contig, int32_t n_ref, const int64_t* d_contig_first,
+                             const int32_t* d_slot_pos, int64_t P, int32_t mbq, int32_t mrq, uint32_t skip_flags,
+                             uint32_t* d_counts, unsigned long long* d_stats, cudaStream_t st);
 cudaError_t as_launch_poisson_test(const int32_t* k, const int32_t* rd, const float* err, int64_t n, double* p,
                                    double* q, cudaStream_t st);
 cudaError_t as_launch_gammaq(const double* s, const double* z, int64_t n, double* out, cudaStream_t st);

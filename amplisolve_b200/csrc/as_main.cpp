@@ -1,5 +1,6 @@
-// The two drop-in executables: same names and argv grammar as the reference's programs
-// (README.md:60-61; AmpliSolveErrorEstimation.cpp:241, AmpliSolveVariantCalling.cpp:199).
+// The drop-in executables: same names and argv grammar as the reference's programs
+// (README.md:60-61; AmpliSolveErrorEstimation.cpp:241, AmpliSolveVariantCalling.cpp:199) and as its pre-processing
+// binary computeCounts / ASEQ PILEUP mode (Execution_examples.md:27).
 // Everything happens in libamplisolve_b200.so behind the C ABI.
 #include <unistd.h>
 
@@ -13,8 +14,10 @@ int main(int argc, char** argv) {
     const int rc = as_error_estimation_main(argc, argv);
 #elif defined(AS_MAIN_VC)
     const int rc = as_variant_calling_main(argc, argv);
+#elif defined(AS_MAIN_CC)
+    const int rc = as_compute_counts_main(argc, argv);
 #else
-#error "define AS_MAIN_EE or AS_MAIN_VC"
+#error "define AS_MAIN_EE, AS_MAIN_VC or AS_MAIN_CC"
 #endif
     // every output file is closed and the context destroyed by now; leave without the CUDA runtime's exit handlers
     // (a few tenths of a second of a program that otherwise runs for two)

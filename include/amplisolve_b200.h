@@ -263,6 +263,24 @@ int as_synth_counts_dev(as_ctx* ctx, uint32_t* d_counts, int32_t n_samples, int6
 int as_synth_twin_links_dev(as_ctx* ctx, int64_t P, const as_synth_params* prm, int32_t* d_twin_next,
                             int32_t* d_twin_head, void* stream);
 
+/* ---- pileup: BAM records -> the count tensor of one sample ---------------------
+ * Replaces the pre-processing step of the reference, `./ASEQ vcf= bam= mbq= mrq= mdc= out=` alias computeCounts
+ * (Execution_examples.md:16-54; the reference ships it as a binary only, so this is a new design with the conventions of
+ * a samtools-style pileup -- amplisolve_b200/csrc/as_pileup.cu states them -- and its parity with that binary is unpinned).
+ * The panel is given as the sorted, unique, 0-based positions of each contig: slot_pos[contig_first[c] .. contig_first[c+1]).
+ * as_pileup_begin   uploads the panel and zeroes the device counts [2 strands][P][4 bases];
+ * as_pileup_add_host adds the reads of a piece of the UNCOMPRESSED record stream of a BAM file (header stripped):
+ *                   records[0..n_bytes), rec_off[i] = byte offset of record i (its block_size field), ref_contig[refID] =
+ *                   panel contig of a BAM reference sequence or -1.  A read counts when mapq >= mrq and (flag & skip_flags)
+ *                   == 0; a base when it is aligned (M, =, X), A/C/G/T and of quality >= mbq.  Any number of pieces.
+ * as_pileup_end_host downloads counts (host, 2 * P * 4 uint32: forward strand first) and the number of reads / bases
+ *                   used (stats_out[2], may be NULL).
+ * The device buffer keeps the layout of one sample of the count tensor, [strand][slot][base]. */
+int as_pileup_begin(as_ctx* ctx, const int64_t* contig_first, int32_t n_contig, const int32_t* slot_pos, int64_t P);
+int as_pileup_add_host(as_ctx* ctx, const uint8_t* records, int64_t n_bytes, const int64_t* rec_off, int64_t n_rec,
+                       const int32_t* ref_contig, int32_t n_ref, int32_t mbq, int32_t mrq, uint32_t skip_flags);
+int as_pileup_end_host(as_ctx* ctx, uint32_t* counts, uint64_t* stats_out);
+
 /* ---- host side of the two programs (text formats; amplisolve_b200/csrc/as_host.cpp) ---------- */
 /* Iteration order of a libstdc++ std::unordered_map<std::string,std::string> after inserting keys
  * in the given sequence: the order in which the reference walks its file lists (EE:1081, VC:672).
@@ -288,6 +306,10 @@ int as_fisher_tests_host(as_ctx* ctx, const int32_t* tables, int64_t n, double* 
  * the return value; like the reference, usage errors print the usage text and return 0. */
 int as_error_estimation_main(int argc, char** argv);
 int as_variant_calling_main(int argc, char** argv);
+/* computeCounts / ASEQ PILEUP mode (Execution_examples.md:27): [vcf=positions] [bam=file.bam] [threads=n] [mbq=n] [mrq=n]
+ * [mdc=n] [out=dir] -> <out>/<bam name>.PILEUP.ASEQ, the 15-column text both programs above read.  BGZF blocks are
+ * inflated on `threads` host threads, the pileup runs on the GPU (as_pileup_*). */
+int as_compute_counts_main(int argc, char** argv);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,30 @@ def test_noise_mode_without_gpu_fails_loudly(tmp_path):
     assert not list((tmp_path / "o").glob("positionSpecificNoise_0*.txt"))
 
 
+def test_compute_counts_reads_the_container_and_fails_loudly_without_gpu(tmp_path):
+    """computeCounts: usage and container errors need no GPU; a valid BAM without a GPU is an error that
+    says so -- there is no CPU pileup behind the program."""
+    import torch
+    from oracle import pileup_oracle as po
+    prog = str(BIN / "computeCounts")
+    r = subprocess.run([prog], capture_output=True, text=True)
+    assert r.returncode == 0 and "Usage: computeCounts" in r.stdout
+    (tmp_path / "positions.txt").write_text("chr1\t1000\t.\t.\t.\n")
+    (tmp_path / "x.bam").write_bytes(b"plain text, not BGZF" * 4)
+    r = subprocess.run([prog, "vcf=positions.txt", "bam=x.bam", "out=o"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "not a BGZF" in r.stdout
+    read = dict(ref_id=0, pos=990, mapq=60, flag=0, cigar=[("M", 30)], seq="ACGT" * 7 + "AC", qual=bytes([30]) * 30)
+    po.write_bam(tmp_path / "ok.bam", [("chr1", 5000)], [read] * 25)
+    r = subprocess.run([prog, "vcf=positions.txt", "bam=ok.bam", "out=o"], cwd=tmp_path, capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0
+        rows = (tmp_path / "o" / "ok.PILEUP.ASEQ").read_text().splitlines()
+        assert rows[1].split("\t")[:2] == ["chr1", "1000"] and rows[1].split("\t")[10] == "25"
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout
+        assert not (tmp_path / "o" / "ok.PILEUP.ASEQ").exists()
+
+
 def test_shard_bounds_keep_twin_groups_whole():
     """as_shard_bounds (what as_create_multi contexts split a panel by): contiguous, covering, and no twin group straddles a
     boundary -- also with a group that spans almost the whole panel; equal to amplisolve_b200.shard.shard_ranges."""

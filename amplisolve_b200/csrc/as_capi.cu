@@ -108,6 +108,7 @@ struct as_ctx {
     DevBuf pile_first, pile_pos, pile_counts, pile_rec, pile_off, pile_ref, pile_stats;  // as_pileup_*
     int64_t pile_P = -1;
     int32_t pile_contigs = 0;
+    double pile_kernel_ms = 0, pile_h2d_ms = 0;  // AS_TIMING only
 };
 
 extern "C" {
@@ -1099,14 +1100,30 @@ int as_pileup_add_host(as_ctx* c, const uint8_t* records, int64_t n_bytes, const
     CU(c->pile_off.need(sizeof(int64_t) * (size_t)n_rec));
     CU(c->pile_ref.need(sizeof(int32_t) * (size_t)n_ref));
     cudaStream_t st = c->exec_stream;
+    const bool timing = getenv("AS_TIMING") != nullptr;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) {
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(ev[0], st));
+    }
     CU(cudaMemcpyAsync(c->pile_rec.p, records, (size_t)n_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->pile_off.p, rec_off, sizeof(int64_t) * (size_t)n_rec, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(c->pile_ref.p, ref_contig, sizeof(int32_t) * (size_t)n_ref, cudaMemcpyHostToDevice, st));
+    if (timing) CU(cudaEventRecord(ev[1], st));
     CU(as_launch_pileup((const uint8_t*)c->pile_rec.p, (const int64_t*)c->pile_off.p, n_rec, n_bytes, (const int32_t*)c->pile_ref.p, n_ref,
                         (const int64_t*)c->pile_first.p, (const int32_t*)c->pile_pos.p, c->pile_P, mbq, mrq, skip_flags,
                         (uint32_t*)c->pile_counts.p, (unsigned long long*)c->pile_stats.p, st));
     c->launches += 1;
+    if (timing) CU(cudaEventRecord(ev[2], st));
     CU(cudaStreamSynchronize(st));  // the caller reuses its buffers for the next piece
+    if (timing) {
+        float a = 0, b = 0;
+        CU(cudaEventElapsedTime(&a, ev[0], ev[1]));
+        CU(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        c->pile_h2d_ms += a;
+        c->pile_kernel_ms += b;
+        for (auto& e : ev) cudaEventDestroy(e);
+    }
     return AS_OK;
 }
 
@@ -1121,6 +1138,10 @@ int as_pileup_end_host(as_ctx* c, uint32_t* counts, uint64_t* stats_out) {
     CU(cudaMemcpyAsync(h, c->pile_stats.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (stats_out) { stats_out[0] = h[0]; stats_out[1] = h[1]; }
+    if (getenv("AS_TIMING")) {
+        fprintf(stderr, "AS_TIMING capi.pileup.h2d %.6f\nAS_TIMING capi.pileup.kernel %.6f\n", 1e-3 * c->pile_h2d_ms, 1e-3 * c->pile_kernel_ms);
+        c->pile_h2d_ms = c->pile_kernel_ms = 0;
+    }
     c->pile_P = -1;
     return AS_OK;
 }

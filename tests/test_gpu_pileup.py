@@ -88,6 +88,18 @@ def test_program_output_equals_the_oracle(ctx, tmp_path, block_bytes, piece_mb, 
     assert "S1.PILEUP.ASEQ" in out
 
 
+def test_several_bams_in_one_run(ctx, tmp_path):
+    """bam=a.bam,b.bam (an extension: one context and one position file for many samples): each file as if run alone"""
+    lines = panel_lines()
+    write_positions(tmp_path, lines)
+    sets = {name: random_reads(2500, seed=k) for k, name in enumerate(("N1", "N2", "T1"))}
+    for name, reads in sets.items():
+        po.write_bam(tmp_path / f"{name}.bam", REFS, reads, block_bytes=4000)
+    run_counts(tmp_path, "N1.bam,N2.bam,T1.bam", ["mdc=3"])
+    for name, reads in sets.items():
+        assert (tmp_path / "aseq" / f"{name}.PILEUP.ASEQ").read_text() == po.render_aseq(lines, po.pileup(REFS, reads), mdc=3)
+
+
 def test_empty_and_headers_only(ctx, tmp_path):
     lines = panel_lines()
     write_positions(tmp_path, lines)

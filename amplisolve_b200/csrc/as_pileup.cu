@@ -13,8 +13,8 @@
 //
 // Input: the UNCOMPRESSED record stream of a BAM file (what BGZF inflates to, header stripped) and the byte offset of
 // every record; the panel as sorted 0-based positions per contig.  One warp per read: the CIGAR is walked by the whole
-// warp (uniform), the bases of an aligned block are spread over the lanes, the slot of a block's first base is found by
-// binary search and the following slots by stepping (panel positions are runs of consecutive positions: amplicons).
+// warp (uniform); for an aligned block the range of panel slots under it is found by two binary searches and the lanes
+// walk those slots (not the read's bases: a base outside the panel costs nothing).
 #include "as_kernels.h"
 
 #include <cuda_runtime.h>
@@ -27,10 +27,10 @@ __device__ __forceinline__ uint32_t rd_u32(const uint8_t* p) {  // BAM records a
 }
 __device__ __forceinline__ uint32_t rd_u16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
-// first index in [lo, hi) with pos[index] >= key
-__device__ __forceinline__ int64_t lower_bound_pos(const int32_t* __restrict__ pos, int64_t lo, int64_t hi, int32_t key) {
+// first index in [lo, hi) with pos[index] >= key (32-bit indices: pos is the slice of one contig)
+__device__ __forceinline__ uint32_t lower_bound_pos(const int32_t* __restrict__ pos, uint32_t lo, uint32_t hi, int32_t key) {
     while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
+        const uint32_t mid = (lo + hi) >> 1;
         if (pos[mid] < key) lo = mid + 1; else hi = mid;
     }
     return lo;
@@ -64,9 +64,11 @@ pileup_kernel(const uint8_t* __restrict__ rec, const int64_t* __restrict__ rec_o
         const uint8_t* seq = cig + 4 * (size_t)n_cig;
         const uint8_t* qual = seq + ((l_seq + 1) >> 1);
         if ((int64_t)(36 + l_name + 4 * (size_t)n_cig + ((l_seq + 1) >> 1) + l_seq) > (int64_t)block_size + 4) continue;
-        const int64_t c0 = contig_first[contig], c1 = contig_first[contig + 1];
-        if (c0 == c1) continue;
-        const int64_t strand = (flag & 0x10u) ? 1 : 0;
+        const int64_t c0 = contig_first[contig];
+        const uint32_t n_c = (uint32_t)(contig_first[contig + 1] - c0);  // slots of this contig
+        if (n_c == 0u) continue;
+        const int32_t* __restrict__ cpos = slot_pos + c0;
+        uint32_t* __restrict__ ccounts = counts + ((flag & 0x10u) ? P : 0) * 4 + c0 * 4;  // this strand, this contig
         uint32_t q = 0;      // query offset
         int32_t g = pos;     // reference offset (0-based)
         bool any = false;
@@ -75,22 +77,18 @@ pileup_kernel(const uint8_t* __restrict__ rec, const int64_t* __restrict__ rec_o
             const uint32_t op = v & 15u, len = v >> 4;
             if (op == 0u || op == 7u || op == 8u) {  // M, =, X: aligned bases
                 if (q + len > l_seq) break;          // malformed
-                if (g <= slot_pos[c1 - 1] && g + (int32_t)len > slot_pos[c0]) {
-                    const int64_t j0 = lower_bound_pos(slot_pos, c0, c1, g);
-                    for (uint32_t i = lane; i < len; i += 32) {
-                        const int32_t gp = g + (int32_t)i;
-                        // the panel is made of runs of consecutive positions: try the stepped slot first
-                        int64_t j = j0 + (int64_t)(gp - slot_pos[j0 < c1 ? j0 : c1 - 1]);
-                        if (j0 >= c1 || j < c0 || j >= c1 || slot_pos[j] != gp) {
-                            j = lower_bound_pos(slot_pos, c0, c1, gp);
-                            if (j >= c1 || slot_pos[j] != gp) continue;
-                        }
-                        const uint32_t qi = q + i;
+                if (g <= cpos[n_c - 1] && g + (int32_t)len > cpos[0]) {
+                    // the panel positions under this block are cpos[j_lo, j_hi): two searches per block (the second over
+                    // at most len entries), then the lanes walk those SLOTS -- no lane is spent on a base outside the panel
+                    const uint32_t j_lo = lower_bound_pos(cpos, 0u, n_c, g);
+                    const uint32_t j_end = n_c - j_lo > len ? j_lo + len : n_c;
+                    const uint32_t j_hi = lower_bound_pos(cpos, j_lo, j_end, g + (int32_t)len);
+                    for (uint32_t j = j_lo + lane; j < j_hi; j += 32) {
+                        const uint32_t qi = q + (uint32_t)(cpos[j] - g);
                         if ((int32_t)qual[qi] < mbq) continue;
-                        const uint32_t code = (seq[qi >> 1] >> ((qi & 1u) ? 0 : 4)) & 15u;
-                        const int base = code == 1u ? 0 : code == 2u ? 1 : code == 4u ? 2 : code == 8u ? 3 : -1;
-                        if (base < 0) continue;
-                        atomicAdd(&counts[(strand * P + j) * 4 + base], 1u);
+                        const uint32_t code = (seq[qi >> 1] >> ((qi & 1u) ? 0 : 4)) & 15u;  // 1, 2, 4, 8 = A, C, G, T
+                        if (code == 0u || (code & (code - 1u)) != 0u) continue;               // =, N and the ambiguity codes
+                        atomicAdd(&ccounts[(size_t)j * 4 + (__ffs((int)code) - 1)], 1u);
                         used_bases += 1;
                         any = true;
                     }

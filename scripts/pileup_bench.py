@@ -82,6 +82,11 @@ def run(out_json=None, n_amplicons=330, amp_len=125, depth=5000, threads=None):
         starts, pos, flag, mapq, seq, qual = make_reads(n_amplicons, amp_len, depth, seed=99)
         refs = [("chr1", int(starts[-1]) + 10_000)]
         raw = bam_bytes(refs, pos, flag, mapq, seq, qual)
+        if os.environ.get("PILEUP_SORTED"):  # coordinate-sorted, as aligners + samtools sort deliver it
+            order = np.argsort(pos, kind="stable")
+            pos, flag, mapq, seq, qual = pos[order], flag[order], mapq[order], seq[order], qual[order]
+            raw = bam_bytes(refs, pos, flag, mapq, seq, qual)
+            res["sorted"] = True
         (td / "S.bam").write_bytes(po.bgzf_compress(raw, level=1))
         with open(td / "positions.txt", "w") as f:
             for s in starts:
@@ -97,6 +102,9 @@ def run(out_json=None, n_amplicons=330, amp_len=125, depth=5000, threads=None):
         res["wall_s_runs"] = walls
         res["phases_s"] = {m.group(1): float(m.group(2)) for m in re.finditer(r"AS_TIMING (\S+) ([0-9.]+)", r.stderr)}
         res["stdout"] = r.stdout.strip()
+        if os.environ.get("PILEUP_NCU"):  # one --set full capture of the pileup kernel on this BAM (after the timed runs)
+            subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", "regex:pileup_kernel", "-c", "1",
+                            "-f", "-o", os.environ["PILEUP_NCU"]] + args[:1] + args[1:], cwd=td, capture_output=True, text=True)
         # eight samples in one process (bam=a,b,...: the context is created once)
         for k in range(1, 8):
             os.link(td / "S.bam", td / f"S{k}.bam")

@@ -56,6 +56,7 @@ def parse_args():
                     help="skip the legs at configs[3]'s own dimensions (200 normals x 1000 tumours, sweep as the step) and at configs[4]'s "
                          "(100 k slots x 10,000 samples at 50,000x)")
     ap.add_argument("--no-e2e-text", action="store_true", help="skip the program-against-program leg (text in, text out)")
+    ap.add_argument("--no-pileup-leg", action="store_true", help="skip the computeCounts leg (BAM -> PILEUP.ASEQ, SURVEY 8 f4)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--e2e-format", choices=["packed", "16", "32"], default="packed",
                     help="host layout of the e2e leg: the packed wire format (8 B/record), the 16-bit one (16 B) or uint32 (32 B)")
@@ -546,6 +547,20 @@ def run_ours(args):
                 e2e_text = {"error": f"{type(exc).__name__}: {exc}"}
         barrier()
 
+    pileup_leg = None
+    if not args.no_pileup_leg and world == 1:
+        try:   # computeCounts on one sample of configs[1], checked against a numpy pileup (scripts/pileup_bench.py)
+            import contextlib
+            import io
+            from scripts import pileup_bench
+            with contextlib.redirect_stdout(io.StringIO()):
+                pileup_leg = pileup_bench.run()
+            pileup_leg.pop("stdout", None)
+        except Exception as exc:
+            import traceback
+            traceback.print_exc()
+            pileup_leg = {"error": f"{type(exc).__name__}: {exc}"}
+
     result = None
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -597,6 +612,8 @@ def run_ours(args):
             result["config_legs"] = config_legs
         if e2e_text is not None:
             result["e2e_text"] = e2e_text
+        if pileup_leg is not None:
+            result["pileup"] = pileup_leg
         if e2e is not None:
             result["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -18,3 +18,9 @@ for k, v in d['e2e_text'].items():
     if isinstance(v, dict):
         print(k, 'ours', [round(x, 2) for x in v['ours_wall_s_runs']], 'ref', round(v.get('reference_wall_s', 0), 2), 'x', round(v.get('speedup_wall', 0), 1))
 PY
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/validate_bench_n1.json'))
+p = d.get('pileup', {})
+print('pileup', {k: p.get(k) for k in ('identical_to_numpy_pileup', 'reads', 'error')}, p.get('pileup_kernel', {}).get('ms'), p.get('phases_s', {}).get('inflate_busy'))
+PY

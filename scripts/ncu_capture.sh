@@ -2,7 +2,7 @@
 # the two streaming kernels of the step and of the sweep kernels.  Outputs under gpurun_out/; summarise here with
 # scripts/ncu_summary.py (profiles/README.md lists the files).
 set -e
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-config-legs --no-e2e-text"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-config-legs --no-e2e-text --no-pileup-leg"
 $CMD > gpurun_out/ncu_plain.json 2> gpurun_out/ncu_plain.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 # the caller and the noise kernel of one timed step (3 warm-up steps = 6 matching launches skipped)

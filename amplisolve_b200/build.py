@@ -20,7 +20,7 @@ LIB = PKG / "lib" / "libamplisolve_b200.so"
 BIN = PKG / "bin"
 OBJ = PKG / "lib" / "obj"
 CU_SOURCES = ["as_kernels.cu", "as_noise_pattern.cu", "as_call_deferred.cu", "as_capi.cu", "as_sort.cu", "as_fisher.cu", "as_pileup.cu"]
-CXX_SOURCES = ["as_host.cpp", "as_bam.cpp"]  # as_bam.cpp inflates BGZF blocks with zlib (-lz)
+CXX_SOURCES = ["as_host.cpp", "as_bam.cpp", "as_serve.cpp"]  # as_bam.cpp inflates BGZF blocks with zlib (-lz)
 HEADERS = ["as_device.cuh", "as_noise.cuh", "as_pipeline.cuh", "as_call.cuh", "as_kernels.h", "as_wire.h",
            "../../include/amplisolve_b200.h"]
 # -cudart shared: the CUDA runtime is NOT linked into the product library (a static runtime would carry every runtime entry
@@ -94,7 +94,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if mains.exists():
         BIN.mkdir(exist_ok=True)
         for prog, macro in (("AmpliSolveErrorEstimation", "AS_MAIN_EE"), ("AmpliSolveVariantCalling", "AS_MAIN_VC"),
-                            ("computeCounts", "AS_MAIN_CC")):
+                            ("computeCounts", "AS_MAIN_CC"), ("amplisolve_b200_serve", "AS_MAIN_SERVE")):
             out = BIN / prog
             if force or _stale(out, [mains, LIB]):
                 cmd = ["g++", "-O2", "-std=c++17", f"-D{macro}", "-o", str(out), str(mains), "-I", str(ROOT / "include"),

@@ -219,6 +219,8 @@ extern "C" int as_compute_counts_main(int argc, char** argv) {
     as_ctx* ctx = nullptr;
     int ctx_rc = AS_OK;
     std::string ctx_err;
+    // in the resident service the context goes back when the program returns (declared before the joiner: destroyed after it)
+    struct CtxGuard { as_ctx*& c; ~CtxGuard() { if (c && as_process_is_resident()) as_destroy(c); } } ctx_guard{ctx};
     std::thread starter([&]() {
         ctx_rc = as_create(0, &ctx);
         if (ctx_rc != AS_OK) ctx_err = as_last_error();

@@ -751,7 +751,7 @@ struct GpuContext {
         double threshold = 268435456.0;
         if (const char* env = getenv("AS_WIDEN_RECORDS")) threshold = atof(env);  // tests
         if (devs.empty() && estimated_records < threshold) devs.push_back(0);
-        if (!devs.empty() && getenv("CUDA_VISIBLE_DEVICES") == nullptr) {  // initialise only what is used; ordinals become 0..n-1
+        if (!devs.empty() && getenv("CUDA_VISIBLE_DEVICES") == nullptr && !as_process_is_resident()) {  // initialise only what is used; ordinals become 0..n-1 (the resident service is initialised already)
             std::string list;
             for (size_t i = 0; i < devs.size(); ++i) list += (i ? "," : "") + std::to_string(devs[i]);
             setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
@@ -776,6 +776,7 @@ struct GpuContext {
     // through _exit and the driver reclaims everything at once.  An error path that returns early still joins the thread.
     ~GpuContext() {
         if (starter.joinable()) starter.join();
+        if (ctx && as_process_is_resident()) as_destroy(ctx);  // the service lives on: give the memory back
     }
 };
 

@@ -10,14 +10,22 @@
 #include "amplisolve_b200.h"
 
 int main(int argc, char** argv) {
-#if defined(AS_MAIN_EE)
-    const int rc = as_error_estimation_main(argc, argv);
-#elif defined(AS_MAIN_VC)
-    const int rc = as_variant_calling_main(argc, argv);
-#elif defined(AS_MAIN_CC)
-    const int rc = as_compute_counts_main(argc, argv);
+#if defined(AS_MAIN_SERVE)
+    const int rc = as_serve_main(argc, argv);
 #else
-#error "define AS_MAIN_EE, AS_MAIN_VC or AS_MAIN_CC"
+#if defined(AS_MAIN_EE)
+    const int prog = 0;
+#elif defined(AS_MAIN_VC)
+    const int prog = 1;
+#elif defined(AS_MAIN_CC)
+    const int prog = 2;
+#else
+#error "define AS_MAIN_EE, AS_MAIN_VC, AS_MAIN_CC or AS_MAIN_SERVE"
+#endif
+    int rc = 0;
+    // AS_SERVER=<socket> and a service listening there: the program runs in that process, on its warm CUDA context
+    if (!as_client_run(prog, argc, argv, &rc))
+        rc = prog == 0 ? as_error_estimation_main(argc, argv) : prog == 1 ? as_variant_calling_main(argc, argv) : as_compute_counts_main(argc, argv);
 #endif
     // every output file is closed and the context destroyed by now; leave without the CUDA runtime's exit handlers
     // (a few tenths of a second of a program that otherwise runs for two)

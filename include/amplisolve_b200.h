@@ -311,6 +311,18 @@ int as_variant_calling_main(int argc, char** argv);
  * inflated on `threads` host threads, the pileup runs on the GPU (as_pileup_*). */
 int as_compute_counts_main(int argc, char** argv);
 
+/* ---- resident service (amplisolve_b200/csrc/as_serve.cpp; no counterpart in the reference) -----
+ * A CUDA process pays 0.25 - 5 s for its context before the first kernel; the three programs above do a few tenths of a
+ * second of work on a gene panel.  as_serve_main (`amplisolve_b200_serve socket=<path> [devices=0,1]`) keeps a context
+ * open and runs the programs of clients in its own process; as_client_run is what the thin mains call first: with
+ * AS_SERVER=<path> in the environment and a service listening it ships argv, the working directory, the AS_* environment
+ * and the caller's stdout / stderr descriptors, waits, stores the exit status in *rc_out and returns 1; otherwise it
+ * returns 0 and the caller runs as_*_main itself.  prog: 0 error estimation, 1 variant calling, 2 compute counts.
+ * as_process_is_resident: 1 inside the service (a program's context is then destroyed when it returns). */
+int as_serve_main(int argc, char** argv);
+int as_client_run(int prog, int argc, char** argv, int* rc_out);
+int as_process_is_resident(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -79,9 +79,25 @@ def stage(td, n_amplicons=N_AMPLICONS, n_normals=N_NORMALS, n_tumours=N_TUMOURS,
             "tumour_rows": rows_t, "setup_s": round(time.time() - t0, 1)}
 
 
-def run_ours(td, out_ee="o", out_vc="v", devices=None):
-    """Both programs on the staged inputs.  Returns wall times and AS_TIMING phases."""
+def start_service(sock, devices=None):
+    """amplisolve_b200_serve on a UNIX socket (a resident CUDA context for the programs); returns the process once it listens"""
+    args = [str(BIN / "amplisolve_b200_serve"), f"socket={sock}"]
+    if devices is not None:
+        args.append("devices=" + ",".join(map(str, devices)))
+    srv = subprocess.Popen(args, cwd="/", stderr=subprocess.PIPE, text=True)
+    line = srv.stderr.readline()
+    if "ready" not in line:
+        srv.kill()
+        raise RuntimeError("amplisolve_b200_serve did not start: " + line)
+    return srv
+
+
+def run_ours(td, out_ee="o", out_vc="v", devices=None, server=None):
+    """Both programs on the staged inputs.  Returns wall times and AS_TIMING phases.  server: socket of a resident service."""
     env = dict(os.environ, AS_TIMING="1")
+    env.pop("AS_SERVER", None)
+    if server is not None:
+        env["AS_SERVER"] = server
     if devices is not None:
         env["AS_DEVICES"] = ",".join(map(str, devices))
     t = time.perf_counter()

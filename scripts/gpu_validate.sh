@@ -16,7 +16,7 @@ for k, v in d['config_legs'].items():
     print(k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items() if a.endswith('ms') or a == 'ms_per_step'})
 for k, v in d['e2e_text'].items():
     if isinstance(v, dict):
-        print(k, 'ours', [round(x, 2) for x in v['ours_wall_s_runs']], 'ref', round(v.get('reference_wall_s', 0), 2), 'x', round(v.get('speedup_wall', 0), 1))
+        print(k, 'ours', [round(x, 2) for x in v['ours_wall_s_runs']], 'served', [round(x, 2) for x in v.get('ours_served', {}).get('wall_s_runs', [])], 'ref', round(v.get('reference_wall_s', 0), 2), 'x', round(v.get('speedup_wall', 0), 1), 'x served', round(v.get('speedup_wall_served', 0), 1))
 PY
 python - <<'PY'
 import json

@@ -83,6 +83,44 @@ def test_programs_end_to_end_byte_identical(name, tmp_path):
     assert len(dummy) == len(slots) and dummy[0] == f"{slots[0][0]}\t{slots[0][1]}\t.\t.\t.\t.\t.\t."
 
 
+def test_programs_through_the_resident_service(tmp_path):
+    """amplisolve_b200_serve holds the CUDA context; the same programs, started with AS_SERVER, run inside it: outputs byte
+    for byte those of the reference, twice in a row (every run gets and returns its own device memory), and the wait for
+    CUDA is gone from the phases."""
+    import os
+    import re
+    import signal
+    sock = str(tmp_path / "as.sock")
+    srv = subprocess.Popen([str(BIN / "amplisolve_b200_serve"), f"socket={sock}"], cwd="/", stderr=subprocess.PIPE, text=True)
+    try:
+        assert "ready" in srv.stderr.readline()
+        for rnd, name in enumerate(["toy_full", gu.CASES[0], "toy_full"]):
+            case = gu.load(name)
+            wd = tmp_path / f"w{rnd}"
+            wd.mkdir()
+            slots = aseq_io.stage_case(wd, case)
+            aseq_io.write_fasta(wd, slots, list(case["ref_letters"]))
+            env = dict(os.environ, AS_SERVER=sock, AS_TIMING="1")
+            r = subprocess.run([str(BIN / "AmpliSolveErrorEstimation"), "panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=N",
+                                "C_value=%g" % float(case["c_value"]), f"coverage_cutoff={int(case['cutoff'])}", "default_error=0.01",
+                                "output_dir=o"], cwd=wd, capture_output=True, text=True, env=env)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+            table = "positionSpecificNoise_%.4f.txt" % float(case["c_value"])
+            assert (wd / "o" / table).read_text() == case["noise_table"]
+            wait = float(re.search(r"AS_TIMING cuda_context_wait ([0-9.]+)", r.stderr).group(1))   # the client's stderr got the phases
+            assert wait < 0.2, wait
+            r = subprocess.run([str(BIN / "AmpliSolveVariantCalling"), f"errorFile=o/{table}", "tumour_dir=T", "output_dir=v",
+                                f"coverage_cutoff={int(case['cutoff'])}", "p_value=0.05"], cwd=wd, capture_output=True, text=True, env=env)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+            assert (wd / "v" / "Summary_Variant_Info.txt").read_text() == case["summary"]
+            for nm in case["tumour_names"]:
+                assert vcf_body(wd / "v" / f"{nm}.vcf") == case["vcfs"][nm], nm
+        assert srv.poll() is None
+    finally:
+        srv.send_signal(signal.SIGTERM)
+        srv.wait(timeout=20)
+
+
 @pytest.mark.parametrize("wire", ["16", "packed"])
 def test_programs_byte_identical_in_either_wire_format(wire, tmp_path):
     """The loaders write the packed wire format and fall back to the 16-bit one for ultra-deep data; AS_WIRE forces one.

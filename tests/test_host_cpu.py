@@ -189,6 +189,42 @@ def test_compute_counts_reads_the_container_and_fails_loudly_without_gpu(tmp_pat
         assert not (tmp_path / "o" / "ok.PILEUP.ASEQ").exists()
 
 
+def test_resident_service_runs_the_programs_for_its_clients(tmp_path):
+    """amplisolve_b200_serve + AS_SERVER: argv, working directory, stdout / stderr and the exit status travel; the output is
+    the one of a run in the program's own process; no service listening -> the program runs by itself.  (Default-error mode
+    and usage errors need no GPU, so the plumbing is tested here; the GPU paths through the service in test_gpu_golden.py.)"""
+    import os
+    import signal
+    import time
+    case = gu.load("synth_small")
+    slots = aseq_io.stage_case(tmp_path, case)
+    aseq_io.write_fasta(tmp_path, slots, list(case["ref_letters"]))
+    args = [str(BIN / "AmpliSolveErrorEstimation"), "panel_design=panel.bed", "reference_genome=ref.fa", "germline_dir=not_available",
+            "C_value=0.002", "coverage_cutoff=100", "default_error=0.02"]
+    sock = str(tmp_path / "as.sock")
+    env = dict(os.environ, AS_SERVER=sock)
+    # nobody listens: the program runs by itself
+    r0 = subprocess.run(args + ["output_dir=alone"], cwd=tmp_path, capture_output=True, text=True, env=env)
+    assert r0.returncode == 0 and (tmp_path / "alone" / "positionSpecificNoise_default.txt").read_text() == case["default_table"]
+    srv = subprocess.Popen([str(BIN / "amplisolve_b200_serve"), f"socket={sock}"], cwd="/", stderr=subprocess.PIPE, text=True,
+                           env=dict(os.environ, AS_SERVE_NO_WARMUP="1"))
+    try:
+        assert "ready" in srv.stderr.readline()
+        r1 = subprocess.run(args + ["output_dir=served"], cwd=tmp_path, capture_output=True, text=True, env=env)
+        assert r1.returncode == 0
+        assert (tmp_path / "served" / "positionSpecificNoise_default.txt").read_text() == case["default_table"]
+        strip = lambda t: re.sub(r"(alone|served)", "X", t)   # noqa: E731
+        assert strip(r1.stdout) == strip(r0.stdout) and "Running function" in r1.stdout      # the client's stdout got the program's text
+        r2 = subprocess.run(args[:2], cwd=tmp_path, capture_output=True, text=True, env=env)  # wrong argc: usage, status 0
+        assert r2.returncode == 0 and "Your input arguments are not correct" in r2.stdout
+        r3 = subprocess.run([str(BIN / "computeCounts"), "vcf=nope.txt", "bam=nope.bam"], cwd=tmp_path, capture_output=True, text=True, env=env)
+        assert r3.returncode == 1 and "Cannot open file" in r3.stdout                           # exit status travels
+        assert srv.poll() is None
+    finally:
+        srv.send_signal(signal.SIGTERM)
+        srv.wait(timeout=10)
+
+
 def test_shard_bounds_keep_twin_groups_whole():
     """as_shard_bounds (what as_create_multi contexts split a panel by): contiguous, covering, and no twin group straddles a
     boundary -- also with a group that spans almost the whole panel; equal to amplisolve_b200.shard.shard_ranges."""

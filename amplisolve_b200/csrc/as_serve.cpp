@@ -122,9 +122,18 @@ extern "C" int as_client_run(int prog, int argc, char** argv, int* rc_out) {
     const int fds[2] = {1, 2};
     memcpy(CMSG_DATA(c), fds, sizeof fds);
     if (sendmsg(fd, &m, MSG_NOSIGNAL) != 4 || !write_all(fd, body.data(), body.size())) { close(fd); return 0; }
-    // the service answers "started" before it runs the program: from here on the program is NOT run a second time
+    // the service answers "started" before it runs the program: from here on the program is NOT run a second time.  A
+    // service that is busy with other clients (or hung) for longer than AS_SERVER_WAIT seconds (default 10) is not waited
+    // for: the program runs in its own process instead.
     uint32_t started = 0;
-    if (!read_all(fd, &started, 4) || started != kMagic) { close(fd); return 0; }
+    {
+        const char* w = getenv("AS_SERVER_WAIT");
+        timeval tv = {w ? atol(w) : 10, 0};
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);
+        if (!read_all(fd, &started, 4) || started != kMagic) { close(fd); return 0; }
+        tv.tv_sec = 0;
+        setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof tv);  // the program itself may take as long as it takes
+    }
     int32_t rc = 1;
     if (!read_all(fd, &rc, 4)) {
         fprintf(stderr, "amplisolve_b200: the service at %s went away while running the program\n", path);

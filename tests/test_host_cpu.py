@@ -219,6 +219,14 @@ def test_resident_service_runs_the_programs_for_its_clients(tmp_path):
         assert r2.returncode == 0 and "Your input arguments are not correct" in r2.stdout
         r3 = subprocess.run([str(BIN / "computeCounts"), "vcf=nope.txt", "bam=nope.bam"], cwd=tmp_path, capture_output=True, text=True, env=env)
         assert r3.returncode == 1 and "Cannot open file" in r3.stdout                           # exit status travels
+        # several clients at once: served one after the other, each with its own directory and output
+        from concurrent.futures import ThreadPoolExecutor
+        def one(k):
+            return subprocess.run(args + [f"output_dir=par{k}"], cwd=tmp_path, capture_output=True, text=True, env=env).returncode
+        with ThreadPoolExecutor(4) as pool:
+            assert list(pool.map(one, range(4))) == [0, 0, 0, 0]
+        for k in range(4):
+            assert (tmp_path / f"par{k}" / "positionSpecificNoise_default.txt").read_text() == case["default_table"]
         assert srv.poll() is None
     finally:
         srv.send_signal(signal.SIGTERM)

@@ -20,7 +20,7 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
-from oracle import pileup_oracle as po  # noqa: E402
+from tests import bam_io  # noqa: E402
 
 BIN = ROOT / "amplisolve_b200" / "bin"
 READ_LEN = 150
@@ -56,7 +56,7 @@ def bam_bytes(refs, pos, flag, mapq, seq, qual):
     code = np.array([1, 2, 4, 8], np.uint8)[seq]
     rec[:, 48:48 + READ_LEN // 2] = (code[:, 0::2] << 4) | code[:, 1::2]
     rec[:, 48 + READ_LEN // 2:] = qual
-    return po.bam_stream(refs, []) + rec.tobytes()
+    return bam_io.bam_stream(refs, []) + rec.tobytes()
 
 
 def numpy_pileup(starts, amp_len, pos, flag, mapq, seq, qual, mbq, mrq):
@@ -87,7 +87,7 @@ def run(out_json=None, n_amplicons=330, amp_len=125, depth=5000, threads=None):
             pos, flag, mapq, seq, qual = pos[order], flag[order], mapq[order], seq[order], qual[order]
             raw = bam_bytes(refs, pos, flag, mapq, seq, qual)
             res["sorted"] = True
-        (td / "S.bam").write_bytes(po.bgzf_compress(raw, level=1))
+        (td / "S.bam").write_bytes(bam_io.bgzf_compress(raw, level=1))
         with open(td / "positions.txt", "w") as f:
             for s in starts:
                 f.write("".join(f"chr1\t{s + 1 + i}\t.\t.\t.\n" for i in range(amp_len)))

@@ -10,6 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import pileup_oracle as po
+from tests import bam_io
 
 pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
@@ -78,7 +79,7 @@ def test_program_output_equals_the_oracle(ctx, tmp_path, block_bytes, piece_mb, 
     lines = panel_lines()
     write_positions(tmp_path, lines)
     reads = random_reads(6000, seed=block_bytes + mbq)
-    po.write_bam(tmp_path / "S1.bam", REFS, reads, block_bytes=block_bytes)
+    bam_io.write_bam(tmp_path / "S1.bam", REFS, reads, block_bytes=block_bytes)
     env = {"AS_BAM_PIECE_MB": piece_mb} if piece_mb is not None else None  # "0": one BGZF block per piece, records carried over
     out = run_counts(tmp_path, "S1.bam", [f"mbq={mbq}", f"mrq={mrq}", f"mdc={mdc}", "threads=3"], env)
     want = po.render_aseq(lines, po.pileup(REFS, reads, mbq=mbq, mrq=mrq), mdc=mdc)
@@ -94,7 +95,7 @@ def test_several_bams_in_one_run(ctx, tmp_path):
     write_positions(tmp_path, lines)
     sets = {name: random_reads(2500, seed=k) for k, name in enumerate(("N1", "N2", "T1"))}
     for name, reads in sets.items():
-        po.write_bam(tmp_path / f"{name}.bam", REFS, reads, block_bytes=4000)
+        bam_io.write_bam(tmp_path / f"{name}.bam", REFS, reads, block_bytes=4000)
     run_counts(tmp_path, "N1.bam,N2.bam,T1.bam", ["mdc=3"])
     for name, reads in sets.items():
         assert (tmp_path / "aseq" / f"{name}.PILEUP.ASEQ").read_text() == po.render_aseq(lines, po.pileup(REFS, reads), mdc=3)
@@ -103,7 +104,7 @@ def test_several_bams_in_one_run(ctx, tmp_path):
 def test_empty_and_headers_only(ctx, tmp_path):
     lines = panel_lines()
     write_positions(tmp_path, lines)
-    po.write_bam(tmp_path / "empty.bam", REFS, [])
+    bam_io.write_bam(tmp_path / "empty.bam", REFS, [])
     run_counts(tmp_path, "empty.bam", ["mdc=1"])
     assert (tmp_path / "aseq" / "empty.PILEUP.ASEQ").read_text() == po.render_aseq(lines, {}, mdc=1)
     run_counts(tmp_path, "empty.bam", ["mdc=0"])  # every line of the position file, all zero
@@ -123,7 +124,7 @@ def test_c_abi_counts_are_the_count_tensor_of_one_sample(ctx):
     import struct
     from amplisolve_b200 import AmpliSolveError
     reads = random_reads(3000, seed=5)
-    stream = po.bam_stream(REFS, reads)
+    stream = bam_io.bam_stream(REFS, reads)
     o = 8 + struct.unpack_from("<i", stream, 4)[0]  # strip the header, index the records
     n_ref = struct.unpack_from("<i", stream, o)[0]
     o += 4

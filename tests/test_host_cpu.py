@@ -169,7 +169,7 @@ def test_compute_counts_reads_the_container_and_fails_loudly_without_gpu(tmp_pat
     """computeCounts: usage and container errors need no GPU; a valid BAM without a GPU is an error that
     says so -- there is no CPU pileup behind the program."""
     import torch
-    from oracle import pileup_oracle as po
+    from tests import bam_io
     prog = str(BIN / "computeCounts")
     r = subprocess.run([prog], capture_output=True, text=True)
     assert r.returncode == 0 and "Usage: computeCounts" in r.stdout
@@ -178,7 +178,7 @@ def test_compute_counts_reads_the_container_and_fails_loudly_without_gpu(tmp_pat
     r = subprocess.run([prog, "vcf=positions.txt", "bam=x.bam", "out=o"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "not a BGZF" in r.stdout
     read = dict(ref_id=0, pos=990, mapq=60, flag=0, cigar=[("M", 30)], seq="ACGT" * 7 + "AC", qual=bytes([30]) * 30)
-    po.write_bam(tmp_path / "ok.bam", [("chr1", 5000)], [read] * 25)
+    bam_io.write_bam(tmp_path / "ok.bam", [("chr1", 5000)], [read] * 25)
     r = subprocess.run([prog, "vcf=positions.txt", "bam=ok.bam", "out=o"], cwd=tmp_path, capture_output=True, text=True)
     if torch.cuda.is_available():
         assert r.returncode == 0

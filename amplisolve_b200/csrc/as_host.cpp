@@ -21,9 +21,11 @@
 #include <cstring>
 #include <ctime>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <sstream>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -53,7 +55,12 @@ struct Panel {
     std::vector<std::string> ref;       // reference text per slot
     std::vector<uint8_t> dup;           // position enumerated at least twice (EE:664) / flagged YES (VC:514)
     std::vector<int32_t> twin_next, twin_head;
-    std::unordered_map<uint64_t, int32_t> first_slot;
+    // (chrom, pos) -> first and last slot of the position so far: one flat table with linear probing (a node-based
+    // unordered_map pair cost 0.2 us per slot, a fifth of the caller program's run on a 200,000-slot panel)
+    struct PosEntry { uint64_t key; int32_t first, last; };
+    std::vector<PosEntry> table;
+    uint64_t table_mask = 0;
+    int64_t n_positions = 0;  // distinct (chrom, pos)
     bool has_twins = false;
 
     int32_t chrom_id(const std::string& c) {
@@ -69,6 +76,10 @@ struct Panel {
         return it == chrom_idx.end() ? -1 : it->second;
     }
     static uint64_t key(int32_t chrom, int32_t pos) { return ((uint64_t)(uint32_t)chrom << 32) | (uint32_t)pos; }
+    static uint64_t mix(uint64_t k) {  // consecutive positions must not land in consecutive cells of one long run
+        k *= 0x9E3779B97F4A7C15ull;
+        return k ^ (k >> 29);
+    }
     int64_t size() const { return (int64_t)slot_pos.size(); }
     void add_slot(int32_t chrom, int32_t pos) {
         slot_chrom.push_back(chrom);
@@ -79,27 +90,35 @@ struct Panel {
         const int64_t P = size();
         twin_next.assign(P, -1);
         twin_head.resize(P);
-        std::unordered_map<uint64_t, int32_t> last;
-        last.reserve(P * 2);
-        first_slot.reserve(P * 2);
+        uint64_t cap = 16;
+        while (cap < (uint64_t)P * 2 + 2) cap <<= 1;
+        table.assign(cap, PosEntry{0, -1, -1});
+        table_mask = cap - 1;
+        n_positions = 0;
         for (int64_t i = 0; i < P; ++i) {
             const uint64_t k = key(slot_chrom[i], slot_pos[i]);
-            auto it = last.find(k);
-            if (it == last.end()) {
+            uint64_t h = mix(k) & table_mask;
+            while (table[h].first >= 0 && table[h].key != k) h = (h + 1) & table_mask;
+            PosEntry& en = table[h];
+            if (en.first < 0) {
+                en.key = k;
+                en.first = en.last = (int32_t)i;
                 twin_head[i] = (int32_t)i;
-                first_slot.emplace(k, (int32_t)i);
-                last.emplace(k, (int32_t)i);
+                ++n_positions;
             } else {
-                twin_next[it->second] = (int32_t)i;
-                twin_head[i] = twin_head[it->second];
-                it->second = (int32_t)i;
+                twin_next[en.last] = (int32_t)i;
+                twin_head[i] = en.first;
+                en.last = (int32_t)i;
                 has_twins = true;
             }
         }
     }
     int32_t lookup(int32_t chrom, int32_t pos) const {
-        auto it = first_slot.find(key(chrom, pos));
-        return it == first_slot.end() ? -1 : it->second;
+        if (table.empty()) return -1;
+        const uint64_t k = key(chrom, pos);
+        uint64_t h = mix(k) & table_mask;
+        while (table[h].first >= 0 && table[h].key != k) h = (h + 1) & table_mask;
+        return table[h].first;
     }
 };
 
@@ -285,6 +304,31 @@ inline bool parse_int(const char*& p, const char* e, long long& v) {
     while (p < e && *p >= '0' && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
     v = neg ? -x : x;
     return true;
+}
+
+// std::stof of the text [b, end) of a threshold (VC:889-890), 0 for an empty one.  The cells a noise table holds -- "%f" of a
+// float ("0.001234"), "-2", "0.01" -- are [-]digits[.digits] with at most 8 digits in all: the digits are an integer n < 10^8
+// and the value is n / 10^s, s <= 8.  double(n) / 10^s is the correctly rounded double of the decimal, and narrowing it gives
+// the correctly rounded FLOAT as strtof does: a float rounding boundary m / 2^k (m < 2^25) near n / 10^s differs from it by
+// at least 1 / (10^s * 2^k) -- relative 1 / (n * 2^k) ~ 1 / (m * 10^s) > 2^-52 -- or not at all, so the first rounding never
+// lands on a boundary it was not on (checked against strtof for every n < 10^7 at s = 6: scripts/parse_bench.cpp).
+// Anything else (exponents, nan, more digits) goes to strtof.
+inline float threshold_text_to_float(const char* b, const char* end) {
+    if (b >= end) return 0.f;
+    static const double pow10[9] = {1., 10., 100., 1e3, 1e4, 1e5, 1e6, 1e7, 1e8};
+    const char* q = b;
+    const bool neg = *q == '-';
+    q += neg ? 1 : 0;
+    uint32_t n = 0;
+    int digits = 0, frac = 0;
+    while (q < end && (unsigned)(*q - '0') <= 9u) { n = n * 10u + (uint32_t)(*q - '0'); ++q; ++digits; }
+    if (q < end && *q == '.') {
+        ++q;
+        while (q < end && (unsigned)(*q - '0') <= 9u) { n = n * 10u + (uint32_t)(*q - '0'); ++q; ++digits; ++frac; }
+    }
+    if (q != end || digits == 0 || digits > 8) return strtof(b, nullptr);
+    const float v = (float)((double)n / pow10[frac]);
+    return neg ? -v : v;
 }
 
 struct MappedFile {  // read-only view of a whole file
@@ -1096,7 +1140,7 @@ int as_error_estimation_main(int argc, char** argv) {
     }
     std::cout << "Reference bases and amplicon duplicated positions have generated" << "\n\t\t --> Parsed in total " << n_amplicons
               << " amplicons and annotated " << P << " positions." << std::endl;
-    std::cout << "Running function storeReference: panel reference bases stored with success " << GREEN << panel.first_slot.size()
+    std::cout << "Running function storeReference: panel reference bases stored with success " << GREEN << panel.n_positions
               << RESET << std::endl;
 
     timer.lap("panel_and_reference_bases", (double)P, "positions");
@@ -1173,7 +1217,7 @@ int as_error_estimation_main(int argc, char** argv) {
                                                        germ_val.data(), germ_state.data(), count.data(), nrec.data(), nullptr);
     if (rc != AS_OK) return report_gpu_error("as_noise_estimate_host");
     timer.lap("noise_model_gpu", (double)P, "positions");
-    std::cout << "thresholds for " << panel.first_slot.size() << " positions estimated on the GPU" << std::endl;
+    std::cout << "thresholds for " << panel.n_positions << " positions estimated on the GPU" << std::endl;
 
     // generateFinalOutput (EE:2546-2944)
     char out_name[4096];
@@ -1244,6 +1288,142 @@ int as_error_estimation_main(int argc, char** argv) {
     return 0;
 }
 
+namespace {
+// ---------------------------------------------------------------------------------------------------
+// The noise table of the error-estimation program (storeInputFile, VC:430-576): one panel slot per row -- chrom, position,
+// reference, duplicated flag, four threshold cells "<fw>_<bw>", four Germ_Max cells.  Fills the panel's slot arrays,
+// thr_view [P][4][2] (std::stof of the cells, VC:889-890), germ_text [P][4] and the text of dummyVCF_1.vcf (VC:564) in
+// pieces to be written one after the other.  force_pieces > 0 fixes the number of pieces (tests).
+// ---------------------------------------------------------------------------------------------------
+void parse_noise_table(const std::string& text, int force_pieces, Panel& panel, std::vector<float>& thr_view,
+                       std::vector<std::string>& germ_text, std::vector<std::string>& dummy_pieces) {
+    // The table is cut into pieces at line ends and parsed on all host threads (a 2,000,000-row table is 170 MB of text:
+    // one thread needs 1.4 s for it, most of it in strtof).  Pass 1 counts the rows of every piece and collects its
+    // chromosome names in order of appearance; the names are registered piece by piece, so ids follow the first
+    // appearance in the file as a sequential parse gives them; pass 2 writes every row at its final index.
+    const char* p = text.data();
+    const char* e = p + text.size();
+    const char* eol = (const char*)memchr(p, '\n', e - p);  // header
+    p = eol ? eol + 1 : e;
+    const size_t body = (size_t)(e - p);
+    const unsigned n_piece = force_pieces > 0 ? (unsigned)force_pieces
+                                              : (unsigned)std::max<size_t>(1, std::min<size_t>(std::max(1u, std::thread::hardware_concurrency()), body / (256 << 10)));
+    std::vector<const char*> cut_at(n_piece + 1, e);
+    cut_at[0] = p;
+    for (unsigned k = 1; k < n_piece; ++k) {
+        const char* c = p + body * k / n_piece;
+        c = std::max(c, cut_at[k - 1]);
+        const char* nl = c < e ? (const char*)memchr(c, '\n', (size_t)(e - c)) : nullptr;
+        cut_at[k] = nl ? nl + 1 : e;
+    }
+    struct Piece {
+        size_t rows = 0;
+        std::vector<std::string> names;  // distinct chromosome names in order of appearance
+        std::string dummy;               // this piece of dummyVCF_1.vcf (VC:564)
+    };
+    std::vector<Piece> pieces(n_piece);
+    auto run_pieces = [&](const std::function<void(unsigned)>& f) {
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < n_piece; ++k) th.emplace_back(f, k);
+        f(0);
+        for (auto& t : th) t.join();
+    };
+    run_pieces([&](unsigned k) {
+        Piece& pc = pieces[k];
+        const char* last_b = nullptr;
+        size_t last_n = 0;
+        for (const char* c = cut_at[k]; c < cut_at[k + 1];) {
+            const char* le = (const char*)memchr(c, '\n', (size_t)(cut_at[k + 1] - c));
+            if (!le) le = cut_at[k + 1];
+            const char* q = skip_ws(c, le);
+            const char* t = token_end(q, le);
+            if (t > q) {
+                ++pc.rows;
+                const size_t cn = (size_t)(t - q);
+                if (!last_b || cn != last_n || memcmp(last_b, q, cn) != 0) {
+                    last_b = q;
+                    last_n = cn;
+                    std::string name(q, t);
+                    if (std::find(pc.names.begin(), pc.names.end(), name) == pc.names.end()) pc.names.push_back(name);
+                }
+            }
+            c = le + 1;
+        }
+    });
+    size_t rows = 0;
+    std::vector<size_t> first_row(n_piece + 1, 0);
+    for (unsigned k = 0; k < n_piece; ++k) {
+        for (const std::string& name : pieces[k].names) panel.chrom_id(name);
+        first_row[k] = rows;
+        rows += pieces[k].rows;
+    }
+    first_row[n_piece] = rows;
+    panel.slot_chrom.resize(rows); panel.slot_pos.resize(rows); panel.pos_text.resize(rows); panel.ref.resize(rows);
+    panel.dup.resize(rows); thr_view.resize(rows * 8); germ_text.resize(rows * 4);
+    const Panel& names = panel;  // pass 2 only reads the name table
+    run_pieces([&](unsigned k) {
+        Piece& pc = pieces[k];
+        pc.dummy.reserve((size_t)(cut_at[k + 1] - cut_at[k]) / 3);
+        size_t row = first_row[k];
+        const char* last_chrom_b = nullptr;
+        size_t last_chrom_n = 0;
+        int32_t last_chrom_id = -1;
+        for (const char* c = cut_at[k]; c < cut_at[k + 1];) {
+            const char* le = (const char*)memchr(c, '\n', (size_t)(cut_at[k + 1] - c));
+            if (!le) le = cut_at[k + 1];
+            const char* fb[12];
+            const char* fe[12];
+            const char* q = c;
+            int nf = 0;
+            for (; nf < 12; ++nf) {
+                q = skip_ws(q, le);
+                const char* t = token_end(q, le);
+                if (t == q) break;
+                fb[nf] = q;
+                fe[nf] = t;
+                q = t;
+            }
+            for (int f = nf; f < 12; ++f) fb[f] = fe[f] = le;  // missing fields read as empty strings
+            if (nf >= 1) {
+                const size_t cn = (size_t)(fe[0] - fb[0]);
+                if (last_chrom_id < 0 || cn != last_chrom_n || memcmp(last_chrom_b, fb[0], cn) != 0) {
+                    last_chrom_id = names.find_chrom(fb[0], cn);
+                    last_chrom_b = fb[0];
+                    last_chrom_n = cn;
+                }
+                panel.slot_chrom[row] = last_chrom_id;
+                panel.slot_pos[row] = (int32_t)strtol(fb[1], nullptr, 10);  // fields end at a blank, a tab or the line end: strtol stops there
+                panel.pos_text[row].assign(fb[1], fe[1]);
+                panel.ref[row].assign(fb[2], fe[2]);
+                panel.dup[row] = (fe[3] - fb[3] == 3 && memcmp(fb[3], "YES", 3) == 0) ? 1 : 0;
+                for (int b = 0; b < 4; ++b) {
+                    // a threshold cell "<fw>_<bw>" as sscanf("%[^_]_%[^_]") + std::stof read it (VC:888-890); no copies
+                    const char* cb = fb[4 + b];
+                    const char* ce = fe[4 + b];
+                    const char* us = (const char*)memchr(cb, '_', (size_t)(ce - cb));
+                    float a = 0.f, bwv = 0.f;
+                    if (us) {
+                        const char* us2 = (const char*)memchr(us + 1, '_', (size_t)(ce - us - 1));  // %[^_] stops at a second '_'
+                        a = threshold_text_to_float(cb, us);
+                        bwv = threshold_text_to_float(us + 1, us2 ? us2 : ce);
+                    }
+                    thr_view[row * 8 + (size_t)b * 2] = a;
+                    thr_view[row * 8 + (size_t)b * 2 + 1] = bwv;
+                    germ_text[row * 4 + (size_t)b].assign(fb[8 + b], fe[8 + b]);
+                }
+                pc.dummy.append(fb[0], fe[0]).push_back('\t');
+                pc.dummy.append(fb[1], fe[1]).append("\t.\t.\t.\t.\t.\t.\n");
+                ++row;
+            }
+            c = le + 1;
+        }
+    });
+    dummy_pieces.clear();
+    for (Piece& pc : pieces) dummy_pieces.push_back(std::move(pc.dummy));
+}
+
+}  // namespace
+
 // ===================================================================================================
 // AmpliSolveVariantCalling (VC:199-360, VC:430-576, VC:633-3304)
 // ===================================================================================================
@@ -1305,70 +1485,10 @@ int as_variant_calling_main(int argc, char** argv) {
             printf("Error from storeInputFile function: Cannot open %s\n", error_file.c_str());
             return 0;
         }
-        std::string dummy_text;  // dummyVCF_1.vcf (VC:564), written in one piece
-        dummy_text.reserve(text.size() / 3);
-        const char* p = text.data();
-        const char* e = p + text.size();
-        const char* eol = (const char*)memchr(p, '\n', e - p);  // header
-        p = eol ? eol + 1 : e;
-        {
-            size_t rows = 0;
-            for (const char* c = p; c < e; ++rows) { c = (const char*)memchr(c, '\n', e - c); c = c ? c + 1 : e; }
-            panel.slot_chrom.reserve(rows); panel.slot_pos.reserve(rows); panel.pos_text.reserve(rows); panel.ref.reserve(rows);
-            panel.dup.reserve(rows); thr_view.reserve(rows * 8); germ_text.reserve(rows * 4);
-        }
-        // a threshold cell "<fw>_<bw>" as sscanf("%[^_]_%[^_]") + std::stof read it (VC:888-890); no copies
-        auto part = [](const char* b, const char* end) -> float { return (b >= end || *b == '_') ? 0.f : strtof(b, nullptr); };
-        const char* last_chrom_b = nullptr;
-        size_t last_chrom_n = 0;
-        int32_t last_chrom_id = -1;
-        while (p < e) {
-            eol = (const char*)memchr(p, '\n', e - p);
-            if (!eol) eol = e;
-            const char* fb[12];
-            const char* fe[12];
-            const char* q = p;
-            int nf = 0;
-            for (; nf < 12; ++nf) {
-                q = skip_ws(q, eol);
-                const char* t = token_end(q, eol);
-                if (t == q) break;
-                fb[nf] = q;
-                fe[nf] = t;
-                q = t;
-            }
-            for (int k = nf; k < 12; ++k) fb[k] = fe[k] = eol;  // missing fields read as empty strings
-            if (nf >= 1) {
-                const size_t cn = (size_t)(fe[0] - fb[0]);
-                if (last_chrom_id < 0 || cn != last_chrom_n || memcmp(last_chrom_b, fb[0], cn) != 0) {
-                    last_chrom_id = panel.chrom_id(std::string(fb[0], fe[0]));
-                    last_chrom_b = fb[0];
-                    last_chrom_n = cn;
-                }
-                panel.add_slot(last_chrom_id, (int32_t)strtol(fb[1], nullptr, 10));  // fields end at a blank, a tab or the line end: strtol stops there
-                panel.pos_text.emplace_back(fb[1], fe[1]);
-                panel.ref.emplace_back(fb[2], fe[2]);
-                panel.dup.push_back((fe[3] - fb[3] == 3 && memcmp(fb[3], "YES", 3) == 0) ? 1 : 0);
-                for (int b = 0; b < 4; ++b) {
-                    const char* cb = fb[4 + b];
-                    const char* ce = fe[4 + b];
-                    const char* us = (const char*)memchr(cb, '_', (size_t)(ce - cb));
-                    float a = 0.f, bwv = 0.f;
-                    if (us) {
-                        a = part(cb, us);
-                        bwv = part(us + 1, ce);
-                    }
-                    thr_view.push_back(a);
-                    thr_view.push_back(bwv);
-                    germ_text.emplace_back(fb[8 + b], fe[8 + b]);
-                }
-                dummy_text.append(fb[0], fe[0]).push_back('\t');
-                dummy_text.append(fb[1], fe[1]).append("\t.\t.\t.\t.\t.\t.\n");
-            }
-            p = eol + 1;
-        }
+        std::vector<std::string> dummy_pieces;  // dummyVCF_1.vcf (VC:564)
+        parse_noise_table(text, 0, panel, thr_view, germ_text, dummy_pieces);
         std::ofstream dummy((interm + "/dummyVCF_1.vcf").c_str());
-        dummy.write(dummy_text.data(), (std::streamsize)dummy_text.size());
+        for (const std::string& d : dummy_pieces) dummy.write(d.data(), (std::streamsize)d.size());
     }
     panel.link();
     const int64_t P = panel.size();
@@ -1650,12 +1770,23 @@ int as_variant_calling_main(int argc, char** argv) {
               "mopolymerFlag"
            << "\n";
     const char* L = "ACGT";
-    size_t ci = 0;
-    for (int t = 0; t < T; ++t) {
+    // One tumour = one VCF and one run of summary rows: the tumours are formatted on all host threads (ostream formatting of
+    // ~20 numbers per call was the largest phase of a configs[1] run), every thread writes its own VCFs, and the summary
+    // runs are written in tumour order afterwards.
+    std::vector<size_t> call_begin((size_t)T + 1, calls.size());
+    for (size_t i = calls.size(); i-- > 0;) call_begin[(size_t)calls[i].sample] = i;
+    for (int t = T - 1; t >= 0; --t) call_begin[(size_t)t] = std::min(call_begin[(size_t)t], call_begin[(size_t)t + 1]);
+    std::vector<std::string> summary_rows((size_t)T);
+    auto write_tumour = [&](int t) {
+        std::ostringstream output;
+        // setprecision(4) is sticky on the reference's summary stream (VC:1066): only the first row of the run prints its
+        // leading columns with the default precision
+        if (call_begin[(size_t)t] > 0) output << std::setprecision(4);
         const std::string vcf_name = output_dir + "/" + files[t].sample + ".vcf";
         std::ofstream vcf(vcf_name.c_str());
         time_t now = time(nullptr);
-        char* dt = ctime(&now);
+        char dt_buf[64];
+        const char* dt = ctime_r(&now, dt_buf);
         vcf << "##fileformat=VCF-like\n##fileDate=" << dt
             << "##source=AmpliSolveVariantCalling\n##reference=Not_Specified_here\n##phasing=Not_Specified_here\n##FILTER=<ID="
                "XXXXXXXXX,Description='XXXXXXXXX'>\n##FILTER=<ID=XXXXXXXXX,Description='XXXXXXXXX'>\n##FILTER=<ID=XXXXXXXXX,"
@@ -1665,9 +1796,7 @@ int as_variant_calling_main(int argc, char** argv) {
             << ">\n##INFO=<ID=AF,Number=.,Type=Float,Description='Allele Frequency'>\n##INFO=<ID=SR,Number=1,Type=String,"
                "Description='Supporting Reads'>\n#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO"
             << "\n";
-        if ((t + 1) % 50 == 0)
-            std::cout << "\tParsed successfully " << GREEN << (t + 1) << "/" << T << RESET << "  samples" << std::endl;
-        for (; ci < calls.size() && calls[ci].sample == t; ++ci) {
+        for (size_t ci = call_begin[(size_t)t]; ci < call_begin[(size_t)t + 1]; ++ci) {
             const as_call& c = calls[ci];
             const int64_t s = c.slot;
             const uint32_t* fw = call_counts[ci].fw;
@@ -1724,6 +1853,23 @@ int as_variant_calling_main(int argc, char** argv) {
                    << std::setprecision(4) << Q_bw << "\t" << tier << "\t" << "-" << "\t" << max_germ_text << "\t" << down << "\t"
                    << up << "\t" << homo << "\n";
         }
+        summary_rows[(size_t)t] = output.str();
+    };
+    {
+        std::atomic<int> next(0);
+        auto work = [&]() {
+            for (int t = next.fetch_add(1); t < T; t = next.fetch_add(1)) write_tumour(t);
+        };
+        const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, T)));
+        std::vector<std::thread> th;
+        for (unsigned k = 1; k < hw; ++k) th.emplace_back(work);
+        work();
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) {
+        if ((t + 1) % 50 == 0)
+            std::cout << "\tParsed successfully " << GREEN << (t + 1) << "/" << T << RESET << "  samples" << std::endl;
+        output.write(summary_rows[(size_t)t].data(), (std::streamsize)summary_rows[(size_t)t].size());
     }
     output.close();
     timer.lap("write_outputs", (double)calls.size(), "calls");

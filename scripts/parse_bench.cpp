@@ -5,7 +5,52 @@
 //       -Wl,-rpath,$PWD/amplisolve_b200/lib -o /tmp/parse_bench && /tmp/parse_bench panel.bed ASEQ_DIR [threads]
 #include "../amplisolve_b200/csrc/as_host.cpp"
 
+// parse_bench --noise-table table.txt pieces [dump.txt] [repeat]: the caller program's noise-table parser alone (as_host.cpp
+// parse_noise_table + Panel::link), `pieces` = 0 for the automatic cut.  The dump holds, per row, everything the parser
+// stored (the thresholds as float bit patterns), for the CPU test that compares it with an independent reading of the table.
+static int noise_table_mode(int argc, char** argv) {
+    if (argc < 4) { fprintf(stderr, "usage: parse_bench --noise-table table.txt pieces [dump.txt] [repeat]\n"); return 2; }
+    std::string text;
+    if (!read_file(argv[2], text)) { fprintf(stderr, "cannot read %s\n", argv[2]); return 1; }
+    const int pieces = atoi(argv[3]);
+    const int repeat = argc > 5 ? atoi(argv[5]) : 1;
+    double best_parse = 1e30, best_link = 1e30;
+    Panel keep;
+    std::vector<float> thr;
+    std::vector<std::string> germ, dummy;
+    for (int r = 0; r < repeat; ++r) {
+        Panel panel;
+        const double t0 = PhaseTimer::now();
+        parse_noise_table(text, pieces, panel, thr, germ, dummy);
+        const double t1 = PhaseTimer::now();
+        panel.link();
+        const double t2 = PhaseTimer::now();
+        best_parse = std::min(best_parse, t1 - t0);
+        best_link = std::min(best_link, t2 - t1);
+        if (r + 1 == repeat) keep = std::move(panel);
+    }
+    const int64_t P = keep.size();
+    if (argc > 4 && argv[4][0] != '-') {
+        FILE* o = fopen(argv[4], "w");
+        if (!o) return 1;
+        for (int64_t i = 0; i < P; ++i) {
+            fprintf(o, "%d %s %d %s %s %d", keep.slot_chrom[i], keep.chroms[(size_t)keep.slot_chrom[i]].c_str(), keep.slot_pos[i],
+                    keep.pos_text[i].c_str(), keep.ref[i].empty() ? "~" : keep.ref[i].c_str(), (int)keep.dup[i]);
+            for (int k = 0; k < 8; ++k) { uint32_t u; memcpy(&u, &thr[(size_t)i * 8 + k], 4); fprintf(o, " %08x", u); }
+            for (int k = 0; k < 4; ++k) fprintf(o, " %s", germ[(size_t)i * 4 + k].empty() ? "~" : germ[(size_t)i * 4 + k].c_str());
+            fprintf(o, " %d %d %d\n", keep.twin_head[i], keep.twin_next[i], keep.lookup(keep.slot_chrom[i], keep.slot_pos[i]));
+        }
+        fputs("DUMMY\n", o);
+        for (const std::string& d : dummy) fwrite(d.data(), 1, d.size(), o);
+        fclose(o);
+    }
+    printf("{\"rows\": %lld, \"positions\": %lld, \"pieces\": %zu, \"parse_s\": %.5f, \"link_s\": %.5f, \"rows_per_s\": %.3g}\n", (long long)P,
+           (long long)keep.n_positions, dummy.size(), best_parse, best_link, P / (best_parse + best_link));
+    return 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "--noise-table") == 0) return noise_table_mode(argc, argv);
     if (argc < 3) { fprintf(stderr, "usage: parse_bench panel.bed aseq_dir [repeat]\n"); return 2; }
     Panel panel;
     int n_amp = 0;

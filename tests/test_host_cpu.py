@@ -300,3 +300,77 @@ def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
     assert variant("blank_lines", lambda t: t.replace("\n", "\n\n")) == base
     assert variant("reversed", lambda t: "\n".join(t.strip("\n").split("\n")[::-1]) + "\n") == base
     assert variant("no_final_newline", lambda t: t.rstrip("\n")) == base
+
+
+def _build_parse_bench(tmp_path):
+    import shutil
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "parse_bench"
+    lib_dir = ROOT / "amplisolve_b200" / "lib"
+    from amplisolve_b200 import lib
+    lib()
+    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I", str(ROOT / "include"), str(ROOT / "scripts" / "parse_bench.cpp"),
+                        f"-L{lib_dir}", "-lamplisolve_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return exe
+
+
+def test_noise_table_parser_in_pieces_equals_an_independent_reading(tmp_path):
+    """The caller program reads the noise table (storeInputFile, VC:430-576) in pieces on all host threads, with its own
+    decimal -> float conversion for the cells "%f" writes (as_host.cpp parse_noise_table, threshold_text_to_float).  Whatever
+    the number of pieces, every row must hold what a plain reading of the table gives: chromosome ids in order of first
+    appearance, position, texts, flag, std::stof of the eight threshold parts (compared as float bit patterns against
+    numpy's correctly rounded conversion), the Germ_Max texts, the twin links of repeated positions and the dummy VCF."""
+    import json
+    import numpy as np
+    exe = _build_parse_bench(tmp_path)
+    table = str(np.load(ROOT / "tests" / "golden" / "toy_slice.npz", allow_pickle=True)["noise_table"])
+    head, body = table.split("\n", 1)
+    rows = [r for r in body.split("\n") if r.strip()]
+    # cells the golden table does not hold: empty parts, a second underscore, exponents, nan, many digits, blanks, CRLF
+    odd = ["chrZ\t77\tN\tNO\t_0.5\t1e-05_2.5e-3\tnan_inf\t0.123456789_12345678.5\t-\t0\t1.5\t-888",
+           "chrZ  78 \t A  YES\t0.25_\t-2_-2\t0.01_0.01\t0.000001_9.999999\t-\t-\t-\t-\r",
+           "chr8\t77\tC\tNO\t0.1_0.2_0.3\t7_8\t.5_5.\t-0.000000_0.000000\t1\t2\t3\t4",
+           "chrZ\t77\tG\tYES\t1_1\t1_1\t1_1\t1_1\t-\t-\t-\t-"]
+    rows = rows[:1500] + odd[:2] + rows[1500:] + odd[2:]
+    path = tmp_path / "table.txt"
+    path.write_text(head + "\n" + "\n".join(rows) + "\n\n")
+
+    # the independent reading
+    chrom_ids, first, last, expect, dummy = {}, {}, {}, [], []
+    heads, nexts = [], []
+    for i, r in enumerate(rows):
+        f = r.split()
+        f += [""] * (12 - len(f))
+        cid = chrom_ids.setdefault(f[0], len(chrom_ids))
+        bits = []
+        for cell in f[4:8]:
+            parts = cell.split("_")
+            for part in (parts[:2] if len(parts) >= 2 else ["", ""]):
+                v = np.float32(0) if part == "" else np.float32(part)
+                bits.append("%08x" % np.array(v, np.float32).view(np.uint32))
+        key = (cid, int(f[1]))
+        heads.append(first.setdefault(key, i))
+        nexts.append(-1)
+        if key in last:
+            nexts[last[key]] = i
+        last[key] = i
+        expect.append([str(cid), f[0], f[1], f[1], f[2] or "~", "1" if f[3] == "YES" else "0"] + bits + [g or "~" for g in f[8:12]])
+        dummy.append(f"{f[0]}\t{f[1]}\t.\t.\t.\t.\t.\t.\n")
+    for i in range(len(rows)):
+        expect[i] += [str(heads[i]), str(nexts[i]), str(heads[i])]
+
+    for pieces in (1, 2, 7, 64, 0):
+        dump = tmp_path / f"dump{pieces}.txt"
+        out = subprocess.run([str(exe), "--noise-table", str(path), str(pieces), str(dump)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        res = json.loads(out.stdout)
+        assert res["rows"] == len(rows) and res["positions"] == len(first)
+        got, got_dummy = dump.read_text().split("DUMMY\n")
+        got = [g.split(" ") for g in got.strip("\n").split("\n")]
+        assert len(got) == len(expect)
+        for g, x in zip(got, expect):
+            assert g == x, (pieces, g, x)
+        assert got_dummy == "".join(dummy)

@@ -331,6 +331,29 @@ inline float threshold_text_to_float(const char* b, const char* end) {
     return neg ? -v : v;
 }
 
+// "%f" of a float threshold (EE:1787), appended to o.  For 0 <= v < 2^20 the value v * 10^6 is EXACT in a double (a 24-bit
+// significand times 10^6 < 2^20), so rint() under the default rounding mode is the round-half-even of the exact decimal that
+// printf performs (compared with snprintf for every float in [0, 0.0625] and a sample above); anything else (negative,
+// -0, huge, nan, inf) goes to snprintf.
+inline void append_percent_f(std::string& o, float v) {
+    if (!(v >= 0.f && v < 1048576.f) || std::signbit(v)) {  // -0 prints its sign
+        char cell[64];
+        snprintf(cell, sizeof cell, "%f", (double)v);
+        o += cell;
+        return;
+    }
+    const uint64_t n = (uint64_t)__builtin_rint((double)v * 1e6);
+    uint64_t ip = n / 1000000u;
+    uint32_t fp = (uint32_t)(n % 1000000u);
+    char buf[32];
+    char* e = buf + sizeof buf;
+    char* q = e;
+    for (int k = 0; k < 6; ++k) { *--q = (char)('0' + fp % 10u); fp /= 10u; }
+    *--q = '.';
+    do { *--q = (char)('0' + ip % 10u); ip /= 10u; } while (ip);
+    o.append(q, (size_t)(e - q));
+}
+
 struct MappedFile {  // read-only view of a whole file
     const char* p = nullptr;
     size_t n = 0;
@@ -1227,7 +1250,8 @@ int as_error_estimation_main(int argc, char** argv) {
         // in order; the bytes are what the reference's streams produce: "%f" (EE:1787), operator<<(double) = "%g" (EE:2815)
         std::ofstream output(out_name);
         output << header << "\n";
-        const int64_t CH = 16384;
+        // chunk size: every thread gets a few chunks also on a small panel
+        const int64_t CH = std::max<int64_t>(512, std::min<int64_t>(16384, P / (4 * (int64_t)std::max(1u, std::thread::hardware_concurrency()))));
         const size_t n_chunks = (size_t)((P + CH - 1) / CH);
         const size_t WAVE = 256;  // chunks formatted before they are written: bounds the text held in memory
         std::vector<std::string> text(std::min(n_chunks, WAVE));
@@ -1255,8 +1279,10 @@ int as_error_estimation_main(int argc, char** argv) {
                             } else if (std::isnan(tf) || std::isnan(tb)) {
                                 o += "\t0.01_0.01";  // "-1_-1" -> EE:2680-2684
                             } else {
-                                snprintf(cell, sizeof cell, "\t%f_%f", (double)tf, (double)tb);  // EE:1787
-                                o += cell;
+                                o += '\t';  // "%f_%f", EE:1787
+                                append_percent_f(o, tf);
+                                o += '_';
+                                append_percent_f(o, tb);
                             }
                         }
                         for (int b = 0; b < 4; ++b) {

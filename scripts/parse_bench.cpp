@@ -49,8 +49,31 @@ static int noise_table_mode(int argc, char** argv) {
     return 0;
 }
 
+// parse_bench --percent-f first_bits last_bits stride: append_percent_f (the noise-table writer's "%f") against snprintf for
+// the floats whose bit patterns are first, first + stride, ... <= last.
+static int percent_f_mode(int argc, char** argv) {
+    if (argc < 5) return 2;
+    const uint64_t first = strtoull(argv[2], nullptr, 0), last = strtoull(argv[3], nullptr, 0), stride = std::max(1ull, strtoull(argv[4], nullptr, 0));
+    long long tried = 0, bad = 0;
+    std::string o;
+    char cell[64];
+    for (uint64_t u = first; u <= last; u += stride) {
+        const uint32_t w = (uint32_t)u;
+        float v;
+        memcpy(&v, &w, 4);
+        o.clear();
+        append_percent_f(o, v);
+        snprintf(cell, sizeof cell, "%f", (double)v);
+        ++tried;
+        if (o != cell) ++bad;
+    }
+    printf("{\"tried\": %lld, \"differences\": %lld}\n", tried, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && strcmp(argv[1], "--noise-table") == 0) return noise_table_mode(argc, argv);
+    if (argc >= 2 && strcmp(argv[1], "--percent-f") == 0) return percent_f_mode(argc, argv);
     if (argc < 3) { fprintf(stderr, "usage: parse_bench panel.bed aseq_dir [repeat]\n"); return 2; }
     Panel panel;
     int n_amp = 0;

@@ -31,6 +31,10 @@
 #include <unordered_map>
 #include <vector>
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
+
 #include "../../include/amplisolve_b200.h"
 #include "as_factorials.h"
 #include "as_wire.h"
@@ -425,6 +429,90 @@ inline bool parse_row_fast(const char*& p, AseqRow& r) {
     return true;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#define AS_ROW_AVX2 1
+__attribute__((target("avx2,bmi,bmi2"))) static inline uint64_t mask64(__m256i lo, __m256i hi) {
+    return (uint64_t)(uint32_t)_mm256_movemask_epi8(lo) | ((uint64_t)(uint32_t)_mm256_movemask_epi8(hi) << 32);
+}
+// four numbers of up to eight digits: lane k holds the eight bytes that END where number k ends, keep = the mask of its own
+// digits (the leading bytes belong to the field before).  Digit values -> pairs -> fours -> the number, in 64-bit lanes.
+__attribute__((target("avx2,bmi,bmi2"))) static inline __m256i digits8x4(__m256i text, __m256i keep) {
+    const __m256i d = _mm256_and_si256(_mm256_sub_epi8(text, _mm256_set1_epi8('0')), keep);
+    const __m256i pairs = _mm256_maddubs_epi16(d, _mm256_set1_epi16(0x010A));           // byte0 * 10 + byte1
+    const __m256i fours = _mm256_madd_epi16(pairs, _mm256_set1_epi32(0x00010064));     // pair0 * 100 + pair1
+    return _mm256_add_epi64(_mm256_mul_epu32(fours, _mm256_set1_epi64x(10000)), _mm256_srli_epi64(fours, 32));
+}
+__attribute__((target("avx2,bmi,bmi2"))) static inline __m256i load8x4(const char* a, const char* b, const char* c, const char* d) {
+    long long w0, w1, w2, w3;
+    memcpy(&w0, a - 8, 8); memcpy(&w1, b - 8, 8); memcpy(&w2, c - 8, 8); memcpy(&w3, d - 8, 8);
+    return _mm256_set_epi64x(w3, w2, w1, w0);
+}
+
+// The rows parse_row_fast takes, without a branch per byte: one 64-byte window gives the bit masks of tabs, the newline,
+// digits and white space; the 14 tabs delimit the fields, the masks prove the shape (no empty field, digits where numbers
+// are, nothing else below '!'), and the ten numbers are converted four at a time in vector lanes.  Returns false -- p
+// untouched -- for anything it is not sure about (a row of more than 63 bytes, a count of more than 8 digits, a position of
+// more than 16): the scalar scanner and then the general parser decide.  Needs 16 readable bytes before p and 64 from p on.
+__attribute__((target("avx2,bmi,bmi2"), noinline)) bool parse_row_avx2(const char*& p, AseqRow& r) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)p), b = _mm256_loadu_si256((const __m256i*)(p + 32));
+    const __m256i nl = _mm256_set1_epi8('\n'), tab = _mm256_set1_epi8('\t'), zero = _mm256_set1_epi8('0');
+    const __m256i nine = _mm256_set1_epi8(9), space = _mm256_set1_epi8(' ');
+    const uint64_t nlm = mask64(_mm256_cmpeq_epi8(a, nl), _mm256_cmpeq_epi8(b, nl));
+    if (nlm == 0) return false;
+    const unsigned n = (unsigned)__builtin_ctzll(nlm);  // the row is bytes [0, n)
+    const uint64_t row = _bzhi_u64(~0ull, n);
+    const uint64_t tm = mask64(_mm256_cmpeq_epi8(a, tab), _mm256_cmpeq_epi8(b, tab)) & row;
+    const __m256i da = _mm256_sub_epi8(a, zero), db = _mm256_sub_epi8(b, zero);
+    const uint64_t dm = mask64(_mm256_cmpeq_epi8(_mm256_min_epu8(da, nine), da), _mm256_cmpeq_epi8(_mm256_min_epu8(db, nine), db));
+    const uint64_t wm = mask64(_mm256_cmpeq_epi8(_mm256_min_epu8(a, space), a), _mm256_cmpeq_epi8(_mm256_min_epu8(b, space), b)) & row;
+    unsigned end = n;
+    if (wm != tm) {  // the only other byte <= ' ' a row may hold is a '\r' before the newline
+        if (n == 0 || p[n - 1] != '\r' || wm != (tm | (1ull << (n - 1)))) return false;
+        end = n - 1;
+    }
+    if (__builtin_popcountll(tm) != 14 || (tm & (tm >> 1)) != 0 || (tm & 1) != 0) return false;
+    alignas(32) uint32_t t[16];
+    uint64_t x = tm;
+#pragma GCC unroll 14
+    for (int k = 0; k < 14; ++k) { t[k] = (unsigned)__builtin_ctzll(x); x = _blsr_u64(x); }
+    t[14] = end;
+    t[15] = end;
+    if (t[13] + 1 >= end) return false;
+    // digits: the position field and everything from the sixth tab to the end, tabs aside
+    const uint64_t counts_at = _bzhi_u64(~0ull, end) & ~_bzhi_u64(~0ull, t[5]) & ~tm;
+    const uint64_t numbers = counts_at | (_bzhi_u64(~0ull, t[1]) & ~_bzhi_u64(~0ull, t[0] + 1));
+    if ((numbers & ~dm) != 0) return false;
+    uint64_t run = counts_at;  // a count of nine digits or more: a run of nine set bits
+    run &= run >> 1;
+    run &= run >> 2;
+    run &= run >> 4;
+    run &= run >> 1;
+    const unsigned lp = t[1] - t[0] - 1;
+    if (run != 0 || lp > 16) return false;
+    // lengths of the count fields 6..13 -> the masks of their digits inside the 8-byte windows
+    const __m256i len8 = _mm256_sub_epi32(_mm256_sub_epi32(_mm256_loadu_si256((const __m256i*)(t + 6)), _mm256_loadu_si256((const __m256i*)(t + 5))),
+                                          _mm256_set1_epi32(1));
+    const __m256i ones = _mm256_set1_epi64x(-1), c64 = _mm256_set1_epi64x(64);
+    const __m256i sh_a = _mm256_sub_epi64(c64, _mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_castsi256_si128(len8)), 3));
+    const __m256i sh_b = _mm256_sub_epi64(c64, _mm256_slli_epi64(_mm256_cvtepu32_epi64(_mm256_extracti128_si256(len8, 1)), 3));
+    const unsigned lp_lo = lp < 8 ? lp : 8, lp_hi = lp - lp_lo;
+    const __m256i sh_c = _mm256_sub_epi64(c64, _mm256_slli_epi64(_mm256_set_epi64x(0, lp_hi, lp_lo, end - t[13] - 1), 3));
+    const __m256i va = digits8x4(load8x4(p + t[6], p + t[7], p + t[8], p + t[9]), _mm256_sllv_epi64(ones, sh_a));
+    const __m256i vb = digits8x4(load8x4(p + t[10], p + t[11], p + t[12], p + t[13]), _mm256_sllv_epi64(ones, sh_b));
+    const __m256i vc = digits8x4(load8x4(p + end, p + t[1], p + t[1] - 8, p + t[1]), _mm256_sllv_epi64(ones, sh_c));
+    _mm256_storeu_si256((__m256i*)(r.v), va);
+    _mm256_storeu_si256((__m256i*)(r.v + 4), vb);
+    alignas(32) long long last[4];
+    _mm256_store_si256((__m256i*)last, vc);
+    r.v[8] = last[0];
+    r.pos = last[2] * 100000000ll + last[1];
+    r.chrom = p;
+    r.chrom_len = t[0];
+    p += n + 1;
+    return true;
+}
+#endif
+
 // Any row the reference's sscanf accepts (whitespace-separated, signs allowed).  Returns 0 = blank line, 1 = parsed,
 // -1 = a first token but not 15 fields.  p moves past the line either way.
 inline int parse_row_general(const char*& p, const char* e, AseqRow& r) {
@@ -473,7 +561,17 @@ void parse_aseq(const MappedFile& file, const Panel& panel, typename Wire<FMT>::
             if (x.k < 0 && x.slot == (int32_t)c) return true;
         return false;
     };
+#ifdef AS_ROW_AVX2
+    static const bool avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi") && __builtin_cpu_supports("bmi2") &&
+                             !(getenv("AS_ROW_SCAN") && strcmp(getenv("AS_ROW_SCAN"), "scalar") == 0);  // the tests run both scanners
+    const char* const simd_begin = file.p + 16;
+#endif
     while (p < e) {
+#ifdef AS_ROW_AVX2
+        if (avx2 && p < fast_end && p >= simd_begin && parse_row_avx2(p, r)) {
+            ++st.rows;
+        } else
+#endif
         if (!(p < fast_end && parse_row_fast(p, r))) {
             const int got = parse_row_general(p, e, r);
             if (got == 0) continue;

@@ -71,7 +71,64 @@ static int percent_f_mode(int argc, char** argv) {
     return bad ? 1 : 0;
 }
 
+// parse_bench --row-scan n seed: n random ASEQ rows -- positions up to 2^31, counts of 1..10 digits, chromosome names of
+// 1..24 characters, "\r\n" ends, tokens in the four unused columns -- through the vector scanner, the byte-wise scanner and
+// the general parser: whenever a faster one accepts a row it must give the fields of the general one and stop at the same byte.
+static int row_scan_mode(int argc, char** argv) {
+    if (argc < 4) return 2;
+    const long n = atol(argv[2]);
+    uint64_t x = strtoull(argv[3], nullptr, 0) * 2654435761ull + 88172645463325252ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    std::string text(32, '#');  // the scanners may look at the bytes before a row
+    text.back() = '\n';
+    std::vector<size_t> starts;
+    for (long i = 0; i < n; ++i) {
+        starts.push_back(text.size());
+        const int cl = 1 + (int)(rnd() % ((rnd() & 7) ? 5 : 24));
+        for (int k = 0; k < cl; ++k) text.push_back((char)('A' + rnd() % 26));
+        const int pd = 1 + (int)(rnd() % 10);
+        text.push_back('\t');
+        text += std::to_string(rnd() % (uint64_t)std::min(2147483647.0, pow(10.0, pd)));
+        if (rnd() & 3) text += "\t.\t.\t.\t.";
+        else for (int k = 0; k < 4; ++k) { text.push_back('\t'); for (int c = 1 + (int)(rnd() % 3); c > 0; --c) text.push_back((char)('!' + rnd() % 90)); }
+        for (int k = 0; k < 9; ++k) {
+            const int d = (rnd() & 15) ? 1 + (int)(rnd() % 5) : 1 + (int)(rnd() % 10);
+            text.push_back('\t');
+            text += std::to_string(rnd() % (uint64_t)pow(10.0, d));
+        }
+        if ((rnd() & 15) == 0) text.push_back('\r');
+        text.push_back('\n');
+    }
+    text.append(512, '\n');
+    long long avx_taken = 0, fast_taken = 0, bad = 0;
+    for (size_t s0 : starts) {
+        const char* e = text.data() + text.size();
+        const char* pg = text.data() + s0;
+        AseqRow g, f, v;
+        const int got = parse_row_general(pg, e, g);
+        const char* pf = text.data() + s0;
+        const bool okf = parse_row_fast(pf, f);
+        auto same = [&](const AseqRow& a, const char* pa) {
+            bool eq = pa == pg && a.chrom == g.chrom && a.chrom_len == g.chrom_len && a.pos == g.pos;
+            for (int k = 0; k < 9; ++k) eq = eq && a.v[k] == g.v[k];
+            return eq;
+        };
+        if (okf) { ++fast_taken; if (got != 1 || !same(f, pf)) ++bad; }
+#ifdef AS_ROW_AVX2
+        if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) {
+            const char* pv = text.data() + s0;
+            const bool okv = parse_row_avx2(pv, v);
+            if (okv) { ++avx_taken; if (got != 1 || !same(v, pv)) ++bad; }
+            else if (pv != text.data() + s0) ++bad;
+        }
+#endif
+    }
+    printf("{\"rows\": %ld, \"vector_scanner_took\": %lld, \"bytewise_scanner_took\": %lld, \"differences\": %lld}\n", n, avx_taken, fast_taken, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "--row-scan") == 0) return row_scan_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--noise-table") == 0) return noise_table_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--percent-f") == 0) return percent_f_mode(argc, argv);
     if (argc < 3) { fprintf(stderr, "usage: parse_bench panel.bed aseq_dir [repeat]\n"); return 2; }

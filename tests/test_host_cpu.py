@@ -2,6 +2,7 @@
 declares, the parts of the two programs that need no GPU (usage text, default-error mode, hash order) behave
 like the reference, and compute entry points fail loudly without a GPU."""
 import re
+import os
 import subprocess
 from pathlib import Path
 
@@ -278,6 +279,9 @@ def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
     P = len(slots)
     counts, _ = synth.make_counts(5, P, depth=3000, seed=9, pos_id=pos_id)
     counts[1, 0, 3, :] = [70000, 1, 0, 2]            # escapes the packed format
+    counts[2, 1, 5, :] = [123456789, 0, 17, 2]       # nine digits: beyond the vector scanner's eight
+    counts[3, 0, 7, :] = [99999999, 3, 0, 0]         # eight digits
+    counts[3, 1, 7, :] = [0, 0, 0, 0]
     (tmp_path / "panel.bed").write_text("".join(f"{c}\t{s}\t{e}\tA{i}\n" for i, (c, s, e) in enumerate(bed)))
 
     def variant(name, transform):
@@ -288,10 +292,15 @@ def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
             text = (d / f"S{i}.PILEUP.ASEQ").read_text()
             head, rows = text.split("\n", 1)
             (d / f"S{i}.PILEUP.ASEQ").write_text(head + "\n" + transform(rows))
-        out = subprocess.run([str(exe), str(tmp_path / "panel.bed"), str(d), "1"], capture_output=True, text=True)
-        assert out.returncode == 0, out.stderr
-        res = json.loads(out.stdout)
-        return res["checksum"], res["rows"], res["escaped"], res["outside"]
+        got = []
+        for scan in ("scalar", "avx2"):  # the byte-wise row scanner and the vector one (taken when the CPU has AVX2)
+            out = subprocess.run([str(exe), str(tmp_path / "panel.bed"), str(d), "1"], capture_output=True, text=True,
+                                 env=dict(os.environ, AS_ROW_SCAN=scan))
+            assert out.returncode == 0, out.stderr
+            res = json.loads(out.stdout)
+            got.append((res["checksum"], res["rows"], res["escaped"], res["outside"]))
+        assert got[0] == got[1], (name, got)
+        return got[0]
 
     base = variant("tabs", lambda t: t)
     assert base[1] == int((counts[:, 0, :, 0] != 0xFFFFFFFF).sum()) and base[2] >= 1 and base[3] == 0
@@ -389,3 +398,16 @@ def test_noise_table_writer_percent_f_equals_printf(tmp_path):
         out = subprocess.run([str(exe), "--percent-f", hex(first), hex(last), str(stride)], capture_output=True, text=True)
         res = json.loads(out.stdout)
         assert out.returncode == 0 and res["differences"] == 0 and res["tried"] > 50000, res
+
+
+def test_row_scanners_agree_with_the_general_parser_on_random_rows(tmp_path):
+    """as_host.cpp has three readers of an ASEQ row (EE:1149, VC:752): the vector scanner (AVX2: bit masks of one 64-byte
+    window, ten numbers converted in vector lanes), the byte-wise scanner and the general sscanf-like parser.  A faster one
+    may decline a row, never read it differently: random rows with positions up to 2^31, counts of up to ten digits, long
+    chromosome names, CRLF ends and tokens in the unused columns."""
+    import json
+    exe = _build_parse_bench(tmp_path)
+    out = subprocess.run([str(exe), "--row-scan", "300000", "11"], capture_output=True, text=True)
+    res = json.loads(out.stdout)
+    assert out.returncode == 0 and res["differences"] == 0, res
+    assert res["bytewise_scanner_took"] > 250000, res

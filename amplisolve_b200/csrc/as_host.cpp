@@ -25,6 +25,7 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -736,17 +737,68 @@ void parallel_for(size_t n, F body) {
 // (8 bytes per record); when more than 1 record in 16 would have to be escaped (ultra-deep or very noisy data) the group is
 // parsed again into the 16-bit format, and later groups go straight there.  Escaped records are in `wide`, sorted by
 // (slot, sample).  AS_WIRE=16 / AS_WIRE=packed in the environment forces one of the two.
+// Pinned buffers of finished programs, kept by the resident service for the next one (pinning memory costs about a
+// millisecond per 4 MB: more than the GPU step of a configs[1] job).  At most four buffers and 4 GB stay parked.
+struct PinnedPool {
+    std::mutex m;
+    std::vector<std::pair<void*, size_t>> free_list;
+    void* take(size_t n, size_t& got) {  // the smallest parked buffer of at least n bytes
+        std::lock_guard<std::mutex> g(m);
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].second >= n && (best == free_list.size() || free_list[i].second < free_list[best].second)) best = i;
+        if (best == free_list.size()) return nullptr;
+        void* p = free_list[best].first;
+        got = free_list[best].second;
+        free_list.erase(free_list.begin() + (long)best);
+        return p;
+    }
+    void give(void* p, size_t n) {
+        void* drop = nullptr;
+        {
+            std::lock_guard<std::mutex> g(m);
+            size_t total = n;
+            for (const auto& f : free_list) total += f.second;
+            if (n > (size_t)4 << 30) {
+                drop = p;
+            } else {
+                free_list.emplace_back(p, n);
+                while (free_list.size() > 4 || total > (size_t)4 << 30) {  // the oldest goes
+                    total -= free_list.front().second;
+                    if (drop) as_host_free(drop);
+                    drop = free_list.front().first;
+                    free_list.erase(free_list.begin());
+                }
+            }
+        }
+        if (drop) as_host_free(drop);
+    }
+};
+PinnedPool g_pinned_pool;
+
 struct HostCounts {
     void* p = nullptr;
     size_t bytes = 0;
     int fmt = 1;  // 1 packed, 2 uint16
     std::vector<as_wide_record> wide;
-    ~HostCounts() { if (p) as_host_free(p); }
+    void release() {
+        if (p) {
+            if (as_process_is_resident()) g_pinned_pool.give(p, bytes);
+            else as_host_free(p);
+        }
+        p = nullptr;
+        bytes = 0;
+    }
+    ~HostCounts() { release(); }
     bool reserve(size_t n) {
         if (n <= bytes) return true;
-        if (p) as_host_free(p);
-        p = nullptr; bytes = 0;
-        if (as_host_alloc(&p, std::max<size_t>(16, n)) != AS_OK) { p = nullptr; return false; }
+        release();
+        n = std::max<size_t>(16, n);
+        if (as_process_is_resident()) {
+            size_t got = 0;
+            if (void* q = g_pinned_pool.take(n, got)) { p = q; bytes = got; return true; }
+        }
+        if (as_host_alloc(&p, n) != AS_OK) { p = nullptr; return false; }
         bytes = n;
         return true;
     }
@@ -896,7 +948,18 @@ double aseq_dir_records(const std::string& dir) {
     return bytes / 45.0;
 }
 
+// In the resident service (as_serve.cpp: one request at a time) the context object of a finished program is parked, not
+// destroyed: the next program that asks for the same devices takes it over with its streams, events and grow-only device
+// and pinned buffers (re-allocating them cost 8 ms of a 0.2 s configs[1] job and 45 ms of a 0.5 s configs[2] slice).
+struct ParkedContext {
+    std::mutex m;
+    as_ctx* ctx = nullptr;
+    std::vector<int> devs;
+};
+ParkedContext g_parked;
+
 struct GpuContext {
+    std::vector<int> made_for;  // device list the context was created for (empty: every visible GPU)
     as_ctx* ctx = nullptr;
     int rc = AS_OK;
     std::string error;
@@ -922,6 +985,15 @@ struct GpuContext {
             setenv("CUDA_VISIBLE_DEVICES", list.c_str(), 1);
             for (size_t i = 0; i < devs.size(); ++i) devs[i] = (int)i;
         }
+        made_for = devs;
+        if (as_process_is_resident() && getenv("AS_DEFER_CHUNKS") == nullptr) {  // (that knob is read when a context is created)
+            std::lock_guard<std::mutex> g(g_parked.m);
+            if (g_parked.ctx && g_parked.devs == devs) {
+                ctx = g_parked.ctx;
+                g_parked.ctx = nullptr;
+                return;
+            }
+        }
         starter = std::thread([this, devs]() mutable {
             if (devs.empty()) {  // a large job: every visible GPU
                 int n = 0;
@@ -941,7 +1013,16 @@ struct GpuContext {
     // through _exit and the driver reclaims everything at once.  An error path that returns early still joins the thread.
     ~GpuContext() {
         if (starter.joinable()) starter.join();
-        if (ctx && as_process_is_resident()) as_destroy(ctx);  // the service lives on: give the memory back
+        if (ctx && as_process_is_resident()) {  // the service lives on: keep one context for the next program, free any other
+            as_ctx* old = nullptr;
+            {
+                std::lock_guard<std::mutex> g(g_parked.m);
+                old = g_parked.ctx;
+                g_parked.ctx = ctx;
+                g_parked.devs = made_for;
+            }
+            if (old) as_destroy(old);
+        }
     }
 };
 

@@ -1332,13 +1332,30 @@ int as_error_estimation_main(int argc, char** argv) {
     for (int64_t i = 0; i < P; ++i)
         if (panel.twin_next[i] >= 0 || panel.twin_head[i] != (int32_t)i) panel.dup[i] = 1;
     {
+        // the two intermediate lists, formatted into one string each (an ostream insertion per field was a third of this phase)
+        std::string text;
+        text.reserve((size_t)P * 24);
+        char num[16];
+        for (int64_t i = 0; i < P; ++i) {
+            text += panel.chroms[panel.slot_chrom[i]];
+            text += '\t';
+            text.append(num, (size_t)snprintf(num, sizeof num, "%d", panel.slot_pos[i]));
+            text += '\t';
+            text += panel.ref[i];
+            text += '\n';
+        }
         std::ofstream refs((stem + "_panelReferenceBases.txt").c_str());
+        refs.write(text.data(), (std::streamsize)text.size());
+        text.clear();
         for (int64_t i = 0; i < P; ++i)
-            refs << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\t" << panel.ref[i] << "\n";
+            if (panel.dup[i] && panel.twin_head[i] == (int32_t)i) {
+                text += panel.chroms[panel.slot_chrom[i]];
+                text += '\t';
+                text.append(num, (size_t)snprintf(num, sizeof num, "%d", panel.slot_pos[i]));
+                text += '\n';
+            }
         std::ofstream dups((stem + "_ampliconDuplicatedPositions.txt").c_str());
-        for (int64_t i = 0; i < P; ++i)
-            if (panel.dup[i] && panel.twin_head[i] == (int32_t)i)
-                dups << panel.chroms[panel.slot_chrom[i]] << "\t" << panel.slot_pos[i] << "\n";
+        dups.write(text.data(), (std::streamsize)text.size());
     }
     std::cout << "Reference bases and amplicon duplicated positions have generated" << "\n\t\t --> Parsed in total " << n_amplicons
               << " amplicons and annotated " << P << " positions." << std::endl;

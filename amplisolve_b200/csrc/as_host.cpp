@@ -15,6 +15,7 @@
 #include <atomic>
 #include <clocale>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -693,6 +694,80 @@ AseqStats load_aseq(const std::string& path, const Panel& panel, typename Wire<F
     return st;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Host threads that stay.  Every parallel phase of the programs (parsing files, the noise table in and out, the call
+// writers) used to start hardware_concurrency threads of its own and join them: about a millisecond per phase on a
+// 32-thread host, eight phases in a 70 ms job.  The pool's workers are created once (by the first phase; the resident
+// service keeps them between programs) and sleep on a condition variable in between.  One phase runs at a time; a phase
+// that finds the pool busy (the GPU worker thread of the caller program beside the main thread's parser) starts threads
+// of its own as before.  The work functions share their items through atomics of their own, so it does not matter which
+// or how many threads arrive.
+// ---------------------------------------------------------------------------------------------------
+class HostPool {
+  public:
+    static HostPool& get() {
+        static HostPool* pool = new HostPool();  // never destroyed: the programs leave through _exit, the service stays
+        return *pool;
+    }
+    // work() on n_threads threads, the caller's included; false (nothing done) when another phase holds the pool
+    bool run(unsigned n_threads, const std::function<void()>& work) {
+        std::unique_lock<std::mutex> phase(phase_m_, std::try_to_lock);
+        if (!phase.owns_lock()) return false;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            job_ = &work;
+            wanted_ = std::min<unsigned>(n_threads - 1, (unsigned)th_.size());
+            taken_ = 0;
+            pending_ = (unsigned)th_.size();
+            ++gen_;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> g(m_);
+        done_cv_.wait(g, [this]() { return pending_ == 0; });
+        job_ = nullptr;
+        return true;
+    }
+
+  private:
+    HostPool() {
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        for (unsigned t = 1; t < hw; ++t) th_.emplace_back([this]() { loop(); });
+        for (auto& t : th_) t.detach();
+    }
+    void loop() {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void()>* f = nullptr;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&]() { return gen_ != seen; });
+                seen = gen_;
+                if (taken_ < wanted_) { ++taken_; f = job_; }
+            }
+            if (f) (*f)();
+            {
+                std::lock_guard<std::mutex> g(m_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    std::mutex phase_m_, m_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> th_;
+    const std::function<void()>* job_ = nullptr;
+    unsigned wanted_ = 0, taken_ = 0, pending_ = 0, gen_ = 0;
+};
+
+void run_on_threads(unsigned n_threads, const std::function<void()>& work) {
+    if (n_threads <= 1) { work(); return; }
+    if (HostPool::get().run(n_threads, work)) return;
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < n_threads; ++t) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+}
+
 // samples [first, first + n) of `files` into one tensor [n][2][P][PER]; sample ids in the wide records are 0..n-1
 template <int FMT>
 bool load_all(const std::vector<CountFile>& files, size_t first, size_t n, const Panel& panel, typename Wire<FMT>::E* counts,
@@ -706,11 +781,7 @@ bool load_all(const std::vector<CountFile>& files, size_t first, size_t n, const
         for (size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
             stats[i] = load_aseq<FMT>(files[first + i].path, panel, counts + (int64_t)i * 2 * P * PER, (int32_t)i, rd_rows_aside);
     };
-    const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max<size_t>(1, n)));
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+    run_on_threads(std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max<size_t>(1, n))), work);
     for (const AseqStats& s : stats)
         if (!s.ok) return false;
     return true;
@@ -725,11 +796,7 @@ void parallel_for(size_t n, F body) {
         for (size_t b = next.fetch_add(grain); b < n; b = next.fetch_add(grain))
             for (size_t i = b; i < std::min(n, b + grain); ++i) body(i);
     };
-    const unsigned hw = (unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), (n + grain - 1) / grain));
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+    run_on_threads((unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), (n + grain - 1) / grain)), work);
 }
 
 // The count tensor of a group of samples in a wire format (a quarter / half of the pinned memory and PCIe traffic of
@@ -1493,11 +1560,7 @@ int as_error_estimation_main(int argc, char** argv) {
                     }
                 }
             };
-            const unsigned hw = (unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), wn));
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < hw; ++t) th.emplace_back(work);
-            work();
-            for (auto& t : th) t.join();
+            run_on_threads((unsigned)std::max<size_t>(1, std::min<size_t>(std::thread::hardware_concurrency(), wn)), work);
             for (size_t k = 0; k < wn; ++k) output.write(text[k].data(), (std::streamsize)text[k].size());
         }
     }
@@ -1545,10 +1608,10 @@ void parse_noise_table(const std::string& text, int force_pieces, Panel& panel, 
     };
     std::vector<Piece> pieces(n_piece);
     auto run_pieces = [&](const std::function<void(unsigned)>& f) {
-        std::vector<std::thread> th;
-        for (unsigned k = 1; k < n_piece; ++k) th.emplace_back(f, k);
-        f(0);
-        for (auto& t : th) t.join();
+        std::atomic<unsigned> next(0);
+        run_on_threads(n_piece, [&]() {
+            for (unsigned k = next.fetch_add(1); k < n_piece; k = next.fetch_add(1)) f(k);
+        });
     };
     run_pieces([&](unsigned k) {
         Piece& pc = pieces[k];
@@ -2082,11 +2145,7 @@ int as_variant_calling_main(int argc, char** argv) {
         auto work = [&]() {
             for (int t = next.fetch_add(1); t < T; t = next.fetch_add(1)) write_tumour(t);
         };
-        const unsigned hw = std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, T)));
-        std::vector<std::thread> th;
-        for (unsigned k = 1; k < hw; ++k) th.emplace_back(work);
-        work();
-        for (auto& x : th) x.join();
+        run_on_threads(std::max(1u, std::min(std::thread::hardware_concurrency(), (unsigned)std::max(1, T))), work);
     }
     for (int t = 0; t < T; ++t) {
         if ((t + 1) % 50 == 0)

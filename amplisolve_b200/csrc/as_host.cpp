@@ -360,6 +360,46 @@ inline void append_percent_f(std::string& o, float v) {
     o.append(q, (size_t)(e - q));
 }
 
+// "%g" of a float Germ_Max value (the reference's ostream << double, EE:2815) for 1e-4 <= v < 1: six significant digits in
+// fixed notation, trailing zeros removed.  Exact: v = m * 2^-s with m < 2^24, and m * 10^D < 2^54 for the D <= 9 decimals
+// needed, so the round-half-even of v * 10^D is integer arithmetic (equal to snprintf on every float of [1e-4, 1):
+// scripts/parse_bench.cpp --percent-g).  Returns false -- nothing appended -- for any other value: the caller uses snprintf.
+inline bool append_percent_g(std::string& o, float v) {
+    if (!(v >= 1e-4f && v < 1.0f)) return false;
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    const uint64_t m = (bits & 0x7FFFFFu) | 0x800000u;  // a normal number
+    const int s = 150 - (int)(bits >> 23);               // v = m * 2^-s, 24 <= s <= 37
+    static const uint64_t p10[10] = {1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull};
+    int D = v >= 0.1f ? 6 : v >= 0.01f ? 7 : v >= 0.001f ? 8 : 9;  // decimals of six significant digits
+    uint64_t n;
+    for (;;) {
+        const uint64_t N = m * p10[D];
+        const uint64_t half = 1ull << (s - 1), rem = N & ((half << 1) - 1);
+        n = N >> s;
+        n += (rem > half || (rem == half && (n & 1))) ? 1 : 0;
+        if (n < 100000ull && D < 9) { ++D; continue; }  // the float constant sat on the other side of the decimal boundary
+        break;
+    }
+    if (n < 100000ull) return false;
+    if (n >= 1000000ull) {  // rounded up into the next decade: 1.00000 x 10^(X+1)
+        n = 100000ull;
+        if (--D < 6) return false;
+    }
+    char buf[16];
+    int len = 0;
+    buf[len++] = '0';
+    buf[len++] = '.';
+    for (int z = 6; z < D; ++z) buf[len++] = '0';
+    char dig[6];
+    for (int k = 5; k >= 0; --k) { dig[k] = (char)('0' + n % 10); n /= 10; }
+    int last = 5;
+    while (last > 0 && dig[last] == '0') --last;
+    for (int k = 0; k <= last; ++k) buf[len++] = dig[k];
+    o.append(buf, (size_t)len);
+    return true;
+}
+
 struct MappedFile {  // read-only view of a whole file
     const char* p = nullptr;
     size_t n = 0;
@@ -1551,9 +1591,15 @@ int as_error_estimation_main(int argc, char** argv) {
                         for (int b = 0; b < 4; ++b) {
                             if (germ_state[(size_t)i * 4 + b] == 0) {
                                 o += "\t-";  // EE:2807-2849
-                            } else {
-                                snprintf(cell, sizeof cell, "\t%g", (double)germ_val[(size_t)i * 4 + b]);  // ostream << double
-                                o += cell;
+                            } else {  // ostream << double
+                                o += '\t';
+                                const float g = germ_val[(size_t)i * 4 + b];
+                                if (g == 0.f && !std::signbit(g)) {
+                                    o += '0';
+                                } else if (!append_percent_g(o, g)) {
+                                    snprintf(cell, sizeof cell, "%g", (double)g);
+                                    o += cell;
+                                }
                             }
                         }
                         o += '\n';

@@ -127,7 +127,30 @@ static int row_scan_mode(int argc, char** argv) {
     return bad ? 1 : 0;
 }
 
+// parse_bench --percent-g first_bits last_bits stride: append_percent_g (the noise-table writer's Germ_Max cells) against snprintf
+// for the floats whose bit patterns are first, first + stride, ... <= last; values it declines count as `declined`.
+static int percent_g_mode(int argc, char** argv) {
+    if (argc < 5) return 2;
+    const uint64_t first = strtoull(argv[2], nullptr, 0), last = strtoull(argv[3], nullptr, 0), stride = std::max(1ull, strtoull(argv[4], nullptr, 0));
+    long long tried = 0, bad = 0, declined = 0;
+    std::string o;
+    char cell[64];
+    for (uint64_t u = first; u <= last; u += stride) {
+        const uint32_t w = (uint32_t)u;
+        float v;
+        memcpy(&v, &w, 4);
+        o.clear();
+        ++tried;
+        if (!append_percent_g(o, v)) { ++declined; if (!o.empty()) ++bad; continue; }
+        snprintf(cell, sizeof cell, "%g", (double)v);
+        if (o != cell) ++bad;
+    }
+    printf("{\"tried\": %lld, \"declined\": %lld, \"differences\": %lld}\n", tried, declined, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "--percent-g") == 0) return percent_g_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--row-scan") == 0) return row_scan_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--noise-table") == 0) return noise_table_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--percent-f") == 0) return percent_f_mode(argc, argv);

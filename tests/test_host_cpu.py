@@ -411,3 +411,27 @@ def test_row_scanners_agree_with_the_general_parser_on_random_rows(tmp_path):
     res = json.loads(out.stdout)
     assert out.returncode == 0 and res["differences"] == 0, res
     assert res["bytewise_scanner_took"] > 250000, res
+
+
+def test_noise_table_writer_percent_g_equals_printf(tmp_path):
+    """The Germ_Max cells of the noise table are ostream << double = "%g" (EE:2815); the writer formats the values of
+    [1e-4, 1) itself, exactly (integer round-half-even of m * 10^D / 2^s: as_host.cpp append_percent_g), and leaves the rest to
+    snprintf.  Against snprintf: the whole range with a stride, every float around the decade boundaries 1e-4, 1e-3, 1e-2,
+    1e-1 and 1 (where the number of decimals changes and 9.999995 rounds into the next decade), and values it must decline."""
+    import json
+    import struct
+    exe = _build_parse_bench(tmp_path)
+
+    def bits(x):
+        return struct.unpack("<I", struct.pack("<f", x))[0]
+
+    out = subprocess.run([str(exe), "--percent-g", hex(bits(1e-4) - 5000), hex(bits(1.0) + 5000), "613"], capture_output=True, text=True)
+    res = json.loads(out.stdout)
+    assert out.returncode == 0 and res["differences"] == 0 and res["tried"] - res["declined"] > 150000, res
+    for edge in (1e-4, 1e-3, 1e-2, 1e-1, 1.0, 0.05, 0.0123455, 0.00999995):
+        out = subprocess.run([str(exe), "--percent-g", hex(bits(edge) - 20000), hex(bits(edge) + 20000), "1"], capture_output=True, text=True)
+        res = json.loads(out.stdout)
+        assert out.returncode == 0 and res["differences"] == 0, (edge, res)
+    out = subprocess.run([str(exe), "--percent-g", hex(bits(-888.0) - 50), hex(bits(-888.0) + 50), "1"], capture_output=True, text=True)
+    res = json.loads(out.stdout)
+    assert out.returncode == 0 and res["declined"] == res["tried"], res

@@ -149,7 +149,32 @@ static int percent_g_mode(int argc, char** argv) {
     return bad ? 1 : 0;
 }
 
+// parse_bench --pool-stress rounds: three threads start parallel phases at the same time (run_on_threads: the pool when it is
+// free, threads of their own when it is not); every phase must run each of its items exactly once and return.
+static int pool_stress_mode(int argc, char** argv) {
+    const int rounds = argc > 2 ? atoi(argv[2]) : 5000;
+    std::atomic<long long> total{0};
+    std::atomic<int> bad{0};
+    auto user = [&](int id) {
+        for (int r = 0; r < rounds; ++r) {
+            const unsigned n = 1 + (unsigned)((r * 7 + id) % 12), items = (unsigned)(r % 50) + 1;
+            std::atomic<unsigned> next{0};
+            std::atomic<long long> sum{0};
+            run_on_threads(n, [&]() {
+                for (unsigned k = next.fetch_add(1); k < items; k = next.fetch_add(1)) sum += k + 1;
+            });
+            if (sum != (long long)items * (items + 1) / 2) ++bad;
+            total += sum;
+        }
+    };
+    std::thread a(user, 0), b(user, 1), c(user, 2);
+    a.join(); b.join(); c.join();
+    printf("{\"phases\": %d, \"items\": %lld, \"bad\": %d}\n", 3 * rounds, (long long)total, (int)bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "--pool-stress") == 0) return pool_stress_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--percent-g") == 0) return percent_g_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--row-scan") == 0) return row_scan_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--noise-table") == 0) return noise_table_mode(argc, argv);

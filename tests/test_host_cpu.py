@@ -435,3 +435,14 @@ def test_noise_table_writer_percent_g_equals_printf(tmp_path):
     out = subprocess.run([str(exe), "--percent-g", hex(bits(-888.0) - 50), hex(bits(-888.0) + 50), "1"], capture_output=True, text=True)
     res = json.loads(out.stdout)
     assert out.returncode == 0 and res["declined"] == res["tried"], res
+
+
+def test_host_thread_pool_under_concurrent_phases(tmp_path):
+    """as_host.cpp runs every parallel phase on one pool of host threads that stay (HostPool); a phase that finds the pool busy
+    starts threads of its own.  Three threads starting 15,000 phases between them: every item of every phase runs exactly once
+    and nothing hangs."""
+    import json
+    exe = _build_parse_bench(tmp_path)
+    out = subprocess.run([str(exe), "--pool-stress", "5000"], capture_output=True, text=True, timeout=300)
+    res = json.loads(out.stdout)
+    assert out.returncode == 0 and res["bad"] == 0 and res["phases"] == 15000, res

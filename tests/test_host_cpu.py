@@ -262,19 +262,9 @@ def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
     tabs, with CRLF line ends, with runs of blanks instead of tabs, with blank lines in between and with the rows in reverse
     order must give the same packed tensor (scripts/parse_bench.cpp: the loader alone, no GPU; checksum over all words)."""
     import json
-    import shutil
     import numpy as np
     from tests import synth
-    if shutil.which("g++") is None:
-        pytest.skip("no g++")
-    exe = tmp_path / "parse_bench"
-    lib_dir = ROOT / "amplisolve_b200" / "lib"
-    from amplisolve_b200 import lib
-    lib()
-    r = subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I", str(ROOT / "include"), str(ROOT / "scripts" / "parse_bench.cpp"),
-                        f"-L{lib_dir}", "-lamplisolve_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)],
-                       capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-2000:]
+    exe = _build_parse_bench(tmp_path)
     bed, slots, pos_id, U = synth.make_panel(30, seed=9)
     P = len(slots)
     counts, _ = synth.make_counts(5, P, depth=3000, seed=9, pos_id=pos_id)
@@ -311,11 +301,18 @@ def test_aseq_loader_fast_and_general_paths_agree(tmp_path):
     assert variant("no_final_newline", lambda t: t.rstrip("\n")) == base
 
 
+_PARSE_BENCH = []
+
+
 def _build_parse_bench(tmp_path):
+    """scripts/parse_bench.cpp (as_host.cpp's host logic behind a small command line), built once per test session."""
     import shutil
+    import tempfile
     if shutil.which("g++") is None:
         pytest.skip("no g++")
-    exe = tmp_path / "parse_bench"
+    if _PARSE_BENCH:
+        return _PARSE_BENCH[0]
+    exe = Path(tempfile.mkdtemp(prefix="as_parse_bench_")) / "parse_bench"
     lib_dir = ROOT / "amplisolve_b200" / "lib"
     from amplisolve_b200 import lib
     lib()
@@ -323,6 +320,7 @@ def _build_parse_bench(tmp_path):
                         f"-L{lib_dir}", "-lamplisolve_b200", f"-Wl,-rpath,{lib_dir}", "-Wl,-rpath,/usr/local/cuda/lib64", "-o", str(exe)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+    _PARSE_BENCH.append(exe)
     return exe
 
 

@@ -379,10 +379,16 @@ int as_thresholds_caller_view_dev(as_ctx* c, const float* d_thr, float* d_view, 
 
 // Slots per tile of the _host pipelines: ~256 MiB of host data per buffer (elem * 8 bytes per record: the denser the
 // host format, the more slots per tile and the fewer tiles), multiple of 1024 slots.
+#define AS_HOST_TILE_MB_DEFAULT 256
 static int64_t tile_slots(const as_ctx* c, int32_t n_samples, int64_t P, int elem) {
     if (c->host_tile_slots > 0) return std::min(c->host_tile_slots, std::max<int64_t>(P, 1));
     const int64_t per_slot = 8ll * elem * std::max(1, n_samples);
-    int64_t t = (256ll << 20) / per_slot;
+    static const int64_t tile_mb = []() {  // host bytes per upload tile; AS_HOST_TILE_MB overrides (measurements)
+        const char* env = getenv("AS_HOST_TILE_MB");
+        const long v = env ? atol(env) : 0;
+        return (int64_t)(v > 0 ? v : AS_HOST_TILE_MB_DEFAULT);
+    }();
+    int64_t t = (tile_mb << 20) / per_slot;
     t = std::max<int64_t>(1024, (t / 1024) * 1024);
     return std::min(t, std::max<int64_t>(P, 1));
 }

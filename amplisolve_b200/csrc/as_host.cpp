@@ -749,29 +749,33 @@ class HostPool {
         static HostPool* pool = new HostPool();  // never destroyed: the programs leave through _exit, the service stays
         return *pool;
     }
-    // work() on n_threads threads, the caller's included; false (nothing done) when another phase holds the pool
+    // work() on up to n_threads threads, the caller's included; false (nothing done) when another phase holds the pool.
+    // Only as many workers as the phase wants are woken; a worker that arrives after the caller has finished its own share
+    // finds the phase closed, so the caller never waits for a thread that has not started.
     bool run(unsigned n_threads, const std::function<void()>& work) {
         std::unique_lock<std::mutex> phase(phase_m_, std::try_to_lock);
         if (!phase.owns_lock()) return false;
+        unsigned wanted;
         {
             std::lock_guard<std::mutex> g(m_);
             job_ = &work;
-            wanted_ = std::min<unsigned>(n_threads - 1, (unsigned)th_.size());
+            wanted = wanted_ = std::min<unsigned>(n_threads - 1, (unsigned)th_.size());
             taken_ = 0;
-            pending_ = (unsigned)th_.size();
             ++gen_;
         }
-        cv_.notify_all();
+        if (wanted >= th_.size()) cv_.notify_all();
+        else for (unsigned k = 0; k < wanted; ++k) cv_.notify_one();
         work();
         std::unique_lock<std::mutex> g(m_);
-        done_cv_.wait(g, [this]() { return pending_ == 0; });
+        wanted_ = taken_;  // closed: no worker starts from here on
+        done_cv_.wait(g, [this]() { return running_ == 0; });
         job_ = nullptr;
         return true;
     }
 
   private:
     HostPool() {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        const unsigned hw = std::min(256u, std::max(1u, std::thread::hardware_concurrency()));
         for (unsigned t = 1; t < hw; ++t) th_.emplace_back([this]() { loop(); });
         for (auto& t : th_) t.detach();
     }
@@ -783,12 +787,13 @@ class HostPool {
                 std::unique_lock<std::mutex> g(m_);
                 cv_.wait(g, [&]() { return gen_ != seen; });
                 seen = gen_;
-                if (taken_ < wanted_) { ++taken_; f = job_; }
+                if (taken_ < wanted_) { ++taken_; ++running_; f = job_; }
             }
-            if (f) (*f)();
+            if (!f) continue;
+            (*f)();
             {
                 std::lock_guard<std::mutex> g(m_);
-                if (--pending_ == 0) done_cv_.notify_one();
+                if (--running_ == 0) done_cv_.notify_one();
             }
         }
     }
@@ -796,7 +801,7 @@ class HostPool {
     std::condition_variable cv_, done_cv_;
     std::vector<std::thread> th_;
     const std::function<void()>* job_ = nullptr;
-    unsigned wanted_ = 0, taken_ = 0, pending_ = 0, gen_ = 0;
+    unsigned wanted_ = 0, taken_ = 0, running_ = 0, gen_ = 0;
 };
 
 void run_on_threads(unsigned n_threads, const std::function<void()>& work) {

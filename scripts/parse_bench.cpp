@@ -173,7 +173,40 @@ static int pool_stress_mode(int argc, char** argv) {
     return bad ? 1 : 0;
 }
 
+// parse_bench --stof n seed: threshold_text_to_float (the noise-table parser's std::stof) against strtof: every "d.dddddd"
+// with a value below n / 10^6 (what "%f" writes), then n random texts [-]digits[.digits] of up to 10 digits, exponents and
+// words that must go to strtof.
+static int stof_mode(int argc, char** argv) {
+    if (argc < 4) return 2;
+    const long n = atol(argv[2]);
+    uint64_t x = strtoull(argv[3], nullptr, 0) * 2654435761ull + 88172645463325252ull;
+    auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    long long tried = 0, bad = 0;
+    char buf[64];
+    auto check = [&](const char* t, size_t len) {
+        const float a = threshold_text_to_float(t, t + len), b = len ? strtof(t, nullptr) : 0.f;
+        ++tried;
+        if (memcmp(&a, &b, 4) != 0) ++bad;
+    };
+    for (long k = 0; k < n; ++k) check(buf, (size_t)snprintf(buf, sizeof buf, "%ld.%06ld", k / 1000000, k % 1000000));
+    for (long k = 0; k < n; ++k) {
+        const int digits = 1 + (int)(rnd() % 10), frac = (int)(rnd() % (unsigned)(digits + 1));
+        std::string d = std::to_string(rnd() % (uint64_t)pow(10.0, digits));
+        d.insert(0, (size_t)digits - d.size(), '0');
+        std::string t = (rnd() & 1) ? "-" : "";
+        t.append(d, 0, (size_t)(digits - frac));
+        if (frac || (rnd() & 1)) t += ".";
+        t.append(d, (size_t)(digits - frac), std::string::npos);
+        if ((rnd() & 31) == 0) t += "e-0" + std::to_string(rnd() % 9);
+        check(t.c_str(), t.size());
+    }
+    for (const char* w : {"nan", "inf", "-inf", "", "-", "+3", ".", "1e5", "0x10", "-0", "-0.000000"}) check(w, strlen(w));
+    printf("{\"tried\": %lld, \"differences\": %lld}\n", tried, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc >= 2 && strcmp(argv[1], "--stof") == 0) return stof_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--pool-stress") == 0) return pool_stress_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--percent-g") == 0) return percent_g_mode(argc, argv);
     if (argc >= 2 && strcmp(argv[1], "--row-scan") == 0) return row_scan_mode(argc, argv);

@@ -444,3 +444,15 @@ def test_host_thread_pool_under_concurrent_phases(tmp_path):
     out = subprocess.run([str(exe), "--pool-stress", "5000"], capture_output=True, text=True, timeout=300)
     res = json.loads(out.stdout)
     assert out.returncode == 0 and res["bad"] == 0 and res["phases"] == 15000, res
+
+
+def test_noise_table_threshold_text_to_float_equals_strtof(tmp_path):
+    """The caller program reads a threshold cell through std::stof (VC:889-890); as_host.cpp converts texts of the form
+    [-]digits[.digits] with at most eight digits itself -- double(n) / 10^s narrowed to float is the correctly rounded float --
+    and leaves the rest to strtof.  Against strtof: every "%f" text below 2.0, and random texts incl. longer ones, exponents
+    and words."""
+    import json
+    exe = _build_parse_bench(tmp_path)
+    out = subprocess.run([str(exe), "--stof", "2000000", "5"], capture_output=True, text=True)
+    res = json.loads(out.stdout)
+    assert out.returncode == 0 and res["differences"] == 0 and res["tried"] > 4000000, res
